@@ -1,0 +1,207 @@
+/*
+ * sdpsr.h -- C ABI of libsdpsr_cuda.so: the B200-native engine behind
+ * SDPSymmetryReduction.jl's Jordan-reduction hot path.
+ *
+ * The reference (DanielBrosch/SDPSymmetryReduction.jl v0.2.1) is pure Julia and
+ * has no FFI; its only extension point is the AbstractPartition contract
+ * (src/abstract_part.jl:1-18).  This header is therefore NEW surface: each entry
+ * point names the reference code it replaces (file:line relative to the
+ * reference root) so that a `CuPartition <: AbstractPartition` Julia back-end can
+ * bind it with `ccall`.
+ *
+ * Conventions
+ *  - Every matrix is COLUMN-MAJOR (Julia), order N, linear index idx = i + N*j
+ *    (0-based); first-occurrence order == ascending idx (src/partitions.jl:24-35).
+ *  - Pointers are plain host pointers unless stated otherwise.  Every bulk
+ *    buffer argument may ALSO be a CUDA device pointer of the context's device
+ *    (copies use cudaMemcpyDefault); this is how a caller keeps data resident.
+ *  - Every function returns 0 (SDPSR_OK) or a negative sdpsr_status; the message
+ *    of the last failure is available from sdpsr_last_error().
+ *  - Calls are blocking: they return after the context's stream has drained.
+ *    A context is not thread-safe; distinct contexts are independent.
+ *  - No torch / C++ types cross this boundary.
+ *  - There is no CPU fallback: without a CUDA device sdpsr_create() fails.
+ */
+#ifndef SDPSR_H
+#define SDPSR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDPSR_VERSION 100 /* 0.1.0 */
+
+typedef struct sdpsr_ctx sdpsr_ctx;
+
+typedef enum sdpsr_status {
+  SDPSR_OK = 0,
+  SDPSR_E_INVALID = -1,        /* bad argument (AssertionError in the reference)        */
+  SDPSR_E_CUDA = -2,           /* CUDA runtime / driver failure                         */
+  SDPSR_E_NO_DEVICE = -3,      /* no CUDA device: there is no CPU fallback              */
+  SDPSR_E_ALLOC = -4,          /* out of device / host memory                           */
+  SDPSR_E_LABEL_OVERFLOW = -5, /* label does not fit the requested integer width
+                                  (InexactError, src/partitions.jl:29,63)              */
+  SDPSR_E_NOT_SYMMETRIC = -6,  /* partition is not transpose-invariant: real eigen path
+                                  impossible (InvalidDecompositionField,
+                                  src/eigen_decomposition.jl:247-253)                  */
+  SDPSR_E_CUSOLVER = -7,       /* cuSOLVER syevd failed / did not converge              */
+  SDPSR_E_STATE = -8,          /* call sequence error (e.g. square before fill)         */
+  SDPSR_E_SINGULAR = -9,       /* constraint rows linearly dependent (Gram singular)    */
+  SDPSR_E_NCCL = -10,          /* NCCL failure / NCCL library not loadable              */
+  SDPSR_E_UNSUPPORTED = -11    /* valid request outside this build's limits             */
+} sdpsr_status;
+
+/* flags for sdpsr_create */
+#define SDPSR_F_DEFAULT 0u
+#define SDPSR_F_FORCE_BITMAP_RANK 1u /* test hook: always use the bitmap-scan ranking path   */
+#define SDPSR_F_TINY_TABLE 2u        /* test hook: start with a 64-slot table (forces growth) */
+#define SDPSR_F_NO_SMEM_CACHE 4u     /* test hook: bypass the per-CTA key cache              */
+#define SDPSR_F_TIMING 8u            /* record CUDA-event timings per kernel family          */
+#define SDPSR_F_NO_SYRK 16u          /* square with the full GEMM even for symmetric X       */
+
+/* which device-resident matrix sdpsr_get_matrix / sdpsr_set_matrix address */
+#define SDPSR_MAT_X 0   /* current element X (src/partitions.jl:121)      */
+#define SDPSR_MAT_X2 1  /* last product X^2 / XY (src/partitions.jl:122)  */
+#define SDPSR_MAT_Q 2   /* eigenvectors of the last sdpsr_eig             */
+#define SDPSR_MAT_W 3   /* Q' A Q of the last sdpsr_block_norms           */
+
+/* kernel families for sdpsr_timing_get */
+#define SDPSR_K_REFINE 0   /* round + key + first-occurrence relabel pass        */
+#define SDPSR_K_GEMM 1     /* FP64 DMMA GEMM                                      */
+#define SDPSR_K_FILL 2     /* label -> value gather                               */
+#define SDPSR_K_PROJECT 3  /* constraint row dots                                 */
+#define SDPSR_K_RANK 4     /* canonical first-occurrence ranking of a key table   */
+#define SDPSR_K_EIG 5      /* cuSOLVER syevd (library)                            */
+#define SDPSR_K_BASIS 6    /* basis_image reduction                               */
+#define SDPSR_K_MISC 7     /* everything else (transpose, norms, ...)             */
+#define SDPSR_K_COUNT 8
+
+/* ------------------------------------------------------------------ lifetime */
+int sdpsr_version(void);
+/* ctx may be NULL: returns the message of the last failed sdpsr_create on this thread. */
+const char* sdpsr_last_error(const sdpsr_ctx* ctx);
+/* Allocates the device state for N x N problems on CUDA device `device`:
+ * labels (u32, double-buffered), X, X2 (f64), key tables, scratch.
+ * Replaces the allocations of src/partitions.jl:117-122.                               */
+int sdpsr_create(sdpsr_ctx** out, int64_t n, int device, uint32_t flags);
+int sdpsr_destroy(sdpsr_ctx* ctx);
+int sdpsr_device_count(int* count);
+
+/* ------------------------------------------------------------- constraints A
+ * The `A` argument of admissible_subspace (src/partitions.jl:112).  The engine
+ * derives from it the per-entry constraint pattern ids, the pattern table and a
+ * factorisation of the Gram matrix A A' that replace `qr(A')` (src/partitions.jl:124)
+ * in project_colspace! (src/utils.jl:62-66).
+ *   dense: A is m x N^2 column-major (a Julia Matrix{Float64}), ld = m.
+ *   csr  : row k holds entries rowptr[k]..rowptr[k+1]-1; this is the CSC storage of
+ *          A' (N^2 x m), i.e. `SparseMatrixCSC(transpose(A))` in Julia.
+ *   csc  : the SparseMatrixCSC storage of A itself (colptr has N^2+1 entries).
+ * index_base is 0 (C / numpy) or 1 (Julia).                                           */
+int sdpsr_set_constraints_dense(sdpsr_ctx* ctx, int64_t m, const double* A);
+int sdpsr_set_constraints_csr(sdpsr_ctx* ctx, int64_t m, const int64_t* rowptr,
+                              const int64_t* colidx, const double* vals, int index_base);
+int sdpsr_set_constraints_csc(sdpsr_ctx* ctx, int64_t m, const int64_t* colptr,
+                              const int64_t* rowval, const double* nzval, int index_base);
+/* number of distinct non-empty constraint column patterns found */
+int sdpsr_constraint_patterns(sdpsr_ctx* ctx, int64_t* npatterns);
+
+/* ------------------------------------------------------------- Partition state
+ * The context holds one Partition S (src/partitions.jl:6-9): labels 0..dim.         */
+/* S = empty partition (all labels 0, dim 0).                                         */
+int sdpsr_partition_reset(sdpsr_ctx* ctx);
+/* Partition{T}(M::AbstractMatrix{<:Integer}) = copy + __sort_unique!
+ * (src/partitions.jl:37-60).  labels: N x N integers of elt_bytes in {1,2,4,8}.     */
+int sdpsr_partition_set_labels(sdpsr_ctx* ctx, const void* labels, int elt_bytes,
+                               int64_t* dim);
+/* P.matrix in canonical first-occurrence numbering.  SDPSR_E_LABEL_OVERFLOW when a
+ * label does not fit elt_bytes (the reference's InexactError for UInt16).             */
+int sdpsr_partition_get_labels(sdpsr_ctx* ctx, void* labels, int elt_bytes);
+/* dim(P) (src/partitions.jl:13) */
+int sdpsr_partition_dim(sdpsr_ctx* ctx, int64_t* dim);
+/* number of entries with label 0 */
+int sdpsr_partition_zero_count(sdpsr_ctx* ctx, int64_t* count);
+/* 1 iff labels[i,j] == labels[j,i] for all i,j */
+int sdpsr_partition_is_symmetric(sdpsr_ctx* ctx, int* is_symmetric);
+/* S = refine!(S, Partition(M)) with M a host/device N x N Float64 matrix
+ * (src/partitions.jl:24-35,62-66).  do_round != 0 applies _clamp_round!(M; atol)
+ * first (src/utils.jl:34-53); do_round == 0 keys on the bits of M as they are
+ * (needed for Part(CL), whose entries are averaged after rounding, :131-133).
+ * On an empty S this is S = Partition(M).                                            */
+int sdpsr_refine_values(sdpsr_ctx* ctx, const double* M, double atol, int do_round,
+                        int64_t* dim);
+/* S = refine!(S, Partition(L)) for an integer label matrix L (src/partitions.jl:62-66). */
+int sdpsr_refine_labels(sdpsr_ctx* ctx, const void* labels, int elt_bytes, int64_t* dim);
+
+/* ------------------------------------------------- admissible_subspace pieces */
+/* The initial partition of src/partitions.jl:129-146, computed on the device:
+ *   CL = symmetrize(round(C - proj(C)));  X0 = round(proj(symmetrize(x0)));
+ *   S = refine!(Part(CL), Part(X0)),  x0 = min-norm solution of A x = b (Krylov.craig).
+ * snap_decimals >= 0 rounds both vectors to that many decimals before the
+ * reference's truncation (DESIGN.md "init safeguard"); < 0 disables it.              */
+int sdpsr_init_partition(sdpsr_ctx* ctx, const double* C, const double* b, double atol,
+                         int snap_decimals, int64_t* dim);
+/* X = fill!(X, S; values) (src/partitions.jl:68-75); len must equal dim(S).          */
+int sdpsr_fill(sdpsr_ctx* ctx, const double* values, int64_t len);
+/* x .-= proj(x); _clamp_round!(x); S = refine!(S, Part(X))   (src/partitions.jl:160-164).
+ * Requires constraints and a preceding sdpsr_fill.  X stays on the device.           */
+int sdpsr_project_round_refine(sdpsr_ctx* ctx, double atol, int64_t* dim);
+/* X2 = X*X; _clamp_round!(X2); S = refine!(S, Part(X2))       (src/partitions.jl:172-174). */
+int sdpsr_square_round_refine(sdpsr_ctx* ctx, double atol, int64_t* dim);
+/* desymmetrize step (src/partitions.jl:210-214):
+ * XY = fill(S,rx) * fill(S,ry); round; S = refine!(S, Part(XY)).                      */
+int sdpsr_product_round_refine(sdpsr_ctx* ctx, const double* rx, const double* ry,
+                               int64_t len, double atol, int64_t* dim);
+
+/* --------------------------------------------------- blockDiagonalize pieces */
+/* A = fill(S, r1); (vals, Q) = eigen(A)  (src/eigen_decomposition.jl:242-254).
+ * cuSOLVER Dsyevd; vals ascending (N doubles, host); Q stays on the device.
+ * SDPSR_E_NOT_SYMMETRIC when S is not transpose-invariant.                            */
+int sdpsr_eig(sdpsr_ctx* ctx, const double* r1, int64_t len, double* vals);
+/* A = fill(S, r2); W = Q' A Q; norms[i,j] = max|W[E_i,E_j]| for eigenspaces of equal
+ * dimension, else 0 (src/eigen_decomposition.jl:177-204).  ptrs: nptr = ne+1 0-based
+ * cluster boundaries; norms: ne x ne column-major (host).                             */
+int sdpsr_block_norms(sdpsr_ctx* ctx, const double* r2, int64_t len, const int64_t* ptrs,
+                      int64_t nptr, double* norms);
+/* irreducible_decomposition + clamptol! (src/eigen_decomposition.jl:295-348,
+ * src/diagonalize.jl:39).  kroot[e] = root eigenspace (0-based, smallest member) of
+ * the isomorphism class of eigenspace e.  Leaves Qhat (N x sum(blk_sizes)) on the
+ * device; blk_sizes must have room for ne entries; *nblk receives the block count.    */
+int sdpsr_irreducible(sdpsr_ctx* ctx, const double* r3, int64_t len, const int64_t* ptrs,
+                      int64_t nptr, const int64_t* kroot, double atol, int64_t* blk_sizes,
+                      int64_t* nblk);
+/* Copies Qhat (N x S, column-major) to the host. */
+int sdpsr_get_qhat(sdpsr_ctx* ctx, double* qhat, int64_t len);
+/* Replaces Qhat (test hook and complex-path helper): N x S column-major. */
+int sdpsr_set_qhat(sdpsr_ctx* ctx, const double* qhat, const int64_t* blk_sizes, int64_t nblk);
+/* basis_image (src/diagonalize.jl:64-89): out is packed as
+ *   for i in 0..dim-1, for k in 0..nblk-1: Qhat_k' * 1[S==i+1] * Qhat_k  (s_k x s_k, col-major)
+ * with |entries| < atol clamped to 0.  out_len must be dim * sum(s_k^2).              */
+int sdpsr_basis_image(sdpsr_ctx* ctx, double atol, double* out, int64_t out_len);
+
+/* -------------------------------------------------------------- plumbing */
+int sdpsr_get_matrix(sdpsr_ctx* ctx, int which, double* out);       /* N x N doubles */
+int sdpsr_set_matrix(sdpsr_ctx* ctx, int which, const double* in);  /* N x N doubles */
+/* C = A * B on the device with the engine's FP64 DMMA GEMM (test / bench hook);
+ * a, b, c are SDPSR_MAT_* ids, c != a, c != b. */
+int sdpsr_gemm(sdpsr_ctx* ctx, int a, int b, int c);
+/* Accumulated CUDA-event time, launch count and algorithmic work (bytes for HBM-bound
+ * families, flops for SDPSR_K_GEMM) per kernel family since the last reset.           */
+int sdpsr_timing_reset(sdpsr_ctx* ctx);
+int sdpsr_timing_get(sdpsr_ctx* ctx, int family, double* total_ms, int64_t* launches,
+                     double* work);
+/* total number of kernels launched by this context since creation */
+int sdpsr_launch_count(sdpsr_ctx* ctx, int64_t* launches);
+
+/* -------------------------------------------------------------- multi-GPU
+ * One context per process / GPU.  The N x N matrices are sharded by column blocks;
+ * every rank keeps the full label matrix.  NCCL is loaded with dlopen at first use.  */
+int sdpsr_comm_unique_id(void* id128 /* 128 bytes out */);
+int sdpsr_comm_init(sdpsr_ctx* ctx, int nranks, int rank, const void* id128);
+int sdpsr_comm_info(sdpsr_ctx* ctx, int* nranks, int* rank);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDPSR_H */

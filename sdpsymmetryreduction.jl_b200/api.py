@@ -1,0 +1,410 @@
+"""Host-side mirror of the reference's Julia API for the Jordan-reduction hot path.
+
+Same names, argument meaning and error behaviour as the reference:
+
+  admissible_subspace(C, A, b; verbose, atol)      src/partitions.jl:77-190
+  blockDiagonalize(P, verbose; epsilon, complex)   src/compat.jl:26-68
+  diagonalize(T, P; verbose, atol)                 src/diagonalize.jl:25-40
+  basis_image(Q, P; atol)                          src/diagonalize.jl:64-89
+  desymmetrize(P; verbose, atol) / unSymmetrize    src/partitions.jl:197-223
+  Partition(M), dim, refine, randomize             src/partitions.jl:6-75, src/abstract_part.jl:97-110
+
+All array work runs in ``libsdpsr_cuda.so``.  What stays in the host language is
+what the reference also keeps as scalar host logic: the driver loops, eigenvalue
+clustering, the Otsu threshold and the union-find of eigenspaces
+(src/eigen_decomposition.jl:19-40,83-139,163-219).
+
+Random coefficients: the reference draws ``rand(dim)`` from the task-local RNG;
+here every driver takes ``rand`` (a callable ``n -> ndarray``) and calls it at
+exactly the reference's points with the reference's lengths, so
+a caller can feed both sides the same numbers.
+"""
+from __future__ import annotations
+
+import logging
+import math
+import time
+from collections import namedtuple
+from typing import Callable, List, Optional
+
+import numpy as np
+
+from . import binding as B
+
+log = logging.getLogger("sdpsr_b200")
+RTOL_DEFAULT = math.sqrt(np.finfo(np.float64).eps)     # Base.rtoldefault(Float64)
+
+BlockDiagonalization = namedtuple("BlockDiagonalization", ["blkSizes", "blks"])
+
+
+class InvalidDecompositionField(Exception):
+    """src/eigen_decomposition.jl:140-150"""
+
+
+class NumericalInconsistency(Exception):
+    """src/eigen_decomposition.jl:152-161"""
+
+
+class DimensionMismatch(Exception):
+    """thrown by check_block_sizes, src/diagonalize.jl:1-23"""
+
+
+def _default_rand():
+    rng = np.random.default_rng()
+    return lambda n: rng.random(int(n))
+
+
+# ----------------------------------------------------------------------------
+# Partition
+# ----------------------------------------------------------------------------
+class Partition:
+    """``Partition{T}``: labels 0..nparts in first-occurrence (column-major) order
+    (src/partitions.jl:6-42).  ``Partition(M)`` builds it from a matrix of numbers on
+    the GPU; ``Partition(nparts, matrix)`` wraps given canonical labels."""
+
+    def __init__(self, *args, device: int = 0, _ctx: Optional[B.Context] = None):
+        self._ctx = _ctx
+        self.device = device
+        if len(args) == 2:
+            self.nparts = int(args[0])
+            self.matrix = np.asarray(args[1])
+        elif len(args) == 1:
+            M = np.asarray(args[0])
+            n = M.shape[0]
+            assert M.shape == (n, n)
+            with B.Context(n, device) as ctx:
+                if np.issubdtype(M.dtype, np.integer) or M.dtype == bool:
+                    self.nparts = ctx.set_labels(M.astype(np.int64))          # :37-42
+                else:
+                    self.nparts = ctx.refine_values(M.astype(np.float64), RTOL_DEFAULT, do_round=False)  # :24-35
+                self.matrix = ctx.get_labels(np.uint32)
+        else:
+            raise TypeError("Partition(M) or Partition(nparts, matrix)")
+
+    @property
+    def shape(self):
+        return self.matrix.shape
+
+    def size(self, *a):
+        return self.matrix.shape if not a else self.matrix.shape[a[0]]
+
+    def __eq__(self, other):                       # src/partitions.jl:16-17
+        return (isinstance(other, Partition) and self.nparts == other.nparts
+                and np.array_equal(self.matrix, other.matrix))
+
+    def __repr__(self):
+        return f"Partition(nparts={self.nparts}, size={self.matrix.shape})"
+
+    def _context(self, flags: int = 0) -> B.Context:
+        """A context whose device partition equals this one."""
+        ctx = self._ctx
+        if ctx is not None and getattr(ctx, "_h", None):
+            return ctx
+        n = self.matrix.shape[0]
+        ctx = B.Context(n, self.device, flags)
+        d = ctx.set_labels(self.matrix)
+        assert d == self.nparts, (d, self.nparts)
+        self._ctx = ctx
+        return ctx
+
+    def release(self):
+        """Free the device state kept alive for follow-up calls."""
+        if self._ctx is not None:
+            self._ctx.close()
+            self._ctx = None
+
+
+def dim(P: Partition) -> int:
+    return P.nparts
+
+
+def refine(P1: Partition, P2: Partition) -> Partition:
+    """``coarsestPart(P, Q) = refine!(deepcopy(P), Q)`` (src/compat.jl:12, src/partitions.jl:62-66)."""
+    n = P1.matrix.shape[0]
+    with B.Context(n, P1.device) as ctx:
+        ctx.set_labels(P1.matrix)
+        d = ctx.refine_labels(P2.matrix)
+        return Partition(d, ctx.get_labels(np.uint32), device=P1.device)
+
+
+def randomize(P: Partition, rand: Optional[Callable] = None) -> np.ndarray:
+    """``randomize(Float64, P)`` (src/abstract_part.jl:97-110)."""
+    rand = rand or _default_rand()
+    ctx = P._context()
+    ctx.fill(rand(P.nparts))
+    return ctx.get_matrix(B.MAT_X)
+
+
+# ----------------------------------------------------------------------------
+# admissible_subspace
+# ----------------------------------------------------------------------------
+def admissible_subspace(C, A, b, *, verbose: bool = False, atol: float = RTOL_DEFAULT,
+                        rand: Optional[Callable] = None, snap_decimals: Optional[int] = 12,
+                        device: int = 0, flags: int = 0, label_dtype=np.uint32,
+                        init_elements=None, trace: Optional[dict] = None,
+                        keep_context: bool = True, ctx: Optional[B.Context] = None) -> Partition:
+    """Optimal admissible partition subspace of  min <C,x>, A x = b, Mat(x) psd
+    (src/partitions.jl:77-190).
+
+    ``init_elements=(CL, X0)`` lets a host that owns the reference's own ``qr`` and
+    ``Krylov.craig`` (the Julia wrapper) supply the two initial elements
+    (:129-142); otherwise they are computed on the device.  ``label_dtype=np.uint16``
+    reproduces the reference's default ``Partition{UInt16}`` including its overflow
+    error (:84).
+    """
+    rand = rand or _default_rand()
+    Cv = C
+    if hasattr(C, "todense"):
+        Cv = np.asarray(C.todense()).reshape(-1)
+    nn = int(np.prod(Cv.shape))
+    n = math.isqrt(nn)
+    if n * n != nn:
+        raise AssertionError("n^2 == length(C)")                    # :118
+    own = ctx is None
+    if own:
+        ctx = B.Context(n, device, flags)
+    t0 = time.perf_counter()
+    if init_elements is None:
+        ctx.set_constraints(A)
+        cur = ctx.init_partition(Cv, b, atol, snap_decimals)         # :124-146
+    else:
+        ctx.set_constraints(A)
+        CL, X0 = init_elements
+        ctx.reset()
+        ctx.refine_values(CL, atol, do_round=False)                  # S = Part(CL)            :145
+        cur = ctx.refine_values(X0, atol, do_round=False)            # refine!(S, Part(X0))    :146
+    maxdim = (n * n + n) // 2
+    if verbose:
+        log.info("Starting the reduction. Dimensions: maximal=%d initial=%d", maxdim, cur)
+    if trace is not None:
+        trace.update({"init": cur, "iters": [], "t_init": time.perf_counter() - t0})
+    it = 0
+    while cur < maxdim:                                              # :154
+        it += 1
+        if verbose:
+            log.debug("Iteration %d, Current dimension: %d", it, cur)
+        ctx.fill(rand(cur))                                          # randomize!(X, S)        :159
+        d_proj = ctx.project_round_refine(atol)                      # :160-164
+        if d_proj != cur:                                            # :166-168
+            ctx.fill(rand(d_proj))
+        d_sq = ctx.square_round_refine(atol)                         # :172-174
+        if trace is not None:
+            trace["iters"].append((d_proj, d_sq))
+        if cur == d_sq:                                              # :180-182
+            break
+        cur = d_sq
+    if verbose:
+        log.info("Minimal admissible subspace converged in %d iterations at dimension: final=%d", it, ctx.dim())
+    if trace is not None:
+        trace["iterations"] = it
+        trace["t_total"] = time.perf_counter() - t0
+    try:
+        labels = ctx.get_labels(label_dtype)
+    except B.SdpsrError as e:
+        if e.code == B.E_LABEL_OVERFLOW:
+            raise OverflowError("InexactError: label does not fit " + str(np.dtype(label_dtype))) from e
+        raise
+    P = Partition(ctx.dim(), labels, device=device, _ctx=ctx if keep_context else None)
+    if own and not keep_context:
+        ctx.close()
+    return P
+
+
+# ----------------------------------------------------------------------------
+# desymmetrize
+# ----------------------------------------------------------------------------
+def desymmetrize(P: Partition, *, verbose: bool = False, atol: float = RTOL_DEFAULT,
+                 rand: Optional[Callable] = None) -> Partition:
+    """WL-style closure under products X*Y (src/partitions.jl:197-223)."""
+    rand = rand or _default_rand()
+    n = P.matrix.shape[0]
+    ctx = B.Context(n, P.device)                 # deepcopy(P): never touch P's own context
+    cur = ctx.set_labels(P.matrix)
+    it = 0
+    while True:
+        it += 1
+        rx = rand(cur)                                               # :210
+        ry = rand(cur)                                               # :211
+        d = ctx.product_round_refine(rx, ry, atol)                   # :212-214
+        if d == cur:
+            break
+        cur = d
+    if verbose:
+        log.info("desymmetization converged in %d iterations", it)
+    return Partition(ctx.dim(), ctx.get_labels(np.uint32), device=P.device, _ctx=ctx)
+
+
+def unSymmetrize(P: Partition, **kw) -> Partition:     # src/compat.jl:70
+    return desymmetrize(P, **kw)
+
+
+# ----------------------------------------------------------------------------
+# host-side scalar logic of Murota Alg. 4.1 (same split as the reference)
+# ----------------------------------------------------------------------------
+def eigen_clusters(values: np.ndarray, atol: float) -> np.ndarray:
+    """``EigenDecomposition`` ctor (src/eigen_decomposition.jl:19-40): 0-based ptrs."""
+    values = np.asarray(values)
+    brk = np.flatnonzero(np.abs(values[1:] - values[:-1]) > atol) + 1
+    gaps = np.abs(values[brk] - values[brk - 1])
+    tiny = gaps < np.spacing(np.maximum(np.abs(values[brk]), np.abs(values[brk - 1])))
+    if tiny.any():
+        log.warning("Possibly numerically challenging example: no clear spectral gap")   # :34-36
+    return np.concatenate([[0], brk, [values.size]]).astype(np.int64)
+
+
+def otsu_threshold(X: np.ndarray, atol: float) -> float:
+    """src/eigen_decomposition.jl:83-139 (16-bin log histogram + Otsu split)."""
+    n_bins = max(int(math.ceil(-math.log10(np.finfo(np.float64).eps))), 4)
+    a = np.abs(np.asarray(X, dtype=np.float64)).reshape(-1)
+    lo, hi = a.min(), a.max()
+    if lo < atol:
+        lo = atol
+    assert lo > 0
+    edges = np.exp(np.linspace(math.log(lo), math.log(hi), n_bins + 1))
+    if np.all(np.diff(edges) > 0):
+        first_gt = np.searchsorted(edges, a, side="right")
+    else:
+        first_gt = np.array([next((i for i, e in enumerate(edges) if e > x), n_bins) for x in a])
+    k = np.clip(first_gt, 1, n_bins)
+    counts = np.bincount(k - 1, minlength=n_bins)[:n_bins]
+    pdf = counts / counts.sum()
+    w = np.cumsum(pdf)
+    mu = np.cumsum(np.log(edges[:-1]) * pdf)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        s2 = (mu[-1] * w - mu) ** 2 / (w * (1 - w))
+    cand = s2[:-1]
+    nan = np.flatnonzero(np.isnan(cand))
+    kk = int(nan[0]) if nan.size else int(np.argmax(cand))
+    return float(edges[kk + 1])
+
+
+class _DisjointSets:
+    """DataStructures.IntDisjointSets: union by rank, ties -> first argument's root."""
+
+    def __init__(self, n):
+        self.p = list(range(n))
+        self.r = [0] * n
+
+    def find(self, x):
+        root = x
+        while self.p[root] != root:
+            root = self.p[root]
+        while self.p[x] != root:
+            self.p[x], x = root, self.p[x]
+        return root
+
+    def union(self, x, y):
+        xr, yr = self.find(x), self.find(y)
+        if xr == yr:
+            return
+        if self.r[xr] < self.r[yr]:
+            xr, yr = yr, xr
+        elif self.r[xr] == self.r[yr]:
+            self.r[xr] += 1
+        self.p[yr] = xr
+
+
+def _isomorphism_classes(norms: np.ndarray, atol: float) -> np.ndarray:
+    """src/eigen_decomposition.jl:205-219 + __isconsistent (:163-167). Returns kroot."""
+    ne = norms.shape[0]
+    thr = otsu_threshold(norms, atol)
+    K = _DisjointSets(ne)
+    ii, jj = np.nonzero(np.triu(norms >= thr, k=1))
+    for i, j in zip(ii.tolist(), jj.tolist()):       # row-major order == the reference's loops
+        K.union(i, j)
+    kpart = [K.find(i) for i in range(ne)]
+    first = {}
+    for i, r in enumerate(kpart):
+        first.setdefault(r, i)
+    if not all(r == f for r, f in first.items()):
+        raise NumericalInconsistency(
+            "eigen_decomposition: the K-partition seems inconsistent with eigenspaces. "
+            "Decrease `atol`, or simply try again.")
+    return np.asarray(kpart, dtype=np.int64)
+
+
+# ----------------------------------------------------------------------------
+# diagonalize / basis_image / blockDiagonalize
+# ----------------------------------------------------------------------------
+def eigen_decomposition(P: Partition, *, atol: float, rand: Callable, ctx: Optional[B.Context] = None):
+    """src/eigen_decomposition.jl:236-273. Returns (values, ptrs, kroot); Q stays on the device."""
+    ctx = ctx or P._context()
+    try:
+        vals = ctx.eig(rand(P.nparts))                               # :242-254
+    except B.SdpsrError as e:
+        if e.code == B.E_NOT_SYMMETRIC:
+            raise InvalidDecompositionField(
+                "Decomposition over Float64 was requested but eigenvalues of type ComplexF64 were found. "
+                "Consider calling `diagonalize` with ComplexF64 as its first argument.") from e
+        raise
+    ptrs = eigen_clusters(vals, atol)
+    norms = ctx.block_norms(rand(P.nparts), ptrs)                    # :259, :203-204
+    kroot = _isomorphism_classes(norms, atol)
+    return vals, ptrs, kroot
+
+
+def diagonalize(P: Partition, *, verbose: bool = False, atol: Optional[float] = None,
+                rand: Optional[Callable] = None, complex: bool = False,
+                fetch: bool = True, ctx: Optional[B.Context] = None):
+    """``diagonalize(Float64, P)`` (src/diagonalize.jl:25-40): list of N x s_k matrices Q_hat."""
+    if complex:
+        raise NotImplementedError(
+            "complex path (SURVEY.md 8(f) rank 1) is not built yet; desymmetrize() is available")
+    rand = rand or _default_rand()
+    n = P.matrix.shape[0]
+    if atol is None:
+        atol = 1e-12 * n
+    ctx = ctx or P._context()
+    t = time.perf_counter()
+    vals, ptrs, kroot = eigen_decomposition(P, atol=atol, rand=rand, ctx=ctx)
+    if verbose:
+        log.info("Determining eigen-decomposition over Float64... %.3fs", time.perf_counter() - t)
+    t = time.perf_counter()
+    sizes = ctx.irreducible(rand(P.nparts), ptrs, kroot, atol)       # :306, clamptol! :39
+    if verbose:
+        log.info("Determining the algebra-isomorphism... %.3fs", time.perf_counter() - t)
+    P._blk_sizes = sizes
+    P._ptrs, P._kroot = ptrs, kroot
+    if not fetch:
+        return sizes
+    return ctx.get_qhat(sizes)
+
+
+def check_block_sizes(sizes, P: Partition, complex: bool = False):
+    """src/diagonalize.jl:1-23"""
+    final = sum(int(s) ** 2 for s in sizes) if complex else sum(int(s) * (int(s) + 1) // 2 for s in sizes)
+    if final != P.nparts:
+        log.error("Dimension mismatch: (final_dim=%d, block_sizes=%s) expected_dim=%d", final, list(sizes), P.nparts)
+        raise DimensionMismatch(
+            "Decomposition failed potentially due to\n"
+            "* Rounding error (try different epsilons and/or try again) or\n"
+            "* Algebra is not block-diagonalizable over the reals (retry with complex type).")
+
+
+def basis_image(Qhat: List[np.ndarray], P: Partition, *, atol: Optional[float] = None):
+    """``basis_image(Q, P)`` (src/diagonalize.jl:64-89): blks[i][k] = Q_k' 1[P==i+1] Q_k."""
+    n = P.matrix.shape[0]
+    if atol is None:
+        atol = 1e-12 * n
+    ctx = P._context()
+    ctx.set_qhat(Qhat)
+    return ctx.basis_image([q.shape[1] for q in Qhat], atol, dim=P.nparts)
+
+
+def blockDiagonalize(P: Partition, verbose: bool = True, *, epsilon: float = RTOL_DEFAULT,
+                     complex: bool = False, rand: Optional[Callable] = None):
+    """src/compat.jl:26-68.  Returns ``(blkSizes, blks)``; ``blks[i][k]`` is the image of
+    the basis element ``P.matrix == i+1`` in block k."""
+    if complex:
+        raise NotImplementedError(
+            "complex path (SURVEY.md 8(f) rank 1) is not built yet; desymmetrize() is available")
+    rand = rand or _default_rand()
+    n = P.matrix.shape[0]
+    ctx = P._context()
+    sizes = diagonalize(P, verbose=verbose, atol=epsilon, rand=rand, fetch=False, ctx=ctx)
+    check_block_sizes(sizes, P, False)
+    t = time.perf_counter()
+    blks = ctx.basis_image(sizes, 1e-12 * n, dim=P.nparts)      # atol default, not epsilon (Appendix C)
+    if verbose:
+        log.info("Calculating image of the basis of the algebra... %.3fs", time.perf_counter() - t)
+    return BlockDiagonalization([int(s) for s in sizes], blks)

@@ -1,0 +1,398 @@
+"""ctypes binding of ``libsdpsr_cuda.so`` (C ABI: ``include/sdpsr.h``).
+
+This is the same call sequence a Julia ``ccall`` wrapper makes;
+Python is the host language here only because the image has no Julia.  There is
+no CPU fallback: if the shared library has not been built, or there is no CUDA
+device, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+# status codes (include/sdpsr.h)
+OK = 0
+E_INVALID, E_CUDA, E_NO_DEVICE, E_ALLOC, E_LABEL_OVERFLOW, E_NOT_SYMMETRIC = -1, -2, -3, -4, -5, -6
+E_CUSOLVER, E_STATE, E_SINGULAR, E_NCCL, E_UNSUPPORTED = -7, -8, -9, -10, -11
+
+F_FORCE_BITMAP_RANK, F_TINY_TABLE, F_NO_SMEM_CACHE, F_TIMING, F_NO_SYRK = 1, 2, 4, 8, 16
+MAT_X, MAT_X2, MAT_Q, MAT_W = 0, 1, 2, 3
+K_REFINE, K_GEMM, K_FILL, K_PROJECT, K_RANK, K_EIG, K_BASIS, K_MISC = range(8)
+K_NAMES = ["refine", "gemm", "fill", "project", "rank", "eig", "basis", "misc"]
+
+
+class LibraryNotBuilt(RuntimeError):
+    pass
+
+
+class SdpsrError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libsdpsr_cuda error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+def lib_path() -> str:
+    return os.environ.get("SDPSR_LIB", os.path.join(_HERE, "libsdpsr_cuda.so"))
+
+
+_i64 = C.c_int64
+_p = C.c_void_p
+_SIGNATURES = {
+    "sdpsr_version": ([], C.c_int),
+    "sdpsr_last_error": ([_p], C.c_char_p),
+    "sdpsr_create": ([C.POINTER(_p), _i64, C.c_int, C.c_uint32], C.c_int),
+    "sdpsr_destroy": ([_p], C.c_int),
+    "sdpsr_device_count": ([C.POINTER(C.c_int)], C.c_int),
+    "sdpsr_set_constraints_dense": ([_p, _i64, _p], C.c_int),
+    "sdpsr_set_constraints_csr": ([_p, _i64, _p, _p, _p, C.c_int], C.c_int),
+    "sdpsr_set_constraints_csc": ([_p, _i64, _p, _p, _p, C.c_int], C.c_int),
+    "sdpsr_constraint_patterns": ([_p, C.POINTER(_i64)], C.c_int),
+    "sdpsr_partition_reset": ([_p], C.c_int),
+    "sdpsr_partition_set_labels": ([_p, _p, C.c_int, C.POINTER(_i64)], C.c_int),
+    "sdpsr_partition_get_labels": ([_p, _p, C.c_int], C.c_int),
+    "sdpsr_partition_dim": ([_p, C.POINTER(_i64)], C.c_int),
+    "sdpsr_partition_zero_count": ([_p, C.POINTER(_i64)], C.c_int),
+    "sdpsr_partition_is_symmetric": ([_p, C.POINTER(C.c_int)], C.c_int),
+    "sdpsr_refine_values": ([_p, _p, C.c_double, C.c_int, C.POINTER(_i64)], C.c_int),
+    "sdpsr_refine_labels": ([_p, _p, C.c_int, C.POINTER(_i64)], C.c_int),
+    "sdpsr_init_partition": ([_p, _p, _p, C.c_double, C.c_int, C.POINTER(_i64)], C.c_int),
+    "sdpsr_fill": ([_p, _p, _i64], C.c_int),
+    "sdpsr_project_round_refine": ([_p, C.c_double, C.POINTER(_i64)], C.c_int),
+    "sdpsr_square_round_refine": ([_p, C.c_double, C.POINTER(_i64)], C.c_int),
+    "sdpsr_product_round_refine": ([_p, _p, _p, _i64, C.c_double, C.POINTER(_i64)], C.c_int),
+    "sdpsr_eig": ([_p, _p, _i64, _p], C.c_int),
+    "sdpsr_block_norms": ([_p, _p, _i64, _p, _i64, _p], C.c_int),
+    "sdpsr_irreducible": ([_p, _p, _i64, _p, _i64, _p, C.c_double, _p, C.POINTER(_i64)], C.c_int),
+    "sdpsr_get_qhat": ([_p, _p, _i64], C.c_int),
+    "sdpsr_set_qhat": ([_p, _p, _p, _i64], C.c_int),
+    "sdpsr_basis_image": ([_p, C.c_double, _p, _i64], C.c_int),
+    "sdpsr_get_matrix": ([_p, C.c_int, _p], C.c_int),
+    "sdpsr_set_matrix": ([_p, C.c_int, _p], C.c_int),
+    "sdpsr_gemm": ([_p, C.c_int, C.c_int, C.c_int], C.c_int),
+    "sdpsr_timing_reset": ([_p], C.c_int),
+    "sdpsr_timing_get": ([_p, C.c_int, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(C.c_double)], C.c_int),
+    "sdpsr_launch_count": ([_p, C.POINTER(_i64)], C.c_int),
+    "sdpsr_comm_unique_id": ([_p], C.c_int),
+    "sdpsr_comm_init": ([_p, C.c_int, C.c_int, _p], C.c_int),
+    "sdpsr_comm_info": ([_p, C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
+}
+
+
+def declared_symbols():
+    return sorted(_SIGNATURES)
+
+
+def load_library():
+    """dlopen libsdpsr_cuda.so and declare every prototype; raises LibraryNotBuilt."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise LibraryNotBuilt(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    for name, (argtypes, restype) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _LIB = lib
+    return lib
+
+
+def device_count() -> int:
+    lib = load_library()
+    c = C.c_int(0)
+    lib.sdpsr_device_count(C.byref(c))
+    return c.value
+
+
+def _ptr(x):
+    """Host ndarray -> address; torch CUDA tensor -> device address (kept resident)."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    raise TypeError(f"unsupported buffer type {type(x)}")
+
+
+def _f64(x) -> np.ndarray:
+    return np.ascontiguousarray(x, dtype=np.float64)
+
+
+class Context:
+    """One ``sdpsr_ctx``: the device state of an N x N problem on one GPU."""
+
+    def __init__(self, n: int, device: int = 0, flags: int = 0):
+        self.lib = load_library()
+        self.n = int(n)
+        self.device = device
+        self._h = _p()
+        st = self.lib.sdpsr_create(C.byref(self._h), self.n, device, flags)
+        if st != OK:
+            msg = self.lib.sdpsr_last_error(None).decode()
+            self._h = None
+            raise SdpsrError(st, msg)
+
+    # -- plumbing ---------------------------------------------------------------
+    def _check(self, st: int):
+        if st != OK:
+            raise SdpsrError(st, self.lib.sdpsr_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.sdpsr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- constraints -------------------------------------------------------------
+    def set_constraints(self, A):
+        """A: (m, N^2) ndarray or scipy.sparse matrix (src/partitions.jl:112)."""
+        import scipy.sparse as sp
+        if sp.issparse(A):
+            A = A.tocsr()
+            A.sum_duplicates()
+            A.sort_indices()
+            m = A.shape[0]
+            assert A.shape[1] == self.n * self.n
+            rp = np.ascontiguousarray(A.indptr, dtype=np.int64)
+            ci = np.ascontiguousarray(A.indices, dtype=np.int64)
+            vv = _f64(A.data)
+            self._check(self.lib.sdpsr_set_constraints_csr(self._h, m, rp.ctypes.data, ci.ctypes.data,
+                                                           vv.ctypes.data, 0))
+        else:
+            A = np.asarray(A, dtype=np.float64)
+            m = A.shape[0]
+            assert A.shape[1] == self.n * self.n
+            Af = np.asfortranarray(A)       # Julia Matrix layout: m x N^2 column-major
+            self._check(self.lib.sdpsr_set_constraints_dense(self._h, m, Af.ctypes.data))
+        self.m = m
+
+    def set_constraints_csc(self, m, colptr, rowval, nzval, index_base=0):
+        colptr = np.ascontiguousarray(colptr, dtype=np.int64)
+        rowval = np.ascontiguousarray(rowval, dtype=np.int64)
+        nzval = _f64(nzval)
+        self._check(self.lib.sdpsr_set_constraints_csc(self._h, m, colptr.ctypes.data, rowval.ctypes.data,
+                                                       nzval.ctypes.data, index_base))
+        self.m = m
+
+    def constraint_patterns(self) -> int:
+        v = _i64(0)
+        self._check(self.lib.sdpsr_constraint_patterns(self._h, C.byref(v)))
+        return v.value
+
+    # -- partition ---------------------------------------------------------------
+    def reset(self):
+        self._check(self.lib.sdpsr_partition_reset(self._h))
+
+    def set_labels(self, M) -> int:
+        M = np.asarray(M)
+        assert M.shape == (self.n, self.n)
+        if M.dtype not in (np.uint8, np.uint16, np.uint32, np.int64):
+            M = M.astype(np.int64)
+        Mf = np.asfortranarray(M)
+        d = _i64(0)
+        self._check(self.lib.sdpsr_partition_set_labels(self._h, Mf.ctypes.data, Mf.dtype.itemsize, C.byref(d)))
+        return d.value
+
+    def refine_labels(self, M) -> int:
+        M = np.asarray(M)
+        assert M.shape == (self.n, self.n)
+        if M.dtype not in (np.uint8, np.uint16, np.uint32, np.int64):
+            M = M.astype(np.int64)
+        Mf = np.asfortranarray(M)
+        d = _i64(0)
+        self._check(self.lib.sdpsr_refine_labels(self._h, Mf.ctypes.data, Mf.dtype.itemsize, C.byref(d)))
+        return d.value
+
+    def get_labels(self, dtype=np.uint32, out=None):
+        dtype = np.dtype(dtype)
+        if out is None:
+            out = np.empty((self.n, self.n), dtype=dtype, order="F")
+            self._check(self.lib.sdpsr_partition_get_labels(self._h, out.ctypes.data, dtype.itemsize))
+            return out
+        self._check(self.lib.sdpsr_partition_get_labels(self._h, _ptr(out), dtype.itemsize))
+        return out
+
+    def dim(self) -> int:
+        d = _i64(0)
+        self._check(self.lib.sdpsr_partition_dim(self._h, C.byref(d)))
+        return d.value
+
+    def zero_count(self) -> int:
+        d = _i64(0)
+        self._check(self.lib.sdpsr_partition_zero_count(self._h, C.byref(d)))
+        return d.value
+
+    def is_symmetric(self) -> bool:
+        v = C.c_int(0)
+        self._check(self.lib.sdpsr_partition_is_symmetric(self._h, C.byref(v)))
+        return bool(v.value)
+
+    def refine_values(self, M, atol: float, do_round: bool = True) -> int:
+        """S = refine!(S, Partition(round?(M))); M ndarray (N,N) or a device tensor
+        holding the column-major N x N doubles."""
+        if isinstance(M, np.ndarray):
+            assert M.shape == (self.n, self.n)
+            M = np.asfortranarray(M, dtype=np.float64)
+        d = _i64(0)
+        self._check(self.lib.sdpsr_refine_values(self._h, _ptr(M), float(atol), int(do_round), C.byref(d)))
+        return d.value
+
+    def init_partition(self, Cvec, b, atol: float, snap_decimals: Optional[int] = 12) -> int:
+        if isinstance(Cvec, np.ndarray):
+            Cvec = _f64(Cvec).reshape(-1)
+            assert Cvec.size == self.n * self.n
+        b = _f64(b)
+        d = _i64(0)
+        snap = -1 if snap_decimals is None else int(snap_decimals)
+        self._check(self.lib.sdpsr_init_partition(self._h, _ptr(Cvec), b.ctypes.data, float(atol), snap, C.byref(d)))
+        return d.value
+
+    def fill(self, values):
+        values = _f64(values)
+        self._check(self.lib.sdpsr_fill(self._h, values.ctypes.data, values.size))
+
+    def project_round_refine(self, atol: float) -> int:
+        d = _i64(0)
+        self._check(self.lib.sdpsr_project_round_refine(self._h, float(atol), C.byref(d)))
+        return d.value
+
+    def square_round_refine(self, atol: float) -> int:
+        d = _i64(0)
+        self._check(self.lib.sdpsr_square_round_refine(self._h, float(atol), C.byref(d)))
+        return d.value
+
+    def product_round_refine(self, rx, ry, atol: float) -> int:
+        rx, ry = _f64(rx), _f64(ry)
+        assert rx.size == ry.size
+        d = _i64(0)
+        self._check(self.lib.sdpsr_product_round_refine(self._h, rx.ctypes.data, ry.ctypes.data, rx.size,
+                                                        float(atol), C.byref(d)))
+        return d.value
+
+    # -- block diagonalisation ------------------------------------------------------
+    def eig(self, r1) -> np.ndarray:
+        r1 = _f64(r1)
+        vals = np.empty(self.n, dtype=np.float64)
+        self._check(self.lib.sdpsr_eig(self._h, r1.ctypes.data, r1.size, vals.ctypes.data))
+        return vals
+
+    def block_norms(self, r2, ptrs) -> np.ndarray:
+        r2 = _f64(r2)
+        ptrs = np.ascontiguousarray(ptrs, dtype=np.int64)
+        ne = ptrs.size - 1
+        norms = np.zeros((ne, ne), dtype=np.float64, order="F")
+        self._check(self.lib.sdpsr_block_norms(self._h, r2.ctypes.data, r2.size, ptrs.ctypes.data, ptrs.size,
+                                               norms.ctypes.data))
+        return norms
+
+    def irreducible(self, r3, ptrs, kroot, atol: float):
+        r3 = _f64(r3)
+        ptrs = np.ascontiguousarray(ptrs, dtype=np.int64)
+        kroot = np.ascontiguousarray(kroot, dtype=np.int64)
+        sizes = np.zeros(ptrs.size - 1, dtype=np.int64)
+        nblk = _i64(0)
+        self._check(self.lib.sdpsr_irreducible(self._h, r3.ctypes.data, r3.size, ptrs.ctypes.data, ptrs.size,
+                                               kroot.ctypes.data, float(atol), sizes.ctypes.data, C.byref(nblk)))
+        return sizes[:nblk.value].copy()
+
+    def get_qhat(self, sizes) -> list:
+        S = int(np.sum(sizes))
+        buf = np.empty((self.n, S), dtype=np.float64, order="F")
+        self._check(self.lib.sdpsr_get_qhat(self._h, buf.ctypes.data, buf.size))
+        out, c = [], 0
+        for s in sizes:
+            out.append(np.ascontiguousarray(buf[:, c:c + int(s)]))
+            c += int(s)
+        return out
+
+    def set_qhat(self, qhat: Sequence[np.ndarray]):
+        sizes = np.array([q.shape[1] for q in qhat], dtype=np.int64)
+        buf = np.asfortranarray(np.concatenate([np.asarray(q, dtype=np.float64) for q in qhat], axis=1))
+        self._check(self.lib.sdpsr_set_qhat(self._h, buf.ctypes.data, sizes.ctypes.data, sizes.size))
+
+    def basis_image(self, sizes, atol: float, dim: Optional[int] = None) -> list:
+        d = self.dim() if dim is None else dim
+        sq = int(sum(int(s) * int(s) for s in sizes))
+        out = np.zeros(d * sq, dtype=np.float64)
+        self._check(self.lib.sdpsr_basis_image(self._h, float(atol), out.ctypes.data, out.size))
+        blks = []
+        for i in range(d):
+            row, off = [], i * sq
+            for s in sizes:
+                s = int(s)
+                row.append(out[off:off + s * s].reshape(s, s, order="F").copy())
+                off += s * s
+            blks.append(row)
+        return blks
+
+    # -- matrices / tools --------------------------------------------------------------
+    def get_matrix(self, which: int) -> np.ndarray:
+        out = np.empty((self.n, self.n), dtype=np.float64, order="F")
+        self._check(self.lib.sdpsr_get_matrix(self._h, which, out.ctypes.data))
+        return out
+
+    def set_matrix(self, which: int, M):
+        if isinstance(M, np.ndarray):
+            M = np.asfortranarray(M, dtype=np.float64)
+        self._check(self.lib.sdpsr_set_matrix(self._h, which, _ptr(M)))
+
+    def gemm(self, a: int, b: int, c: int):
+        self._check(self.lib.sdpsr_gemm(self._h, a, b, c))
+
+    def timing_reset(self):
+        self._check(self.lib.sdpsr_timing_reset(self._h))
+
+    def timing(self) -> dict:
+        out = {}
+        for fam, name in enumerate(K_NAMES):
+            ms, n, w = C.c_double(0), _i64(0), C.c_double(0)
+            self._check(self.lib.sdpsr_timing_get(self._h, fam, C.byref(ms), C.byref(n), C.byref(w)))
+            out[name] = {"ms": ms.value, "launches": n.value, "work": w.value}
+        return out
+
+    def launch_count(self) -> int:
+        v = _i64(0)
+        self._check(self.lib.sdpsr_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    # -- multi-GPU ----------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        st = lib.sdpsr_comm_unique_id(buf)
+        if st != OK:
+            raise SdpsrError(st, "ncclGetUniqueId failed / NCCL not loadable")
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, uid: bytes):
+        buf = C.create_string_buffer(uid, 128)
+        self._check(self.lib.sdpsr_comm_init(self._h, nranks, rank, buf))
+
+    def comm_info(self):
+        a, b = C.c_int(0), C.c_int(0)
+        self._check(self.lib.sdpsr_comm_info(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value

@@ -1,0 +1,654 @@
+// blockdiag.cu -- device side of blockDiagonalize (Murota et al., Alg. 4.1).
+//
+// Replaces  eigen(A)                  src/eigen_decomposition.jl:246   (cuSOLVER Xsyevd -- the
+//                                                                       one library call on the path)
+//           Q' A Q + block_norms      src/eigen_decomposition.jl:177-204
+//           irreducible_decomposition src/eigen_decomposition.jl:295-348
+//           basis_image               src/diagonalize.jl:64-89
+// The scalar decisions in between (eigenvalue clustering, Otsu threshold, union-find,
+// consistency check) stay in the host language, exactly as the reference has them.
+#include <cusolverDn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "sdpsr_internal.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                        int64_t n, int64_t ld) {
+  __shared__ double t[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t bi = blockIdx.x, bj = blockIdx.y;
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = bj * 32 + tx, j = bi * 32 + r;
+    t[r][tx] = (i < n && j < n) ? in[i + ld * j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = bi * 32 + tx, j = bj * 32 + r;
+    if (i < n && j < n) out[i + ld * j] = t[tx][r];
+  }
+}
+
+// norms[i + ne*j] = max |W[a,b]| over a in E_i, b in E_j, for i <= j with equal dimensions.
+// Non-negative doubles order like their bit patterns, so atomicMax on the bits is exact.
+__global__ void __launch_bounds__(256) block_max_kernel(const double* __restrict__ W, int64_t n, int64_t ld,
+                                                        const uint32_t* __restrict__ space,
+                                                        const uint32_t* __restrict__ sdim, int64_t ne,
+                                                        unsigned long long* __restrict__ norms) {
+  const int64_t b = blockIdx.y;
+  const uint32_t sj = space[b];
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nround = (n + step - 1) / step * step;
+  for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < nround; a += step) {
+    const bool valid = a < n;
+    uint32_t si = 0xffffffffu;
+    unsigned long long bits = 0ull;
+    if (valid) {
+      si = space[a];
+      if (si <= sj && sdim[si] == sdim[sj])
+        bits = (unsigned long long)__double_as_longlong(fabs(W[a + ld * b]));
+      else
+        si = 0xfffffffeu;
+    }
+    // lanes of one warp mostly share the eigenspace: reduce inside equal-key groups first
+    const unsigned mask = __match_any_sync(0xffffffffu, si);
+    unsigned long long m = bits;
+    for (int o = 16; o; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, m, o);
+      const uint32_t osi = __shfl_xor_sync(0xffffffffu, si, o);
+      if (osi == si && other > m) m = other;
+    }
+    // after the butterfly only lanes whose whole warp shares the key hold the group max; fall back
+    // to one atomic per lane otherwise (rare: only at eigenspace boundaries)
+    if (valid && si < 0xfffffffeu) {
+      if (mask == 0xffffffffu) {
+        if ((threadIdx.x & 31) == 0 && m) atomicMax(norms + si + ne * sj, m);
+      } else if (bits) {
+        atomicMax(norms + si + ne * sj, bits);
+      }
+    }
+  }
+}
+
+// F[:, f] = Q[:, col[f]]
+__global__ void gather_cols_kernel(const double* __restrict__ Q, int64_t ld, const int64_t* __restrict__ cols,
+                                   double* __restrict__ F) {
+  const int64_t f = blockIdx.y;
+  const double* src = Q + ld * cols[f];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ld; i += (int64_t)gridDim.x * blockDim.x)
+    F[i + ld * f] = src[i];
+}
+
+// one CTA per (pair, t):   out[pair*maxm + t] = dot(Q[:, qcol[pair] + t], V[:, vcol[pair]])
+__global__ void __launch_bounds__(256) pair_dot_kernel(const double* __restrict__ Q, const double* __restrict__ V,
+                                                       int64_t n, int64_t ld, const int64_t* __restrict__ qcol,
+                                                       const int64_t* __restrict__ vcol,
+                                                       const int64_t* __restrict__ mult, int64_t maxm,
+                                                       double* __restrict__ out) {
+  __shared__ double ws[8];
+  const int64_t pair = blockIdx.y, t = blockIdx.x;
+  if (t >= mult[pair]) return;
+  const double* q = Q + ld * (qcol[pair] + t);
+  const double* v = V + ld * vcol[pair];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += q[i] * v[i];
+  for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tt = 0.0;
+    for (int w = 0; w < 8; ++w) tt += ws[w];
+    out[pair * maxm + t] = tt;
+  }
+}
+
+// Qhat[:, dst[pair]] = Q[:, qcol[pair] .. + mult) * u[pair, :] / ||w[pair, :]||
+__global__ void __launch_bounds__(256) pair_combine_kernel(const double* __restrict__ Q, int64_t n, int64_t ld,
+                                                           const int64_t* __restrict__ qcol,
+                                                           const int64_t* __restrict__ mult, int64_t maxm,
+                                                           const double* __restrict__ u, const double* __restrict__ w,
+                                                           const int64_t* __restrict__ dst, double* __restrict__ Qhat) {
+  const int64_t pair = blockIdx.y;
+  const int64_t mlt = mult[pair];
+  double nrm2 = 0.0;
+  for (int64_t t = 0; t < mlt; ++t) nrm2 += w[pair * maxm + t] * w[pair * maxm + t];
+  const double nrm = sqrt(nrm2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int64_t t = 0; t < mlt; ++t) s += Q[i + ld * (qcol[pair] + t)] * (u[pair * maxm + t] / nrm);
+    Qhat[i + ld * dst[pair]] = s;
+  }
+}
+
+__global__ void clamp_kernel(double* __restrict__ x, uint64_t total, double atol) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
+    if (fabs(x[i]) < atol) x[i] = 0.0;
+}
+
+// Qt[c + S*r] = Qhat[r + ld*c]  (row-major copy so that one matrix row is contiguous)
+__global__ void qhat_rowmajor_kernel(const double* __restrict__ Qhat, int64_t n, int64_t ld, int64_t S,
+                                     double* __restrict__ Qt) {
+  const int64_t c = blockIdx.y;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+    Qt[c + S * r] = Qhat[r + ld * c];
+}
+
+// --- CSR-by-label (the reference's _constraints, src/diagonalize.jl:42-50) ----------------
+__global__ void __launch_bounds__(256) class_count_kernel(const uint32_t* __restrict__ lab,
+                                                          const uint32_t* __restrict__ rank, int64_t n, int64_t ld,
+                                                          unsigned long long* __restrict__ cnt) {
+  const int64_t j = blockIdx.y;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nround = (n + step - 1) / step * step;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += step) {
+    const bool valid = i < n;
+    const uint32_t c = valid ? rank[lab[i + ld * j]] : 0xffffffffu;
+    const unsigned mask = __match_any_sync(0xffffffffu, c);
+    if (valid && c != 0u && (int)(__ffs(mask) - 1) == (int)(threadIdx.x & 31))
+      atomicAdd(cnt + c, (unsigned long long)__popc(mask));
+  }
+}
+
+__global__ void __launch_bounds__(256) class_scatter_kernel(const uint32_t* __restrict__ lab,
+                                                            const uint32_t* __restrict__ rank, int64_t n, int64_t ld,
+                                                            unsigned long long* __restrict__ cursor,
+                                                            uint32_t* __restrict__ rows, uint32_t* __restrict__ cols) {
+  const int64_t j = blockIdx.y;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nround = (n + step - 1) / step * step;
+  const int lane = threadIdx.x & 31;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += step) {
+    const bool valid = i < n;
+    const uint32_t c = valid ? rank[lab[i + ld * j]] : 0xffffffffu;
+    const unsigned mask = __match_any_sync(0xffffffffu, c);
+    const int leader = __ffs(mask) - 1;
+    unsigned long long basepos = 0ull;
+    if (valid && c != 0u && lane == leader) basepos = atomicAdd(cursor + c, (unsigned long long)__popc(mask));
+    basepos = __shfl_sync(0xffffffffu, basepos, leader);
+    if (valid && c != 0u) {
+      const unsigned long long pos = basepos + __popc(mask & ((1u << lane) - 1u));
+      rows[pos] = (uint32_t)i;
+      cols[pos] = (uint32_t)j;
+    }
+  }
+}
+
+constexpr int BI_PAIRS = 16;     // output elements accumulated per thread
+constexpr int BI_CHUNK = 4096;   // entries per CTA
+
+// partial[chunk][p] = sum over the chunk's entries (r,c) of Qt[r][ca[p]] * Qt[c][cb[p]]
+__global__ void __launch_bounds__(256) basis_partial_kernel(const uint32_t* __restrict__ rows,
+                                                            const uint32_t* __restrict__ cols,
+                                                            const unsigned long long* __restrict__ chunk_beg,
+                                                            const unsigned long long* __restrict__ chunk_end,
+                                                            const double* __restrict__ Qt, int64_t S,
+                                                            const int* __restrict__ ca, const int* __restrict__ cb,
+                                                            int npairs, double* __restrict__ partial) {
+  __shared__ int sa[BI_PAIRS], sb[BI_PAIRS];
+  __shared__ double red[8][BI_PAIRS];
+  if (threadIdx.x < BI_PAIRS) {
+    sa[threadIdx.x] = threadIdx.x < npairs ? ca[threadIdx.x] : 0;
+    sb[threadIdx.x] = threadIdx.x < npairs ? cb[threadIdx.x] : 0;
+  }
+  __syncthreads();
+  double acc[BI_PAIRS];
+#pragma unroll
+  for (int p = 0; p < BI_PAIRS; ++p) acc[p] = 0.0;
+  const unsigned long long e0 = chunk_beg[blockIdx.x], e1 = chunk_end[blockIdx.x];
+  for (unsigned long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+    const double* qr = Qt + S * (int64_t)rows[e];
+    const double* qc = Qt + S * (int64_t)cols[e];
+#pragma unroll
+    for (int p = 0; p < BI_PAIRS; ++p)
+      if (p < npairs) acc[p] += qr[sa[p]] * qc[sb[p]];
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int p = 0; p < BI_PAIRS; ++p) {
+    double v = acc[p];
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[wid][p] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < npairs) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    partial[(int64_t)blockIdx.x * BI_PAIRS + threadIdx.x] = t;
+  }
+}
+
+int ensure_buffer(sdpsr_ctx* ctx, double** p) {
+  if (!*p) {
+    SDPSR_CUDA(cudaMalloc(p, ctx->elems * sizeof(double)));
+    SDPSR_CUDA(cudaMemsetAsync(*p, 0, ctx->elems * sizeof(double), ctx->stream));
+  }
+  return SDPSR_OK;
+}
+
+struct Solver {
+  cusolverDnHandle_t h = nullptr;
+  cusolverDnParams_t params = nullptr;
+  double* d_vals = nullptr;
+};
+
+}  // namespace
+
+void sdpsr_blockdiag_free(sdpsr_ctx* ctx) {
+  if (ctx->solver) {
+    Solver* s = reinterpret_cast<Solver*>(ctx->solver);
+    if (s->params) cusolverDnDestroyParams(s->params);
+    if (s->h) cusolverDnDestroy(s->h);
+    cudaFree(s->d_vals);
+    delete s;
+    ctx->solver = nullptr;
+  }
+  cudaFree(ctx->solver_work);
+  cudaFree(ctx->solver_info);
+  free(ctx->solver_hwork);
+  cudaFree(ctx->Q);
+  cudaFree(ctx->W);
+  cudaFree(ctx->T);
+  cudaFree(ctx->Qhat);
+  ctx->solver_work = nullptr;
+  ctx->solver_info = nullptr;
+  ctx->solver_hwork = nullptr;
+  ctx->Q = ctx->W = ctx->T = ctx->Qhat = nullptr;
+}
+
+#define CTX_ENTER()                 \
+  if (!ctx) return SDPSR_E_INVALID; \
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return ctx->fail(SDPSR_E_CUDA, "cudaSetDevice failed")
+
+static int finish(sdpsr_ctx* ctx) {
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  SDPSR_CUDA(cudaGetLastError());
+  return SDPSR_OK;
+}
+
+static int fill_into(sdpsr_ctx* ctx, const double* r, int64_t len, double* dst) {
+  SDPSR_REQUIRE(len == ctx->dim, SDPSR_E_INVALID, "length(values) != dim(P) (src/partitions.jl:69)");
+  SDPSR_REQUIRE(r != nullptr || len == 0, SDPSR_E_INVALID, "coefficient vector is NULL");
+  SDPSR_TRY(sdpsr_upload_values(ctx, r, len));
+  SDPSR_TRY(sdpsr_build_lut(ctx, ctx->d_values, len));
+  SDPSR_TRY(sdpsr_materialize_fill(ctx, dst));
+  ctx->x_is_fill = false;   // the lut no longer belongs to X
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_eig(sdpsr_ctx* ctx, const double* r1, int64_t len, double* vals) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(vals != nullptr, SDPSR_E_INVALID, "vals is NULL");
+  int sym = 0;
+  SDPSR_TRY(sdpsr_symmetric_check(ctx, &sym));
+  SDPSR_REQUIRE(sym, SDPSR_E_NOT_SYMMETRIC,
+                "partition is not transpose-invariant: no real symmetric eigendecomposition "
+                "(InvalidDecompositionField, src/eigen_decomposition.jl:247-253)");
+  SDPSR_TRY(ensure_buffer(ctx, &ctx->Q));
+  SDPSR_TRY(fill_into(ctx, r1, len, ctx->Q));
+  if (!ctx->solver) {
+    Solver* s = new Solver();
+    ctx->solver = s;
+    SDPSR_REQUIRE(cusolverDnCreate(&s->h) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER, "cusolverDnCreate failed");
+    SDPSR_REQUIRE(cusolverDnSetStream(s->h, ctx->stream) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
+                  "cusolverDnSetStream failed");
+    SDPSR_REQUIRE(cusolverDnCreateParams(&s->params) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
+                  "cusolverDnCreateParams failed");
+    SDPSR_CUDA(cudaMalloc(&s->d_vals, (size_t)ctx->n * sizeof(double)));
+    SDPSR_CUDA(cudaMalloc(&ctx->solver_info, sizeof(int)));
+  }
+  Solver* s = reinterpret_cast<Solver*>(ctx->solver);
+  size_t wdev = 0, whost = 0;
+  SDPSR_REQUIRE(cusolverDnXsyevd_bufferSize(s->h, s->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, ctx->n,
+                                            CUDA_R_64F, ctx->Q, ctx->ld, CUDA_R_64F, s->d_vals, CUDA_R_64F, &wdev,
+                                            &whost) == CUSOLVER_STATUS_SUCCESS,
+                SDPSR_E_CUSOLVER, "cusolverDnXsyevd_bufferSize failed");
+  if (wdev > ctx->solver_work_bytes) {
+    cudaFree(ctx->solver_work);
+    ctx->solver_work = nullptr;
+    SDPSR_CUDA(cudaMalloc(&ctx->solver_work, wdev));
+    ctx->solver_work_bytes = wdev;
+  }
+  if (whost > ctx->solver_hwork_bytes) {
+    free(ctx->solver_hwork);
+    ctx->solver_hwork = malloc(whost);
+    SDPSR_REQUIRE(ctx->solver_hwork != nullptr, SDPSR_E_ALLOC, "host workspace allocation failed");
+    ctx->solver_hwork_bytes = whost;
+  }
+  cusolverStatus_t st;
+  {
+    Timed tm(ctx, SDPSR_K_EIG, 0.0);
+    st = cusolverDnXsyevd(s->h, s->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, ctx->n, CUDA_R_64F, ctx->Q,
+                          ctx->ld, CUDA_R_64F, s->d_vals, CUDA_R_64F, ctx->solver_work, wdev, ctx->solver_hwork, whost,
+                          ctx->solver_info);
+  }
+  SDPSR_REQUIRE(st == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
+                "cusolverDnXsyevd failed (status " + std::to_string((int)st) + ")");
+  int* hinfo = reinterpret_cast<int*>(ctx->h_pinned) + 64;
+  SDPSR_CUDA(cudaMemcpyAsync(hinfo, ctx->solver_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_CUDA(cudaMemcpyAsync(vals, s->d_vals, (size_t)ctx->n * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  SDPSR_TRY(finish(ctx));
+  SDPSR_REQUIRE(*hinfo == 0, SDPSR_E_CUSOLVER, "syevd did not converge (info = " + std::to_string(*hinfo) + ")");
+  ctx->have_Q = true;
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_block_norms(sdpsr_ctx* ctx, const double* r2, int64_t len, const int64_t* ptrs, int64_t nptr,
+                                 double* norms) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(ctx->have_Q, SDPSR_E_STATE, "sdpsr_block_norms must follow sdpsr_eig");
+  SDPSR_REQUIRE(ptrs && nptr >= 2 && norms, SDPSR_E_INVALID, "bad eigenspace pointers");
+  const int64_t ne = nptr - 1, n = ctx->n, ld = ctx->ld;
+  SDPSR_REQUIRE(ptrs[0] == 0 && ptrs[ne] == n, SDPSR_E_INVALID, "ptrs must run from 0 to N");
+  std::vector<uint32_t> space((size_t)n), sdim((size_t)ne);
+  for (int64_t e = 0; e < ne; ++e) {
+    SDPSR_REQUIRE(ptrs[e + 1] > ptrs[e], SDPSR_E_INVALID, "ptrs must be strictly increasing");
+    sdim[(size_t)e] = (uint32_t)(ptrs[e + 1] - ptrs[e]);
+    for (int64_t a = ptrs[e]; a < ptrs[e + 1]; ++a) space[(size_t)a] = (uint32_t)e;
+  }
+  SDPSR_TRY(ensure_buffer(ctx, &ctx->W));
+  SDPSR_TRY(ensure_buffer(ctx, &ctx->T));
+  // A2 = fill(S, r2) -> X ; T = A2 * Q ; X2 = Q' ; W = Q' * T            (:203)
+  SDPSR_TRY(fill_into(ctx, r2, len, ctx->X));
+  ctx->x_valid = false;
+  SDPSR_TRY(sdpsr_gemm_f64(ctx, ctx->X, ld, ctx->Q, ld, ctx->T, ld, ld, n, n, false));
+  const unsigned nb = (unsigned)((n + 31) / 32);
+  if (ld != n) SDPSR_CUDA(cudaMemsetAsync(ctx->X2, 0, ctx->elems * 8, ctx->stream));
+  transpose_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(ctx->Q, ctx->X2, n, ld);
+  count_launch(ctx);
+  SDPSR_TRY(sdpsr_gemm_f64(ctx, ctx->X2, ld, ctx->T, ld, ctx->W, ld, ld, n, n, false));
+  // block maxima
+  uint32_t *d_space = nullptr, *d_sdim = nullptr;
+  unsigned long long* d_norms = nullptr;
+  SDPSR_CUDA(cudaMalloc(&d_space, (size_t)n * 4));
+  SDPSR_CUDA(cudaMalloc(&d_sdim, (size_t)ne * 4));
+  SDPSR_CUDA(cudaMalloc(&d_norms, (size_t)ne * ne * 8));
+  SDPSR_CUDA(cudaMemcpyAsync(d_space, space.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  SDPSR_CUDA(cudaMemcpyAsync(d_sdim, sdim.data(), (size_t)ne * 4, cudaMemcpyHostToDevice, ctx->stream));
+  SDPSR_CUDA(cudaMemsetAsync(d_norms, 0, (size_t)ne * ne * 8, ctx->stream));
+  {
+    Timed tm(ctx, SDPSR_K_MISC, (double)ctx->elems * 8.0);
+    block_max_kernel<<<dim3((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)n), 256, 0, ctx->stream>>>(
+        ctx->W, n, ld, d_space, d_sdim, ne, d_norms);
+    count_launch(ctx);
+  }
+  SDPSR_CUDA(cudaGetLastError());
+  SDPSR_CUDA(cudaMemcpyAsync(norms, d_norms, (size_t)ne * ne * 8, cudaMemcpyDefault, ctx->stream));
+  int st = finish(ctx);
+  cudaFree(d_space);
+  cudaFree(d_sdim);
+  cudaFree(d_norms);
+  SDPSR_TRY(st);
+  // the kernel filled i <= j (bit patterns of non-negative doubles == the doubles); mirror
+  for (int64_t j = 0; j < ne; ++j)
+    for (int64_t i = 0; i < j; ++i) norms[j + ne * i] = norms[i + ne * j];
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_irreducible(sdpsr_ctx* ctx, const double* r3, int64_t len, const int64_t* ptrs, int64_t nptr,
+                                 const int64_t* kroot, double atol, int64_t* blk_sizes, int64_t* nblk) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(ctx->have_Q, SDPSR_E_STATE, "sdpsr_irreducible must follow sdpsr_eig");
+  SDPSR_REQUIRE(ptrs && nptr >= 2 && kroot && blk_sizes && nblk, SDPSR_E_INVALID, "bad arguments");
+  const int64_t ne = nptr - 1, n = ctx->n, ld = ctx->ld;
+  // classes in order of their first (= root) eigenspace                     (:299-309)
+  std::vector<std::vector<int64_t>> classes;
+  std::vector<int64_t> class_of((size_t)ne, -1);
+  for (int64_t e = 0; e < ne; ++e) {
+    const int64_t r = kroot[e];
+    SDPSR_REQUIRE(r >= 0 && r <= e && kroot[r] == r, SDPSR_E_INVALID,
+                  "kroot[e] must be the smallest member of e's class (src/eigen_decomposition.jl:310)");
+    if (r == e) {
+      class_of[(size_t)e] = (int64_t)classes.size();
+      classes.emplace_back();
+    }
+    classes[(size_t)class_of[(size_t)r]].push_back(e);
+    class_of[(size_t)e] = class_of[(size_t)r];
+  }
+  int64_t S = 0;
+  for (auto& k : classes) S += (int64_t)k.size();
+  // Qhat buffer (ld x S)
+  cudaFree(ctx->Qhat);
+  ctx->Qhat = nullptr;
+  SDPSR_CUDA(cudaMalloc(&ctx->Qhat, (size_t)ld * (size_t)S * 8));
+  SDPSR_CUDA(cudaMemsetAsync(ctx->Qhat, 0, (size_t)ld * (size_t)S * 8, ctx->stream));
+  ctx->qhat_cols = S;
+  ctx->blk_sizes.clear();
+  // first columns, and the list of (root, member) pairs that need work
+  std::vector<int64_t> first_src, first_dst;     // Qhat[:, dst] = Q[:, src]
+  std::vector<int64_t> fcols;                    // eigenvector columns whose image under A3 is needed
+  std::vector<int64_t> findex((size_t)ne, -1);
+  struct Pair { int64_t i, j, dst; };
+  std::vector<Pair> pairs;
+  int64_t col = 0;
+  for (auto& k : classes) {
+    ctx->blk_sizes.push_back((int64_t)k.size());
+    first_src.push_back(ptrs[k[0]]);
+    first_dst.push_back(col);
+    if (k.size() > 1) {
+      for (int64_t e : k)
+        if (findex[(size_t)e] < 0) {
+          findex[(size_t)e] = (int64_t)fcols.size();
+          fcols.push_back(ptrs[e]);
+        }
+      for (size_t t = 1; t < k.size(); ++t) {
+        SDPSR_REQUIRE(ptrs[k[t] + 1] - ptrs[k[t]] == ptrs[k[0] + 1] - ptrs[k[0]], SDPSR_E_INVALID,
+                      "isomorphic eigenspaces must have equal dimension");
+        pairs.push_back(Pair{k[0], k[t], col + (int64_t)t});
+      }
+    }
+    col += (int64_t)k.size();
+  }
+  *nblk = (int64_t)classes.size();
+  for (size_t k = 0; k < classes.size(); ++k) blk_sizes[k] = ctx->blk_sizes[k];
+
+  // first column of every block = first eigenvector of the root eigenspace   (:311-314)
+  for (size_t f = 0; f < first_src.size(); ++f)
+    SDPSR_CUDA(cudaMemcpyAsync(ctx->Qhat + ld * first_dst[f], ctx->Q + ld * first_src[f], (size_t)ld * 8,
+                               cudaMemcpyDeviceToDevice, ctx->stream));
+
+  // draw #3 is consumed whether or not it is needed, like the reference (:306)
+  SDPSR_REQUIRE(len == ctx->dim, SDPSR_E_INVALID, "length(values) != dim(P) (src/partitions.jl:69)");
+  if (!pairs.empty()) {
+    SDPSR_TRY(ensure_buffer(ctx, &ctx->T));
+    SDPSR_TRY(ensure_buffer(ctx, &ctx->W));
+    SDPSR_TRY(fill_into(ctx, r3, len, ctx->X));          // A3
+    ctx->x_valid = false;
+    const int64_t nf = (int64_t)fcols.size();
+    SDPSR_REQUIRE(nf <= n, SDPSR_E_INVALID, "internal: too many first vectors");
+    int64_t* d_fcols = nullptr;
+    SDPSR_CUDA(cudaMalloc(&d_fcols, (size_t)nf * 8));
+    SDPSR_CUDA(cudaMemcpyAsync(d_fcols, fcols.data(), (size_t)nf * 8, cudaMemcpyHostToDevice, ctx->stream));
+    // F = Q[:, fcols]  (into W), V = A3 * F (into T)
+    gather_cols_kernel<<<dim3((unsigned)std::min<int64_t>((ld + 255) / 256, 64), (unsigned)nf), 256, 0, ctx->stream>>>(
+        ctx->Q, ld, d_fcols, ctx->W);
+    count_launch(ctx);
+    SDPSR_TRY(sdpsr_gemm_f64(ctx, ctx->X, ld, ctx->W, ld, ctx->T, ld, ld, nf, n, false));
+    // per pair: u = Q_j' v_i, w = Q_i' v_j, column = Q_j u / ||w||          (:327-336)
+    const int64_t np = (int64_t)pairs.size();
+    int64_t maxm = 1;
+    std::vector<int64_t> h((size_t)np * 6);
+    for (int64_t p = 0; p < np; ++p) {
+      const Pair& pr = pairs[(size_t)p];
+      const int64_t mlt = ptrs[pr.i + 1] - ptrs[pr.i];
+      maxm = std::max(maxm, mlt);
+      h[(size_t)p] = ptrs[pr.j];                        // qcol for u  (Q_j)
+      h[(size_t)(np + p)] = findex[(size_t)pr.i];       // vcol for u  (v_i)
+      h[(size_t)(2 * np + p)] = ptrs[pr.i];             // qcol for w  (Q_i)
+      h[(size_t)(3 * np + p)] = findex[(size_t)pr.j];   // vcol for w  (v_j)
+      h[(size_t)(4 * np + p)] = mlt;
+      h[(size_t)(5 * np + p)] = pr.dst;
+    }
+    int64_t* d_h = nullptr;
+    double* d_uw = nullptr;
+    SDPSR_CUDA(cudaMalloc(&d_h, h.size() * 8));
+    SDPSR_CUDA(cudaMalloc(&d_uw, (size_t)np * (size_t)maxm * 2 * 8));
+    SDPSR_CUDA(cudaMemcpyAsync(d_h, h.data(), h.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    double* d_u = d_uw;
+    double* d_w = d_uw + np * maxm;
+    SDPSR_REQUIRE(np <= 65535, SDPSR_E_UNSUPPORTED, "more than 65535 isomorphic eigenspace pairs");
+    pair_dot_kernel<<<dim3((unsigned)maxm, (unsigned)np), 256, 0, ctx->stream>>>(ctx->Q, ctx->T, n, ld, d_h, d_h + np,
+                                                                                  d_h + 4 * np, maxm, d_u);
+    pair_dot_kernel<<<dim3((unsigned)maxm, (unsigned)np), 256, 0, ctx->stream>>>(ctx->Q, ctx->T, n, ld, d_h + 2 * np,
+                                                                                  d_h + 3 * np, d_h + 4 * np, maxm, d_w);
+    pair_combine_kernel<<<dim3((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)np), 256, 0, ctx->stream>>>(
+        ctx->Q, n, ld, d_h, d_h + 4 * np, maxm, d_u, d_w, d_h + 5 * np, ctx->Qhat);
+    count_launch(ctx, 3);
+    SDPSR_CUDA(cudaGetLastError());
+    SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_h);
+    cudaFree(d_uw);
+    cudaFree(d_fcols);
+  }
+  // clamptol!.(Q_hat, atol)                                                  (src/diagonalize.jl:39)
+  {
+    const uint64_t total = (uint64_t)ld * (uint64_t)S;
+    const int grid = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    clamp_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->Qhat, total, atol);
+    count_launch(ctx);
+  }
+  return finish(ctx);
+}
+
+extern "C" int sdpsr_get_qhat(sdpsr_ctx* ctx, double* qhat, int64_t len) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(ctx->Qhat && qhat, SDPSR_E_STATE, "no Qhat (call sdpsr_irreducible first)");
+  SDPSR_REQUIRE(len == ctx->n * ctx->qhat_cols, SDPSR_E_INVALID, "len must be N * sum(blk_sizes)");
+  SDPSR_CUDA(cudaMemcpy2DAsync(qhat, (size_t)ctx->n * 8, ctx->Qhat, (size_t)ctx->ld * 8, (size_t)ctx->n * 8,
+                               (size_t)ctx->qhat_cols, cudaMemcpyDefault, ctx->stream));
+  return finish(ctx);
+}
+
+extern "C" int sdpsr_set_qhat(sdpsr_ctx* ctx, const double* qhat, const int64_t* blk_sizes, int64_t nblk) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(qhat && blk_sizes && nblk >= 1, SDPSR_E_INVALID, "bad arguments");
+  int64_t S = 0;
+  ctx->blk_sizes.assign(blk_sizes, blk_sizes + nblk);
+  for (int64_t k = 0; k < nblk; ++k) {
+    SDPSR_REQUIRE(blk_sizes[k] >= 1, SDPSR_E_INVALID, "block sizes must be positive");
+    S += blk_sizes[k];
+  }
+  cudaFree(ctx->Qhat);
+  ctx->Qhat = nullptr;
+  SDPSR_CUDA(cudaMalloc(&ctx->Qhat, (size_t)ctx->ld * (size_t)S * 8));
+  SDPSR_CUDA(cudaMemsetAsync(ctx->Qhat, 0, (size_t)ctx->ld * (size_t)S * 8, ctx->stream));
+  SDPSR_CUDA(cudaMemcpy2DAsync(ctx->Qhat, (size_t)ctx->ld * 8, qhat, (size_t)ctx->n * 8, (size_t)ctx->n * 8, (size_t)S,
+                               cudaMemcpyDefault, ctx->stream));
+  ctx->qhat_cols = S;
+  return finish(ctx);
+}
+
+// basis_image (src/diagonalize.jl:64-89)
+extern "C" int sdpsr_basis_image(sdpsr_ctx* ctx, double atol, double* out, int64_t out_len) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(ctx->Qhat && out, SDPSR_E_STATE, "no Qhat (call sdpsr_irreducible first)");
+  const int64_t n = ctx->n, ld = ctx->ld, S = ctx->qhat_cols, d = ctx->dim;
+  int64_t Sq = 0;
+  for (int64_t s : ctx->blk_sizes) Sq += s * s;
+  SDPSR_REQUIRE(out_len == d * Sq, SDPSR_E_INVALID, "out_len must be dim * sum(s_k^2)");
+  if (d == 0) return SDPSR_OK;
+  KeyTable& t = ctx->tab[ctx->cur];
+  // ---- CSR by canonical label (_constraints, :42-50) --------------------------------------
+  unsigned long long* d_cnt = nullptr;
+  SDPSR_CUDA(cudaMalloc(&d_cnt, ((size_t)d + 2) * 8));
+  SDPSR_CUDA(cudaMemsetAsync(d_cnt, 0, ((size_t)d + 2) * 8, ctx->stream));
+  const dim3 g2((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)n);
+  class_count_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->labels, t.rank, n, ld, d_cnt);
+  count_launch(ctx);
+  std::vector<unsigned long long> cnt((size_t)d + 2);
+  SDPSR_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, cnt.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<unsigned long long> start((size_t)d + 2, 0);
+  for (int64_t i = 1; i <= d; ++i) start[(size_t)i + 1] = start[(size_t)i] + cnt[(size_t)i];
+  const unsigned long long nent = start[(size_t)d + 1];
+  SDPSR_CUDA(cudaMemcpyAsync(d_cnt, start.data(), start.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  uint32_t* d_rc = nullptr;
+  SDPSR_CUDA(cudaMalloc(&d_rc, std::max<size_t>(1, (size_t)nent) * 8));
+  uint32_t* d_rows = d_rc;
+  uint32_t* d_cols = d_rc + nent;
+  class_scatter_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->labels, t.rank, n, ld, d_cnt, d_rows, d_cols);
+  count_launch(ctx);
+  // chunks: class i owns chunks [cstart[i], cstart[i+1])
+  std::vector<unsigned long long> cbeg, cend;
+  std::vector<int64_t> cstart((size_t)d + 2, 0);
+  for (int64_t i = 1; i <= d; ++i) {
+    cstart[(size_t)i] = (int64_t)cbeg.size();
+    for (unsigned long long e = start[(size_t)i]; e < start[(size_t)i + 1]; e += BI_CHUNK) {
+      cbeg.push_back(e);
+      cend.push_back(std::min<unsigned long long>(e + BI_CHUNK, start[(size_t)i + 1]));
+    }
+  }
+  cstart[(size_t)d + 1] = (int64_t)cbeg.size();
+  const int64_t nchunks = (int64_t)cbeg.size();
+  unsigned long long* d_cb = nullptr;
+  double* d_part = nullptr;
+  double* d_qt = nullptr;
+  int* d_pairs = nullptr;
+  SDPSR_CUDA(cudaMalloc(&d_cb, std::max<size_t>(1, (size_t)nchunks) * 16));
+  SDPSR_CUDA(cudaMalloc(&d_part, std::max<size_t>(1, (size_t)nchunks) * BI_PAIRS * 8));
+  SDPSR_CUDA(cudaMalloc(&d_qt, (size_t)n * (size_t)S * 8));
+  SDPSR_CUDA(cudaMalloc(&d_pairs, 2 * BI_PAIRS * sizeof(int)));
+  SDPSR_CUDA(cudaMemcpyAsync(d_cb, cbeg.data(), (size_t)nchunks * 8, cudaMemcpyHostToDevice, ctx->stream));
+  SDPSR_CUDA(cudaMemcpyAsync(d_cb + nchunks, cend.data(), (size_t)nchunks * 8, cudaMemcpyHostToDevice, ctx->stream));
+  qhat_rowmajor_kernel<<<dim3((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)S), 256, 0, ctx->stream>>>(
+      ctx->Qhat, n, ld, S, d_qt);
+  count_launch(ctx);
+  // ---- all output elements (k, a, b) as pairs of Qhat columns, BI_PAIRS at a time ----------
+  std::vector<int> pa, pb;
+  std::vector<int64_t> poff;   // offset of (k,a,b) inside one class's packed record
+  {
+    int64_t colbase = 0, off = 0;
+    for (int64_t s : ctx->blk_sizes) {
+      for (int64_t b = 0; b < s; ++b)
+        for (int64_t a = 0; a < s; ++a) {   // column-major s x s: element (a,b) at a + s*b
+          pa.push_back((int)(colbase + a));
+          pb.push_back((int)(colbase + b));
+          poff.push_back(off + a + s * b);
+        }
+      colbase += s;
+      off += s * s;
+    }
+  }
+  std::vector<double> part((size_t)std::max<int64_t>(1, nchunks) * BI_PAIRS);
+  std::vector<double> result((size_t)(d * Sq), 0.0);
+  int status = SDPSR_OK;
+  for (size_t p0 = 0; p0 < pa.size() && status == SDPSR_OK; p0 += BI_PAIRS) {
+    const int np = (int)std::min<size_t>(BI_PAIRS, pa.size() - p0);
+    int hp[2 * BI_PAIRS] = {0};
+    for (int p = 0; p < np; ++p) {
+      hp[p] = pa[p0 + p];
+      hp[BI_PAIRS + p] = pb[p0 + p];
+    }
+    cudaMemcpyAsync(d_pairs, hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream);
+    if (nchunks) {
+      Timed tm(ctx, SDPSR_K_BASIS, (double)nent * (8.0 + 16.0 * np));
+      basis_partial_kernel<<<(unsigned)nchunks, 256, 0, ctx->stream>>>(d_rows, d_cols, d_cb, d_cb + nchunks, d_qt, S,
+                                                                      d_pairs, d_pairs + BI_PAIRS, np, d_part);
+      count_launch(ctx);
+    }
+    cudaMemcpyAsync(part.data(), d_part, (size_t)nchunks * BI_PAIRS * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      status = ctx->fail(SDPSR_E_CUDA, "basis_image kernel failed");
+      break;
+    }
+    for (int64_t i = 1; i <= d; ++i)
+      for (int p = 0; p < np; ++p) {
+        double s = 0.0;
+        for (int64_t c = cstart[(size_t)i]; c < cstart[(size_t)i + 1]; ++c) s += part[(size_t)c * BI_PAIRS + p];
+        if (std::fabs(s) < atol) s = 0.0;                  // clamptol!, :85
+        result[(size_t)((i - 1) * Sq + poff[p0 + p])] = s;
+      }
+  }
+  cudaFree(d_cnt);
+  cudaFree(d_rc);
+  cudaFree(d_cb);
+  cudaFree(d_part);
+  cudaFree(d_qt);
+  cudaFree(d_pairs);
+  SDPSR_TRY(status);
+  SDPSR_CUDA(cudaMemcpy(out, result.data(), result.size() * 8, cudaMemcpyDefault));
+  return finish(ctx);
+}

@@ -1,0 +1,89 @@
+// comm.cu -- multi-GPU plumbing: one context per process / GPU, NCCL loaded with dlopen
+// so that single-GPU users need no NCCL at all.  The reference has no distributed code;
+// this is new surface.
+#include <dlfcn.h>
+
+#include <cstring>
+
+#include "sdpsr_internal.cuh"
+
+namespace {
+
+struct ncclUniqueIdLike {
+  char internal[128];
+};
+typedef void* ncclComm_t;
+typedef int ncclResult_t;
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueIdLike*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueIdLike, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+NcclApi& api() {
+  static NcclApi a;
+  if (a.lib) return a;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nme : names) {
+    a.lib = dlopen(nme, RTLD_NOW | RTLD_GLOBAL);
+    if (a.lib) break;
+  }
+  if (!a.lib) return a;
+  a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.lib, "ncclGetUniqueId");
+  a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.lib, "ncclCommInitRank");
+  a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
+  a.AllGather = (decltype(a.AllGather))dlsym(a.lib, "ncclAllGather");
+  a.AllReduce = (decltype(a.AllReduce))dlsym(a.lib, "ncclAllReduce");
+  a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
+  a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.AllReduce;
+  return a;
+}
+
+}  // namespace
+
+void sdpsr_comm_free(sdpsr_ctx* ctx) {
+  if (ctx->nccl && api().ok) api().CommDestroy((ncclComm_t)ctx->nccl);
+  ctx->nccl = nullptr;
+  ctx->nranks = 1;
+  ctx->rank = 0;
+}
+
+extern "C" int sdpsr_comm_unique_id(void* id128) {
+  if (!id128) return SDPSR_E_INVALID;
+  if (!api().ok) return SDPSR_E_NCCL;
+  ncclUniqueIdLike id;
+  if (api().GetUniqueId(&id) != 0) return SDPSR_E_NCCL;
+  std::memcpy(id128, &id, 128);
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_comm_init(sdpsr_ctx* ctx, int nranks, int rank, const void* id128) {
+  if (!ctx) return SDPSR_E_INVALID;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return ctx->fail(SDPSR_E_CUDA, "cudaSetDevice failed");
+  SDPSR_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks && id128, SDPSR_E_INVALID, "bad communicator arguments");
+  SDPSR_REQUIRE(api().ok, SDPSR_E_NCCL, "libnccl.so.2 could not be loaded");
+  sdpsr_comm_free(ctx);
+  ncclUniqueIdLike id;
+  std::memcpy(&id, id128, 128);
+  ncclComm_t comm = nullptr;
+  const ncclResult_t r = api().CommInitRank(&comm, nranks, id, rank);
+  SDPSR_REQUIRE(r == 0, SDPSR_E_NCCL,
+                std::string("ncclCommInitRank failed: ") + (api().GetErrorString ? api().GetErrorString(r) : "?"));
+  ctx->nccl = comm;
+  ctx->nranks = nranks;
+  ctx->rank = rank;
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_comm_info(sdpsr_ctx* ctx, int* nranks, int* rank) {
+  if (!ctx) return SDPSR_E_INVALID;
+  if (nranks) *nranks = ctx->nranks;
+  if (rank) *rank = ctx->rank;
+  return SDPSR_OK;
+}

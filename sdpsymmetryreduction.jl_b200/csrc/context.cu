@@ -1,0 +1,484 @@
+// context.cu -- lifetime, buffers, host<->device staging and the Partition part of
+// the C ABI (include/sdpsr.h).  Reference sites are cited per entry point there.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "sdpsr_internal.cuh"
+
+static thread_local std::string g_create_error;
+
+// ---------------------------------------------------------------------------
+// timing
+// ---------------------------------------------------------------------------
+static cudaEvent_t take_event(sdpsr_ctx* c) {
+  if (!c->ev_pool.empty()) {
+    cudaEvent_t e = c->ev_pool.back();
+    c->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+static void drain_events(sdpsr_ctx* c) {
+  if (c->ev_pending.empty()) return;
+  cudaStreamSynchronize(c->stream);
+  for (auto& p : c->ev_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      c->t_ms[p.family] += ms;
+      c->t_launch[p.family] += 1;
+      c->t_work[p.family] += p.work;
+    }
+    c->ev_pool.push_back(p.a);
+    c->ev_pool.push_back(p.b);
+  }
+  c->ev_pending.clear();
+}
+
+Timed::Timed(sdpsr_ctx* ctx, int family, double work_) : c(ctx), fam(family), work(work_) {
+  if (c->flags & SDPSR_F_TIMING) {
+    a = take_event(c);
+    b = take_event(c);
+    cudaEventRecord(a, c->stream);
+  }
+}
+Timed::~Timed() {
+  if (a) {
+    cudaEventRecord(b, c->stream);
+    c->ev_pending.push_back(EventPair{a, b, fam, work});
+    if (c->ev_pending.size() > 4096) drain_events(c);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// small kernels for staging
+// ---------------------------------------------------------------------------
+namespace {
+
+template <typename T>
+__global__ void labels_in_kernel(const T* __restrict__ src, uint32_t* __restrict__ dst, int64_t n, int64_t ld,
+                                 uint32_t* __restrict__ bad) {
+  const int64_t j = blockIdx.y;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ld; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t v = 0u;
+    if (i < n) {
+      const long long s = (long long)src[i + n * j];
+      if (s < 0 || s > 0xfffffffell) {
+        *bad = 1u;
+      } else {
+        v = (uint32_t)s;
+      }
+    }
+    dst[i + ld * j] = v;
+  }
+}
+
+template <typename T>
+__global__ void labels_out_kernel(const uint32_t* __restrict__ src, T* __restrict__ dst, int64_t total,
+                                  uint64_t maxval, uint32_t* __restrict__ bad) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t v = src[i];
+    if ((uint64_t)v > maxval) *bad = 1u;
+    dst[i] = (T)v;
+  }
+}
+
+__global__ void count_zero_kernel(const uint32_t* __restrict__ labels, int64_t n, int64_t ld,
+                                  unsigned long long* __restrict__ out) {
+  const int64_t j = blockIdx.y;
+  unsigned long long c = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    c += labels[i + ld * j] == 0u ? 1ull : 0ull;
+  for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------
+extern "C" int sdpsr_version(void) { return SDPSR_VERSION; }
+
+extern "C" const char* sdpsr_last_error(const sdpsr_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int sdpsr_device_count(int* count) {
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (count) *count = (e == cudaSuccess) ? c : 0;
+  return e == cudaSuccess ? SDPSR_OK : SDPSR_E_NO_DEVICE;
+}
+
+static int create_impl(sdpsr_ctx* ctx) {
+  SDPSR_CUDA(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  SDPSR_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+  ctx->sm_count = prop.multiProcessorCount;
+  SDPSR_REQUIRE(prop.major >= 10, SDPSR_E_UNSUPPORTED,
+                std::string("libsdpsr_cuda is built for sm_100a only; device is ") + prop.name);
+  SDPSR_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  const size_t e = ctx->elems;
+  SDPSR_CUDA(cudaMalloc(&ctx->labels, e * sizeof(uint32_t)));
+  SDPSR_CUDA(cudaMalloc(&ctx->labels_alt, e * sizeof(uint32_t)));
+  SDPSR_CUDA(cudaMalloc(&ctx->X, e * sizeof(double)));
+  SDPSR_CUDA(cudaMalloc(&ctx->X2, e * sizeof(double)));
+  SDPSR_CUDA(cudaMalloc(&ctx->d_scalars, 64 * sizeof(uint64_t)));
+  SDPSR_CUDA(cudaMallocHost(&ctx->h_pinned, 4096));
+  SDPSR_CUDA(cudaMemsetAsync(ctx->X, 0, e * sizeof(double), ctx->stream));
+  SDPSR_CUDA(cudaMemsetAsync(ctx->X2, 0, e * sizeof(double), ctx->stream));
+  SDPSR_CUDA(cudaMemsetAsync(ctx->labels_alt, 0, e * sizeof(uint32_t), ctx->stream));
+  return sdpsr_partition_reset(ctx);
+}
+
+extern "C" int sdpsr_create(sdpsr_ctx** out, int64_t n, int device, uint32_t flags) {
+  if (!out) return SDPSR_E_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    g_create_error = "no CUDA device visible: libsdpsr_cuda has no CPU fallback";
+    cudaGetLastError();
+    return SDPSR_E_NO_DEVICE;
+  }
+  if (n < 1 || n > 65520 || device < 0 || device >= ndev) {
+    g_create_error = "sdpsr_create: need 1 <= n <= 65520 and a valid device index";
+    return SDPSR_E_INVALID;
+  }
+  sdpsr_ctx* ctx = new sdpsr_ctx();
+  ctx->device = device;
+  ctx->n = n;
+  ctx->ld = round_up(n, 16);
+  ctx->elems = (size_t)ctx->ld * (size_t)n;
+  ctx->flags = flags;
+  const int st = create_impl(ctx);
+  if (st != SDPSR_OK) {
+    g_create_error = ctx->err;
+    sdpsr_destroy(ctx);
+    return st;
+  }
+  *out = ctx;
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_destroy(sdpsr_ctx* ctx) {
+  if (!ctx) return SDPSR_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  drain_events(ctx);
+  for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+  sdpsr_comm_free(ctx);
+  sdpsr_blockdiag_free(ctx);
+  sdpsr_constraints_free(ctx);
+  sdpsr_table_free(ctx->tab[0]);
+  sdpsr_table_free(ctx->tab[1]);
+  cudaFree(ctx->labels);
+  cudaFree(ctx->labels_alt);
+  cudaFree(ctx->labels_tmp);
+  cudaFree(ctx->X);
+  cudaFree(ctx->X2);
+  cudaFree(ctx->lut);
+  cudaFree(ctx->d_values);
+  cudaFree(ctx->rk_mi);
+  cudaFree(ctx->bitmap);
+  cudaFree(ctx->bm_block);
+  cudaFree(ctx->d_scalars);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return SDPSR_OK;
+}
+
+#define CTX_ENTER()                                   \
+  if (!ctx) return SDPSR_E_INVALID;                   \
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return ctx->fail(SDPSR_E_CUDA, "cudaSetDevice failed")
+
+static int finish(sdpsr_ctx* ctx) {
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  SDPSR_CUDA(cudaGetLastError());
+  return SDPSR_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Partition state
+// ---------------------------------------------------------------------------
+extern "C" int sdpsr_partition_reset(sdpsr_ctx* ctx) {
+  CTX_ENTER();
+  SDPSR_CUDA(cudaMemsetAsync(ctx->labels, 0, ctx->elems * sizeof(uint32_t), ctx->stream));
+  KeyTable& t = ctx->tab[ctx->cur];
+  SDPSR_TRY(sdpsr_table_alloc(ctx, t, 64));
+  SDPSR_CUDA(cudaMemsetAsync(t.keys, 0xff, (size_t)t.cap * 12, ctx->stream));
+  SDPSR_CUDA(cudaMemsetAsync(t.meta, 0, 4 * sizeof(uint32_t), ctx->stream));
+  SDPSR_CUDA(cudaMemsetAsync(t.rank, 0, sizeof(uint32_t), ctx->stream));
+  t.count = 0;
+  ctx->dim = 0;
+  ctx->x_is_fill = false;
+  ctx->x_valid = false;
+  return finish(ctx);
+}
+
+static int stage_labels(sdpsr_ctx* ctx, const void* labels, int elt_bytes) {
+  SDPSR_REQUIRE(labels != nullptr, SDPSR_E_INVALID, "labels is NULL");
+  SDPSR_REQUIRE(elt_bytes == 1 || elt_bytes == 2 || elt_bytes == 4 || elt_bytes == 8, SDPSR_E_INVALID,
+                "elt_bytes must be 1, 2, 4 or 8");
+  SDPSR_TRY(sdpsr_ensure_tmp_labels(ctx));
+  const size_t nn = (size_t)ctx->n * (size_t)ctx->n;
+  void* raw = ctx->X2;   // staging: X2 holds no state between calls that matter here
+  SDPSR_CUDA(cudaMemcpyAsync(raw, labels, nn * elt_bytes, cudaMemcpyDefault, ctx->stream));
+  uint32_t* bad = ctx->d_scalars;
+  SDPSR_CUDA(cudaMemsetAsync(bad, 0, sizeof(uint32_t), ctx->stream));
+  dim3 grid((unsigned)std::min<int64_t>((ctx->ld + 255) / 256, 64), (unsigned)ctx->n);
+  // 8-byte inputs are read as signed (Julia Int64); negative labels are rejected
+  switch (elt_bytes) {
+    case 1: labels_in_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)raw, ctx->labels_tmp, ctx->n, ctx->ld, bad); break;
+    case 2: labels_in_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>((const uint16_t*)raw, ctx->labels_tmp, ctx->n, ctx->ld, bad); break;
+    case 4: labels_in_kernel<uint32_t><<<grid, 256, 0, ctx->stream>>>((const uint32_t*)raw, ctx->labels_tmp, ctx->n, ctx->ld, bad); break;
+    default: labels_in_kernel<int64_t><<<grid, 256, 0, ctx->stream>>>((const int64_t*)raw, ctx->labels_tmp, ctx->n, ctx->ld, bad); break;
+  }
+  count_launch(ctx);
+  SDPSR_CUDA(cudaGetLastError());
+  uint32_t* hb = reinterpret_cast<uint32_t*>(ctx->h_pinned) + 16;
+  SDPSR_CUDA(cudaMemcpyAsync(hb, bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  SDPSR_REQUIRE(*hb == 0u, SDPSR_E_INVALID, "labels must be integers in 0 .. 2^32-2 (src/partitions.jl:46)");
+  // X2 was used as staging: restore its zero padding contract lazily (it is fully overwritten by
+  // the next product), and forget whatever it held.
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_partition_set_labels(sdpsr_ctx* ctx, const void* labels, int elt_bytes, int64_t* dim) {
+  CTX_ENTER();
+  SDPSR_TRY(stage_labels(ctx, labels, elt_bytes));
+  RefineSpec sp;
+  sp.mode = KM_PAIR;
+  sp.lab2 = ctx->labels_tmp;
+  sp.ignore_labels = true;
+  sp.do_round = false;
+  SDPSR_TRY(sdpsr_refine_pass(ctx, sp, dim));
+  ctx->x_valid = false;
+  return finish(ctx);
+}
+
+extern "C" int sdpsr_refine_labels(sdpsr_ctx* ctx, const void* labels, int elt_bytes, int64_t* dim) {
+  CTX_ENTER();
+  SDPSR_TRY(stage_labels(ctx, labels, elt_bytes));
+  RefineSpec sp;
+  sp.mode = KM_PAIR;
+  sp.lab2 = ctx->labels_tmp;
+  sp.do_round = false;
+  SDPSR_TRY(sdpsr_refine_pass(ctx, sp, dim));
+  return finish(ctx);
+}
+
+extern "C" int sdpsr_partition_get_labels(sdpsr_ctx* ctx, void* labels, int elt_bytes) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(labels != nullptr, SDPSR_E_INVALID, "labels is NULL");
+  SDPSR_REQUIRE(elt_bytes == 1 || elt_bytes == 2 || elt_bytes == 4 || elt_bytes == 8, SDPSR_E_INVALID,
+                "elt_bytes must be 1, 2, 4 or 8");
+  SDPSR_TRY(sdpsr_ensure_tmp_labels(ctx));
+  const int64_t nn = ctx->n * ctx->n;
+  SDPSR_TRY(sdpsr_canonical_labels(ctx, ctx->labels_tmp));
+  if (elt_bytes == 4) {
+    SDPSR_CUDA(cudaMemcpyAsync(labels, ctx->labels_tmp, (size_t)nn * 4, cudaMemcpyDefault, ctx->stream));
+    return finish(ctx);
+  }
+  // the reference throws InexactError as soon as a label exceeds typemax(T)
+  const uint64_t maxval = elt_bytes == 1 ? 0xffull : elt_bytes == 2 ? 0xffffull : ~0ull;
+  SDPSR_REQUIRE((uint64_t)ctx->dim <= maxval, SDPSR_E_LABEL_OVERFLOW,
+                "dim(P) does not fit the requested label type (InexactError in the reference)");
+  uint32_t* bad = ctx->d_scalars;
+  SDPSR_CUDA(cudaMemsetAsync(bad, 0, sizeof(uint32_t), ctx->stream));
+  void* raw = ctx->X2;
+  const int grid = (int)std::min<int64_t>((nn + 255) / 256, (int64_t)ctx->sm_count * 8);
+  switch (elt_bytes) {
+    case 1: labels_out_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(ctx->labels_tmp, (uint8_t*)raw, nn, maxval, bad); break;
+    case 2: labels_out_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(ctx->labels_tmp, (uint16_t*)raw, nn, maxval, bad); break;
+    default: labels_out_kernel<uint64_t><<<grid, 256, 0, ctx->stream>>>(ctx->labels_tmp, (uint64_t*)raw, nn, maxval, bad); break;
+  }
+  count_launch(ctx);
+  SDPSR_CUDA(cudaGetLastError());
+  SDPSR_CUDA(cudaMemcpyAsync(labels, raw, (size_t)nn * elt_bytes, cudaMemcpyDefault, ctx->stream));
+  return finish(ctx);
+}
+
+extern "C" int sdpsr_partition_dim(sdpsr_ctx* ctx, int64_t* dim) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(dim != nullptr, SDPSR_E_INVALID, "dim is NULL");
+  *dim = ctx->dim;
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_partition_zero_count(sdpsr_ctx* ctx, int64_t* count) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(count != nullptr, SDPSR_E_INVALID, "count is NULL");
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 2);
+  SDPSR_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream));
+  dim3 grid((unsigned)std::min<int64_t>((ctx->n + 255) / 256, 64), (unsigned)ctx->n);
+  count_zero_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->labels, ctx->n, ctx->ld, d);
+  count_launch(ctx);
+  unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_pinned) + 16;
+  SDPSR_CUDA(cudaMemcpyAsync(h, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_TRY(finish(ctx));
+  *count = (int64_t)*h;
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_partition_is_symmetric(sdpsr_ctx* ctx, int* is_symmetric) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(is_symmetric != nullptr, SDPSR_E_INVALID, "is_symmetric is NULL");
+  return sdpsr_symmetric_check(ctx, is_symmetric);
+}
+
+// ---------------------------------------------------------------------------
+// dense matrix staging
+// ---------------------------------------------------------------------------
+static int matrix_ptr(sdpsr_ctx* ctx, int which, double** p) {
+  switch (which) {
+    case SDPSR_MAT_X: *p = ctx->X; break;
+    case SDPSR_MAT_X2: *p = ctx->X2; break;
+    case SDPSR_MAT_Q: *p = ctx->Q; break;
+    case SDPSR_MAT_W: *p = ctx->W; break;
+    default: return ctx->fail(SDPSR_E_INVALID, "unknown matrix id");
+  }
+  if (!*p) {
+    // Q and W are allocated on first use
+    double** slot = which == SDPSR_MAT_Q ? &ctx->Q : &ctx->W;
+    SDPSR_CUDA(cudaMalloc(slot, ctx->elems * sizeof(double)));
+    SDPSR_CUDA(cudaMemsetAsync(*slot, 0, ctx->elems * sizeof(double), ctx->stream));
+    *p = *slot;
+  }
+  return SDPSR_OK;
+}
+
+static int upload_matrix(sdpsr_ctx* ctx, double* dst, const double* src) {
+  if (ctx->ld != ctx->n) SDPSR_CUDA(cudaMemsetAsync(dst, 0, ctx->elems * sizeof(double), ctx->stream));
+  SDPSR_CUDA(cudaMemcpy2DAsync(dst, (size_t)ctx->ld * 8, src, (size_t)ctx->n * 8, (size_t)ctx->n * 8, (size_t)ctx->n,
+                               cudaMemcpyDefault, ctx->stream));
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_get_matrix(sdpsr_ctx* ctx, int which, double* out) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(out != nullptr, SDPSR_E_INVALID, "out is NULL");
+  double* p = nullptr;
+  SDPSR_TRY(matrix_ptr(ctx, which, &p));
+  if (which == SDPSR_MAT_X) {
+    SDPSR_REQUIRE(ctx->x_valid, SDPSR_E_STATE, "X is not defined yet (call sdpsr_fill first)");
+    if (ctx->x_is_fill) SDPSR_TRY(sdpsr_materialize_fill(ctx, ctx->X));
+  }
+  SDPSR_CUDA(cudaMemcpy2DAsync(out, (size_t)ctx->n * 8, p, (size_t)ctx->ld * 8, (size_t)ctx->n * 8, (size_t)ctx->n,
+                               cudaMemcpyDefault, ctx->stream));
+  return finish(ctx);
+}
+
+extern "C" int sdpsr_set_matrix(sdpsr_ctx* ctx, int which, const double* in) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(in != nullptr, SDPSR_E_INVALID, "in is NULL");
+  double* p = nullptr;
+  SDPSR_TRY(matrix_ptr(ctx, which, &p));
+  SDPSR_TRY(upload_matrix(ctx, p, in));
+  if (which == SDPSR_MAT_X) {
+    ctx->x_valid = true;
+    ctx->x_is_fill = false;
+  }
+  return finish(ctx);
+}
+
+extern "C" int sdpsr_gemm(sdpsr_ctx* ctx, int a, int b, int c) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(c != a && c != b, SDPSR_E_INVALID, "output must not alias an input");
+  double *pa, *pb, *pc;
+  SDPSR_TRY(matrix_ptr(ctx, a, &pa));
+  SDPSR_TRY(matrix_ptr(ctx, b, &pb));
+  SDPSR_TRY(matrix_ptr(ctx, c, &pc));
+  SDPSR_TRY(sdpsr_gemm_f64(ctx, pa, ctx->ld, pb, ctx->ld, pc, ctx->ld, ctx->ld, ctx->n, ctx->n, false));
+  return finish(ctx);
+}
+
+// ---------------------------------------------------------------------------
+// refine / fill / square
+// ---------------------------------------------------------------------------
+extern "C" int sdpsr_refine_values(sdpsr_ctx* ctx, const double* M, double atol, int do_round, int64_t* dim) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(M != nullptr, SDPSR_E_INVALID, "M is NULL");
+  SDPSR_TRY(upload_matrix(ctx, ctx->X2, M));
+  SDPSR_TRY(sdpsr_generic_refine_values(ctx, ctx->X2, atol, do_round != 0, nullptr, dim));
+  return finish(ctx);
+}
+
+extern "C" int sdpsr_fill(sdpsr_ctx* ctx, const double* values, int64_t len) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(len == ctx->dim, SDPSR_E_INVALID, "length(values) != dim(P) (src/partitions.jl:69)");
+  SDPSR_REQUIRE(values != nullptr || len == 0, SDPSR_E_INVALID, "values is NULL");
+  SDPSR_TRY(sdpsr_upload_values(ctx, values, len));
+  SDPSR_TRY(sdpsr_build_lut(ctx, ctx->d_values, len));
+  ctx->x_is_fill = true;    // X == fill(S, lut); materialised on demand
+  ctx->x_valid = true;
+  return finish(ctx);
+}
+
+extern "C" int sdpsr_square_round_refine(sdpsr_ctx* ctx, double atol, int64_t* dim) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(ctx->x_valid, SDPSR_E_STATE, "X is not defined yet (call sdpsr_fill first)");
+  if (ctx->x_is_fill) {
+    SDPSR_TRY(sdpsr_materialize_fill(ctx, ctx->X));
+    // S is unchanged, so X stays a valid fill; keep the flag for a later projection
+  }
+  SDPSR_TRY(sdpsr_gemm_f64(ctx, ctx->X, ctx->ld, ctx->X, ctx->ld, ctx->X2, ctx->ld, ctx->ld, ctx->n, ctx->n,
+                           false));
+  SDPSR_TRY(sdpsr_generic_refine_values(ctx, ctx->X2, atol, true, nullptr, dim));
+  return finish(ctx);
+}
+
+extern "C" int sdpsr_product_round_refine(sdpsr_ctx* ctx, const double* rx, const double* ry, int64_t len,
+                                          double atol, int64_t* dim) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(len == ctx->dim, SDPSR_E_INVALID, "length(values) != dim(P) (src/partitions.jl:69)");
+  double* Y = nullptr;
+  SDPSR_TRY(matrix_ptr(ctx, SDPSR_MAT_W, &Y));
+  SDPSR_TRY(sdpsr_upload_values(ctx, ry, len));
+  SDPSR_TRY(sdpsr_build_lut(ctx, ctx->d_values, len));
+  SDPSR_TRY(sdpsr_materialize_fill(ctx, Y));
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));   // d_values is reused below
+  SDPSR_TRY(sdpsr_upload_values(ctx, rx, len));
+  SDPSR_TRY(sdpsr_build_lut(ctx, ctx->d_values, len));
+  SDPSR_TRY(sdpsr_materialize_fill(ctx, ctx->X));
+  ctx->x_valid = true;
+  SDPSR_TRY(sdpsr_gemm_f64(ctx, ctx->X, ctx->ld, Y, ctx->ld, ctx->X2, ctx->ld, ctx->ld, ctx->n, ctx->n, false));
+  SDPSR_TRY(sdpsr_generic_refine_values(ctx, ctx->X2, atol, true, nullptr, dim));
+  return finish(ctx);
+}
+
+// ---------------------------------------------------------------------------
+// timing / counters
+// ---------------------------------------------------------------------------
+extern "C" int sdpsr_timing_reset(sdpsr_ctx* ctx) {
+  CTX_ENTER();
+  drain_events(ctx);
+  for (int i = 0; i < SDPSR_K_COUNT; ++i) {
+    ctx->t_ms[i] = 0;
+    ctx->t_launch[i] = 0;
+    ctx->t_work[i] = 0;
+  }
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_timing_get(sdpsr_ctx* ctx, int family, double* total_ms, int64_t* launches, double* work) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(family >= 0 && family < SDPSR_K_COUNT, SDPSR_E_INVALID, "unknown kernel family");
+  drain_events(ctx);
+  if (total_ms) *total_ms = ctx->t_ms[family];
+  if (launches) *launches = ctx->t_launch[family];
+  if (work) *work = ctx->t_work[family];
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_launch_count(sdpsr_ctx* ctx, int64_t* launches) {
+  CTX_ENTER();
+  if (launches) *launches = ctx->launches;
+  return SDPSR_OK;
+}

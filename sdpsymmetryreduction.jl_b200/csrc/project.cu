@@ -1,0 +1,611 @@
+// project.cu -- the constraint matrix A, the projection onto its row space and the
+// initial partition.
+//
+// Replaces `qr(A')` + project_colspace! (src/partitions.jl:124-126, src/utils.jl:59-69),
+// the projection step of the loop (src/partitions.jl:160-164) and the two initial
+// elements CL, X0 (src/partitions.jl:129-146, Krylov.craig at :137).
+//
+// proj(v) = A' (A A')^-1 A v.  Two facts make it cheap on the device:
+//   * (A' c)[idx] depends only on the *column pattern* A[:, idx]; entries are tagged once
+//     with a pattern id, and t[p] = sum_k A[k,p] c[k] (ascending k, separate multiply and
+//     add -- the order of Julia's sparse mul!) is evaluated once per pattern on the host;
+//   * A v needs only the stored non-zeros: a deterministic chunked gather-dot.
+// The m x m Gram system is solved on the host (m <= a few hundred).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "sdpsr_internal.cuh"
+
+namespace {
+
+constexpr int CHUNK = 8192;   // non-zeros per reduction chunk
+
+__device__ __forceinline__ uint64_t mix64d(uint64_t k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return k;
+}
+
+// h[col] += mix(row, value bits): an order-independent 64-bit signature of column `col` of A
+__global__ void __launch_bounds__(256) pattern_hash_kernel(const uint32_t* __restrict__ col,
+                                                           const double* __restrict__ val,
+                                                           const uint32_t* __restrict__ chunk_row,
+                                                           const uint32_t* __restrict__ chunk_beg,
+                                                           const uint32_t* __restrict__ chunk_end,
+                                                           unsigned long long* __restrict__ h) {
+  const uint32_t c = blockIdx.x;
+  const uint64_t row = chunk_row[c];
+  for (uint32_t i = chunk_beg[c] + threadIdx.x; i < chunk_end[c]; i += blockDim.x) {
+    const uint64_t vb = (uint64_t)__double_as_longlong(val[i]);
+    atomicAdd(h + col[i], (unsigned long long)mix64d((row + 1) * 0x9e3779b97f4a7c15ull ^ mix64d(vb)));
+  }
+}
+
+__global__ void relabel_kernel(uint32_t* __restrict__ ids, const uint32_t* __restrict__ rank, uint64_t total) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
+    ids[i] = rank[ids[i]];
+}
+
+__global__ void __launch_bounds__(256) pattern_count_kernel(const uint32_t* __restrict__ pid, int64_t n, int64_t ld,
+                                                            unsigned long long* __restrict__ cnt) {
+  // padding rows (i >= n) are excluded: they are not entries of the matrix
+  const int64_t j = blockIdx.y;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nround = (n + step - 1) / step * step;     // warp-uniform trip count
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += step) {
+    const bool valid = i < n;
+    const uint32_t p = valid ? pid[i + ld * j] : 0xffffffffu;
+    const unsigned mask = __match_any_sync(0xffffffffu, p);
+    if (valid && (int)(__ffs(mask) - 1) == (int)(threadIdx.x & 31))
+      atomicAdd(cnt + p, (unsigned long long)__popc(mask));
+  }
+}
+
+// partial[c] = sum over the chunk of val * x[col]; x = xs[col] or lut[labels[col]]
+__global__ void __launch_bounds__(256) rowdot_kernel(const uint32_t* __restrict__ col, const double* __restrict__ val,
+                                                     const uint32_t* __restrict__ chunk_beg,
+                                                     const uint32_t* __restrict__ chunk_end,
+                                                     const double* __restrict__ xs, const double* __restrict__ lut,
+                                                     const uint32_t* __restrict__ labels,
+                                                     double* __restrict__ partial) {
+  __shared__ double ws[8];
+  const uint32_t c = blockIdx.x;
+  double s = 0.0;
+  for (uint32_t i = chunk_beg[c] + threadIdx.x; i < chunk_end[c]; i += blockDim.x) {
+    const uint32_t cc = col[i];
+    const double x = xs ? xs[cc] : lut[labels[cc]];
+    s += val[i] * x;
+  }
+  for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += ws[w];
+    partial[c] = t;
+  }
+}
+
+__device__ __forceinline__ double snap_round(double c, double pw, int do_snap, double atol, double scale) {
+  if (do_snap) c = __ddiv_rn(rint(__dmul_rn(c, pw)), pw);      // numpy.round(c, decimals)
+  if (fabs(c) < atol) return 0.0;                                // _clamp_round!, src/utils.jl:34-53
+  int n;
+  const double x = frexp(c, &n);
+  const long long q = __double2ll_rz(__dmul_rn(scale, x));
+  return ldexp(__ddiv_rn((double)q, scale), n);
+}
+
+// mode 0: out = round(snap(src - t[pid]))   (CL before symmetrisation)
+// mode 1: out = t[pid]                      (x0 = A' coef0)
+// mode 2: out = round(snap(t[pid]))         (X0 = proj(sym(x0)))
+__global__ void __launch_bounds__(256) init_elem_kernel(int mode, const double* __restrict__ src,
+                                                        const uint32_t* __restrict__ pid,
+                                                        const double* __restrict__ tpat, double* __restrict__ out,
+                                                        uint64_t total, double pw, int do_snap, double atol,
+                                                        double scale) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const double t = tpat[pid[i]];
+    double v;
+    if (mode == 0)
+      v = snap_round(__dsub_rn(src[i], t), pw, do_snap, atol, scale);
+    else if (mode == 1)
+      v = t;
+    else
+      v = snap_round(t, pw, do_snap, atol, scale);
+    out[i] = v;
+  }
+}
+
+// out[i,j] = (in[i,j] + in[j,i]) / 2   (src/utils.jl:71-81), 32x32 tiles through shared memory
+__global__ void __launch_bounds__(256) symmetrize_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                         int64_t n, int64_t ld) {
+  __shared__ double t[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t bi = blockIdx.x, bj = blockIdx.y;
+  for (int r = ty; r < 32; r += 8) {   // transposed tile: rows bj*32.., columns bi*32..
+    const int64_t i = bj * 32 + tx, j = bi * 32 + r;
+    t[r][tx] = (i < n && j < n) ? in[i + ld * j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = bi * 32 + tx, j = bj * 32 + r;
+    if (i < n && j < n) out[i + ld * j] = (in[i + ld * j] + t[tx][r]) / 2;
+  }
+}
+
+__global__ void __launch_bounds__(256) symcheck_kernel(const uint32_t* __restrict__ lab, int64_t n, int64_t ld,
+                                                       uint32_t* __restrict__ bad) {
+  __shared__ uint32_t t[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t bi = blockIdx.x, bj = blockIdx.y;
+  if (bi < bj) return;
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = bj * 32 + tx, j = bi * 32 + r;
+    t[r][tx] = (i < n && j < n) ? lab[i + ld * j] : 0u;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = bi * 32 + tx, j = bj * 32 + r;
+    if (i < n && j < n && lab[i + ld * j] != t[tx][r]) *bad = 1u;
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+void sdpsr_constraints_free(sdpsr_ctx* ctx) {
+  ConstraintSet& c = ctx->cons;
+  cudaFree(c.d_col);
+  cudaFree(c.d_val);
+  cudaFree(c.d_chunk_row);
+  cudaFree(c.d_chunk_beg);
+  cudaFree(c.d_partial);
+  cudaFree(c.d_pid);
+  cudaFree(c.d_tpat);
+  c = ConstraintSet();
+}
+
+int sdpsr_symmetric_check(sdpsr_ctx* ctx, int* is_sym) {
+  uint32_t* bad = ctx->d_scalars + 8;
+  SDPSR_CUDA(cudaMemsetAsync(bad, 0, sizeof(uint32_t), ctx->stream));
+  const unsigned nb = (unsigned)((ctx->n + 31) / 32);
+  symcheck_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(ctx->labels, ctx->n, ctx->ld, bad);
+  count_launch(ctx);
+  SDPSR_CUDA(cudaGetLastError());
+  uint32_t* hb = reinterpret_cast<uint32_t*>(ctx->h_pinned) + 32;
+  SDPSR_CUDA(cudaMemcpyAsync(hb, bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  *is_sym = (*hb == 0u) ? 1 : 0;
+  return SDPSR_OK;
+}
+
+// LU with partial pivoting of the m x m Gram matrix (row-major), in place
+static bool lu_factor(std::vector<double>& a, std::vector<int>& piv, int m) {
+  piv.resize(m);
+  double amax = 0.0;
+  for (double v : a) amax = std::max(amax, std::fabs(v));
+  for (int k = 0; k < m; ++k) {
+    int p = k;
+    double best = std::fabs(a[(size_t)k * m + k]);
+    for (int i = k + 1; i < m; ++i)
+      if (std::fabs(a[(size_t)i * m + k]) > best) {
+        best = std::fabs(a[(size_t)i * m + k]);
+        p = i;
+      }
+    if (!(best > 1e-13 * amax)) return false;
+    piv[k] = p;
+    if (p != k)
+      for (int j = 0; j < m; ++j) std::swap(a[(size_t)k * m + j], a[(size_t)p * m + j]);
+    for (int i = k + 1; i < m; ++i) {
+      const double f = a[(size_t)i * m + k] / a[(size_t)k * m + k];
+      a[(size_t)i * m + k] = f;
+      for (int j = k + 1; j < m; ++j) a[(size_t)i * m + j] -= f * a[(size_t)k * m + j];
+    }
+  }
+  return true;
+}
+
+int sdpsr_solve_gram(sdpsr_ctx* ctx, std::vector<double>& x) {
+  ConstraintSet& c = ctx->cons;
+  const int m = (int)c.m;
+  const std::vector<double>& a = c.gram_lu;
+  for (int k = 0; k < m; ++k)
+    if (c.gram_piv[k] != k) std::swap(x[k], x[c.gram_piv[k]]);
+  for (int i = 1; i < m; ++i) {
+    double s = x[i];
+    for (int j = 0; j < i; ++j) s -= a[(size_t)i * m + j] * x[j];
+    x[i] = s;
+  }
+  for (int i = m - 1; i >= 0; --i) {
+    double s = x[i];
+    for (int j = i + 1; j < m; ++j) s -= a[(size_t)i * m + j] * x[j];
+    x[i] = s / a[(size_t)i * m + i];
+  }
+  return SDPSR_OK;
+}
+
+int sdpsr_upload_tpat(sdpsr_ctx* ctx, const std::vector<double>& coef) {
+  ConstraintSet& c = ctx->cons;
+  std::vector<double> t((size_t)c.npat + 1, 0.0);
+  for (int64_t p = 1; p <= c.npat; ++p) {
+    double s = 0.0;
+    for (int64_t e = c.pat_ptr[p]; e < c.pat_ptr[p + 1]; ++e) {
+      volatile double prod = c.pat_val[e] * coef[c.pat_row[e]];   // separate multiply and add
+      s = s + prod;
+    }
+    t[p] = s;
+  }
+  SDPSR_CUDA(cudaMemcpyAsync(c.d_tpat, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));   // `t` dies at return
+  return SDPSR_OK;
+}
+
+int sdpsr_rowdots(sdpsr_ctx* ctx, const double* x_array, const double* lut, std::vector<double>& out) {
+  ConstraintSet& c = ctx->cons;
+  out.assign((size_t)c.m, 0.0);
+  if (c.nchunks == 0) return SDPSR_OK;
+  {
+    Timed tm(ctx, SDPSR_K_PROJECT, (double)c.nnz * 20.0);
+    rowdot_kernel<<<(unsigned)c.nchunks, 256, 0, ctx->stream>>>(c.d_col, c.d_val, c.d_chunk_beg,
+                                                                c.d_chunk_beg + c.nchunks, x_array, lut, ctx->labels,
+                                                                c.d_partial);
+    count_launch(ctx);
+  }
+  SDPSR_CUDA(cudaGetLastError());
+  std::vector<double> part((size_t)c.nchunks);
+  SDPSR_CUDA(cudaMemcpyAsync(part.data(), c.d_partial, part.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int64_t i = 0; i < c.nchunks; ++i) out[c.chunk_row[i]] += part[i];   // fixed order: deterministic
+  return SDPSR_OK;
+}
+
+// Build everything derived from the host CSR copy in ctx->cons (h_rowptr / h_col / h_val).
+int sdpsr_constraints_finalize(sdpsr_ctx* ctx) {
+  ConstraintSet& c = ctx->cons;
+  const int64_t m = c.m, n = ctx->n, ld = ctx->ld;
+  const int64_t nnz = c.h_rowptr[m];
+  c.nnz = nnz;
+  SDPSR_REQUIRE(nnz < 0xffffffffll, SDPSR_E_UNSUPPORTED, "more than 2^32-1 stored constraint entries");
+  // ---- device CSR with padded column indices, reduction chunks ----------------------
+  std::vector<uint32_t> col((size_t)nnz);
+  for (int64_t k = 0; k < m; ++k) {
+    int64_t prev = -1;
+    for (int64_t e = c.h_rowptr[k]; e < c.h_rowptr[k + 1]; ++e) {
+      const int64_t idx = c.h_col[e];
+      SDPSR_REQUIRE(idx >= 0 && idx < n * n, SDPSR_E_INVALID, "constraint column index out of range");
+      SDPSR_REQUIRE(idx > prev, SDPSR_E_INVALID, "constraint rows must have strictly increasing column indices");
+      prev = idx;
+      col[(size_t)e] = (uint32_t)((idx % n) + ld * (idx / n));
+    }
+  }
+  std::vector<uint32_t> cbeg, cend;
+  c.chunk_row.clear();
+  for (int64_t k = 0; k < m; ++k)
+    for (int64_t e = c.h_rowptr[k]; e < c.h_rowptr[k + 1]; e += CHUNK) {
+      c.chunk_row.push_back((uint32_t)k);
+      cbeg.push_back((uint32_t)e);
+      cend.push_back((uint32_t)std::min<int64_t>(e + CHUNK, c.h_rowptr[k + 1]));
+    }
+  c.nchunks = (int64_t)cbeg.size();
+  const size_t nz_alloc = std::max<size_t>((size_t)nnz, 1), ch_alloc = std::max<size_t>((size_t)c.nchunks, 1);
+  SDPSR_CUDA(cudaMalloc(&c.d_col, nz_alloc * sizeof(uint32_t)));
+  SDPSR_CUDA(cudaMalloc(&c.d_val, nz_alloc * sizeof(double)));
+  SDPSR_CUDA(cudaMalloc(&c.d_chunk_row, ch_alloc * sizeof(uint32_t)));
+  SDPSR_CUDA(cudaMalloc(&c.d_chunk_beg, 2 * ch_alloc * sizeof(uint32_t)));
+  SDPSR_CUDA(cudaMalloc(&c.d_partial, ch_alloc * sizeof(double)));
+  SDPSR_CUDA(cudaMalloc(&c.d_pid, ctx->elems * sizeof(uint32_t)));
+  if (nnz) {
+    SDPSR_CUDA(cudaMemcpyAsync(c.d_col, col.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SDPSR_CUDA(cudaMemcpyAsync(c.d_val, c.h_val.data(), (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SDPSR_CUDA(cudaMemcpyAsync(c.d_chunk_row, c.chunk_row.data(), (size_t)c.nchunks * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SDPSR_CUDA(cudaMemcpyAsync(c.d_chunk_beg, cbeg.data(), (size_t)c.nchunks * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SDPSR_CUDA(cudaMemcpyAsync(c.d_chunk_beg + c.nchunks, cend.data(), (size_t)c.nchunks * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  // ---- pattern ids: hash every column, first-occurrence rank of the hashes ------------
+  unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->X2);
+  SDPSR_CUDA(cudaMemsetAsync(h, 0, ctx->elems * 8, ctx->stream));
+  if (c.nchunks) {
+    pattern_hash_kernel<<<(unsigned)c.nchunks, 256, 0, ctx->stream>>>(c.d_col, c.d_val, c.d_chunk_row, c.d_chunk_beg,
+                                                                      c.d_chunk_beg + c.nchunks, h);
+    count_launch(ctx);
+    SDPSR_CUDA(cudaGetLastError());
+  }
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));   // host vectors above die below
+  KeyTable scratch;
+  RefineSpec sp;
+  sp.mode = KM_RAW;
+  sp.vals = ctx->X2;
+  sp.do_round = false;
+  sp.raw_bits = true;
+  sp.ignore_labels = true;
+  sp.out_override = c.d_pid;
+  sp.table_override = &scratch;
+  int64_t npat = 0;
+  int st = sdpsr_refine_pass(ctx, sp, &npat);
+  if (st != SDPSR_OK) {
+    sdpsr_table_free(scratch);
+    return st;
+  }
+  c.npat = npat;
+  {
+    const int grid = (int)std::min<uint64_t>((ctx->elems + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    relabel_kernel<<<grid, 256, 0, ctx->stream>>>(c.d_pid, scratch.rank, ctx->elems);
+    count_launch(ctx);
+  }
+  // representative entry of every pattern (its first occurrence) and pattern sizes
+  std::vector<uint32_t> occ((size_t)npat), mi((size_t)npat), rk((size_t)scratch.cap + 1);
+  if (npat) {
+    SDPSR_CUDA(cudaMemcpyAsync(occ.data(), scratch.occ, (size_t)npat * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SDPSR_CUDA(cudaMemcpyAsync(rk.data(), scratch.rank, rk.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  std::vector<uint32_t> allmin((size_t)scratch.cap);
+  SDPSR_CUDA(cudaMemcpyAsync(allmin.data(), scratch.minidx, allmin.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned long long* dcnt = nullptr;
+  SDPSR_CUDA(cudaMalloc(&dcnt, ((size_t)npat + 1) * 8));
+  SDPSR_CUDA(cudaMemsetAsync(dcnt, 0, ((size_t)npat + 1) * 8, ctx->stream));
+  pattern_count_kernel<<<dim3((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)n), 256, 0, ctx->stream>>>(
+      c.d_pid, n, ld, dcnt);
+  count_launch(ctx);
+  std::vector<unsigned long long> cnt((size_t)npat + 1);
+  SDPSR_CUDA(cudaMemcpyAsync(cnt.data(), dcnt, cnt.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dcnt);
+  sdpsr_table_free(scratch);
+  std::vector<int64_t> rep((size_t)npat + 1, -1);
+  for (int64_t i = 0; i < npat; ++i) {
+    const uint32_t slot = occ[(size_t)i];
+    const uint32_t r = rk[(size_t)slot + 1];
+    const uint32_t pidx = allmin[slot];
+    rep[r] = (int64_t)(pidx % ld) + n * (int64_t)(pidx / ld);
+  }
+  c.pat_cnt.assign(cnt.begin(), cnt.end());
+  // ---- pattern table: column of A at each representative entry -------------------------
+  c.pat_ptr.assign((size_t)npat + 2, 0);
+  c.pat_row.clear();
+  c.pat_val.clear();
+  for (int64_t p = 1; p <= npat; ++p) {
+    c.pat_ptr[(size_t)p] = (int64_t)c.pat_row.size();
+    const int64_t idx = rep[(size_t)p];
+    SDPSR_REQUIRE(idx >= 0, SDPSR_E_CUDA, "internal: pattern without representative");
+    for (int64_t k = 0; k < m; ++k) {
+      const int64_t* b = c.h_col.data() + c.h_rowptr[k];
+      const int64_t* e = c.h_col.data() + c.h_rowptr[k + 1];
+      const int64_t* it = std::lower_bound(b, e, idx);
+      if (it != e && *it == idx) {
+        c.pat_row.push_back((int32_t)k);
+        c.pat_val.push_back(c.h_val[(size_t)(it - c.h_col.data())]);
+      }
+    }
+  }
+  c.pat_ptr[(size_t)npat + 1] = (int64_t)c.pat_row.size();
+  // consistency: pattern sizes must add up to nnz (catches a 64-bit signature collision)
+  {
+    int64_t tot = 0;
+    for (int64_t p = 1; p <= npat; ++p) tot += (c.pat_ptr[p + 1] - c.pat_ptr[p]) * (int64_t)cnt[(size_t)p];
+    SDPSR_REQUIRE(tot == nnz, SDPSR_E_CUDA, "internal: constraint pattern signature collision");
+  }
+  // ---- Gram matrix G = A A' = sum_p cnt[p] v_p v_p' and its LU ----------------------------
+  c.gram_lu.assign((size_t)m * m, 0.0);
+  for (int64_t p = 1; p <= npat; ++p)
+    for (int64_t e1 = c.pat_ptr[p]; e1 < c.pat_ptr[p + 1]; ++e1)
+      for (int64_t e2 = c.pat_ptr[p]; e2 < c.pat_ptr[p + 1]; ++e2)
+        c.gram_lu[(size_t)c.pat_row[e1] * m + c.pat_row[e2]] += (double)cnt[(size_t)p] * c.pat_val[e1] * c.pat_val[e2];
+  SDPSR_REQUIRE(lu_factor(c.gram_lu, c.gram_piv, (int)m), SDPSR_E_SINGULAR,
+                "constraint rows are linearly dependent (A A' is singular)");
+  SDPSR_CUDA(cudaMalloc(&c.d_tpat, ((size_t)npat + 1) * sizeof(double)));
+  SDPSR_CUDA(cudaMemsetAsync(c.d_tpat, 0, ((size_t)npat + 1) * sizeof(double), ctx->stream));
+  c.ready = true;
+  return SDPSR_OK;
+}
+
+#define CTX_ENTER()                 \
+  if (!ctx) return SDPSR_E_INVALID; \
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return ctx->fail(SDPSR_E_CUDA, "cudaSetDevice failed")
+
+static int finish(sdpsr_ctx* ctx) {
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  SDPSR_CUDA(cudaGetLastError());
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_set_constraints_csr(sdpsr_ctx* ctx, int64_t m, const int64_t* rowptr, const int64_t* colidx,
+                                         const double* vals, int index_base) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(m >= 1 && rowptr && (index_base == 0 || index_base == 1), SDPSR_E_INVALID, "bad CSR arguments");
+  sdpsr_constraints_free(ctx);
+  ConstraintSet& c = ctx->cons;
+  c.m = m;
+  c.h_rowptr.assign((size_t)m + 1, 0);
+  const int64_t nnz_in = rowptr[m] - rowptr[0];
+  SDPSR_REQUIRE(nnz_in >= 0 && (nnz_in == 0 || (colidx && vals)), SDPSR_E_INVALID, "bad CSR arguments");
+  c.h_col.reserve((size_t)nnz_in);
+  c.h_val.reserve((size_t)nnz_in);
+  for (int64_t k = 0; k < m; ++k) {
+    for (int64_t e = rowptr[k] - rowptr[0]; e < rowptr[k + 1] - rowptr[0]; ++e) {
+      if (vals[e] == 0.0) continue;   // explicit zeros carry no constraint
+      c.h_col.push_back(colidx[e] - index_base);
+      c.h_val.push_back(vals[e]);
+    }
+    c.h_rowptr[(size_t)k + 1] = (int64_t)c.h_col.size();
+  }
+  SDPSR_TRY(sdpsr_constraints_finalize(ctx));
+  return finish(ctx);
+}
+
+extern "C" int sdpsr_set_constraints_dense(sdpsr_ctx* ctx, int64_t m, const double* A) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(m >= 1 && A, SDPSR_E_INVALID, "bad dense constraint arguments");
+  sdpsr_constraints_free(ctx);
+  ConstraintSet& c = ctx->cons;
+  c.m = m;
+  const int64_t nn = ctx->n * ctx->n;
+  std::vector<int64_t> cntk((size_t)m, 0);
+  for (int64_t idx = 0; idx < nn; ++idx)
+    for (int64_t k = 0; k < m; ++k)
+      if (A[k + m * idx] != 0.0) ++cntk[(size_t)k];
+  c.h_rowptr.assign((size_t)m + 1, 0);
+  for (int64_t k = 0; k < m; ++k) c.h_rowptr[(size_t)k + 1] = c.h_rowptr[(size_t)k] + cntk[(size_t)k];
+  c.h_col.resize((size_t)c.h_rowptr[m]);
+  c.h_val.resize((size_t)c.h_rowptr[m]);
+  std::vector<int64_t> pos(c.h_rowptr.begin(), c.h_rowptr.end() - 1);
+  for (int64_t idx = 0; idx < nn; ++idx)
+    for (int64_t k = 0; k < m; ++k) {
+      const double v = A[k + m * idx];
+      if (v != 0.0) {
+        c.h_col[(size_t)pos[k]] = idx;
+        c.h_val[(size_t)pos[k]++] = v;
+      }
+    }
+  SDPSR_TRY(sdpsr_constraints_finalize(ctx));
+  return finish(ctx);
+}
+
+extern "C" int sdpsr_set_constraints_csc(sdpsr_ctx* ctx, int64_t m, const int64_t* colptr, const int64_t* rowval,
+                                         const double* nzval, int index_base) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(m >= 1 && colptr && (index_base == 0 || index_base == 1), SDPSR_E_INVALID, "bad CSC arguments");
+  sdpsr_constraints_free(ctx);
+  ConstraintSet& c = ctx->cons;
+  c.m = m;
+  const int64_t nn = ctx->n * ctx->n;
+  const int64_t off = colptr[0];
+  std::vector<int64_t> cntk((size_t)m, 0);
+  for (int64_t e = 0; e < colptr[nn] - off; ++e) {
+    const int64_t k = rowval[e] - index_base;
+    SDPSR_REQUIRE(k >= 0 && k < m, SDPSR_E_INVALID, "CSC row index out of range");
+    if (nzval[e] != 0.0) ++cntk[(size_t)k];
+  }
+  c.h_rowptr.assign((size_t)m + 1, 0);
+  for (int64_t k = 0; k < m; ++k) c.h_rowptr[(size_t)k + 1] = c.h_rowptr[(size_t)k] + cntk[(size_t)k];
+  c.h_col.resize((size_t)c.h_rowptr[m]);
+  c.h_val.resize((size_t)c.h_rowptr[m]);
+  std::vector<int64_t> pos(c.h_rowptr.begin(), c.h_rowptr.end() - 1);
+  for (int64_t idx = 0; idx < nn; ++idx)
+    for (int64_t e = colptr[idx] - off; e < colptr[idx + 1] - off; ++e) {
+      if (nzval[e] == 0.0) continue;
+      const int64_t k = rowval[e] - index_base;
+      c.h_col[(size_t)pos[k]] = idx;
+      c.h_val[(size_t)pos[k]++] = nzval[e];
+    }
+  SDPSR_TRY(sdpsr_constraints_finalize(ctx));
+  return finish(ctx);
+}
+
+extern "C" int sdpsr_constraint_patterns(sdpsr_ctx* ctx, int64_t* npatterns) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(ctx->cons.ready && npatterns, SDPSR_E_STATE, "constraints not set");
+  *npatterns = ctx->cons.npat;
+  return SDPSR_OK;
+}
+
+// x .-= proj(x); round; S = refine!(S, Part(X))   (src/partitions.jl:160-164)
+extern "C" int sdpsr_project_round_refine(sdpsr_ctx* ctx, double atol, int64_t* dim) {
+  CTX_ENTER();
+  ConstraintSet& c = ctx->cons;
+  SDPSR_REQUIRE(c.ready, SDPSR_E_STATE, "constraints not set (sdpsr_set_constraints_*)");
+  SDPSR_REQUIRE(ctx->x_valid && ctx->x_is_fill, SDPSR_E_STATE,
+                "sdpsr_project_round_refine must follow sdpsr_fill (src/partitions.jl:159-161)");
+  std::vector<double> coef;
+  SDPSR_TRY(sdpsr_rowdots(ctx, nullptr, ctx->lut, coef));   // A x, x = fill(S, values)
+  SDPSR_TRY(sdpsr_solve_gram(ctx, coef));                   // (A A')^-1 A x
+  SDPSR_TRY(sdpsr_upload_tpat(ctx, coef));
+  RefineSpec sp;
+  sp.fillproj = true;
+  sp.lut = ctx->lut;
+  sp.tpat = c.d_tpat;
+  sp.pid = c.d_pid;
+  sp.vals_out = ctx->X;          // the projected, rounded element stays as X (:163)
+  sp.atol = atol;
+  sp.do_round = true;
+  double sc;
+  long long isc;
+  int qb;
+  SDPSR_TRY(sdpsr_round_params(ctx, atol, &sc, &isc, &qb));
+  if (12 + qb + bits_for((uint64_t)ctx->tab[ctx->cur].cap) <= 64) {
+    sp.mode = KM_ROUND;
+    SDPSR_TRY(sdpsr_refine_pass(ctx, sp, dim));
+  } else {
+    // wide rounding grid: materialise X first, then the generic two-step refine
+    SDPSR_TRY(sdpsr_ensure_tmp_labels(ctx));
+    KeyTable scratch;
+    sp.mode = KM_RAW;
+    sp.out_override = ctx->labels_tmp;
+    sp.table_override = &scratch;
+    int st = sdpsr_refine_pass(ctx, sp, nullptr);
+    if (st == SDPSR_OK) {
+      RefineSpec pr;
+      pr.mode = KM_PAIR;
+      pr.lab2 = ctx->labels_tmp;
+      pr.do_round = false;
+      st = sdpsr_refine_pass(ctx, pr, dim);
+    }
+    sdpsr_table_free(scratch);
+    SDPSR_TRY(st);
+  }
+  ctx->x_valid = true;
+  ctx->x_is_fill = false;
+  return finish(ctx);
+}
+
+// The initial partition of src/partitions.jl:129-146 on the device.
+extern "C" int sdpsr_init_partition(sdpsr_ctx* ctx, const double* C, const double* b, double atol,
+                                    int snap_decimals, int64_t* dim) {
+  CTX_ENTER();
+  ConstraintSet& c = ctx->cons;
+  SDPSR_REQUIRE(c.ready, SDPSR_E_STATE, "constraints not set (sdpsr_set_constraints_*)");
+  SDPSR_REQUIRE(C && b, SDPSR_E_INVALID, "C or b is NULL");
+  SDPSR_REQUIRE(snap_decimals <= 15, SDPSR_E_INVALID, "snap_decimals must be <= 15");
+  double scale;
+  long long iscale;
+  int qbits;
+  SDPSR_TRY(sdpsr_round_params(ctx, atol, &scale, &iscale, &qbits));
+  const int do_snap = snap_decimals >= 0 ? 1 : 0;
+  double pw = 1.0;
+  for (int i = 0; i < snap_decimals; ++i) pw *= 10.0;
+  const int grid = (int)std::min<uint64_t>((ctx->elems + 255) / 256, (uint64_t)ctx->sm_count * 16);
+  const unsigned nb = (unsigned)((ctx->n + 31) / 32);
+  std::vector<double> coef;
+
+  // CL = symmetrize(round(C - proj(C)))                                   (:129-134)
+  if (ctx->ld != ctx->n) SDPSR_CUDA(cudaMemsetAsync(ctx->X, 0, ctx->elems * 8, ctx->stream));
+  SDPSR_CUDA(cudaMemcpy2DAsync(ctx->X, (size_t)ctx->ld * 8, C, (size_t)ctx->n * 8, (size_t)ctx->n * 8, (size_t)ctx->n,
+                               cudaMemcpyDefault, ctx->stream));
+  SDPSR_TRY(sdpsr_rowdots(ctx, ctx->X, nullptr, coef));
+  SDPSR_TRY(sdpsr_solve_gram(ctx, coef));
+  SDPSR_TRY(sdpsr_upload_tpat(ctx, coef));
+  init_elem_kernel<<<grid, 256, 0, ctx->stream>>>(0, ctx->X, c.d_pid, c.d_tpat, ctx->X2, ctx->elems, pw, do_snap, atol, scale);
+  symmetrize_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(ctx->X2, ctx->X, ctx->n, ctx->ld);
+  count_launch(ctx, 2);
+  SDPSR_CUDA(cudaGetLastError());
+  SDPSR_TRY(sdpsr_partition_reset(ctx));
+  {
+    RefineSpec sp;                                                        // S = Part(CL)   (:145)
+    sp.mode = KM_RAW;
+    sp.vals = ctx->X;
+    sp.do_round = false;
+    sp.ignore_labels = true;
+    SDPSR_TRY(sdpsr_refine_pass(ctx, sp, nullptr));
+  }
+  // X0 = round(proj(symmetrize(x0))), x0 = A' (A A')^-1 b                   (:137-142)
+  coef.assign(b, b + c.m);
+  SDPSR_TRY(sdpsr_solve_gram(ctx, coef));
+  SDPSR_TRY(sdpsr_upload_tpat(ctx, coef));
+  init_elem_kernel<<<grid, 256, 0, ctx->stream>>>(1, nullptr, c.d_pid, c.d_tpat, ctx->X2, ctx->elems, pw, do_snap, atol, scale);
+  symmetrize_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(ctx->X2, ctx->X, ctx->n, ctx->ld);
+  count_launch(ctx, 2);
+  SDPSR_TRY(sdpsr_rowdots(ctx, ctx->X, nullptr, coef));
+  SDPSR_TRY(sdpsr_solve_gram(ctx, coef));
+  SDPSR_TRY(sdpsr_upload_tpat(ctx, coef));
+  init_elem_kernel<<<grid, 256, 0, ctx->stream>>>(2, nullptr, c.d_pid, c.d_tpat, ctx->X2, ctx->elems, pw, do_snap, atol, scale);
+  count_launch(ctx);
+  SDPSR_CUDA(cudaGetLastError());
+  SDPSR_TRY(sdpsr_generic_refine_values(ctx, ctx->X2, atol, false, nullptr, dim));   // refine!(S, Part(X0)) (:146)
+  ctx->x_valid = false;
+  ctx->x_is_fill = false;
+  return finish(ctx);
+}

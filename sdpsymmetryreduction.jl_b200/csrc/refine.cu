@@ -1,0 +1,710 @@
+// refine.cu -- the partition kernels of the Jordan-reduction hot path (sm_100a).
+//
+// Replaces, as ONE streaming pass over the N x N entries,
+//   _clamp_round!            src/utils.jl:34-53
+//   Partition{T}(M)          src/partitions.jl:24-35   (Dict pass)
+//   refine! + __sort_unique! src/partitions.jl:44-66   (unique + LUT + relabel)
+// and fill! (src/partitions.jl:68-75).
+//
+// Design (DESIGN.md "refine pass"): each entry forms a 64-bit key
+//   (old provisional id, code of the rounded value)
+// and obtains the slot of that key in a global open-addressing table; slot+1 is
+// the entry's new *provisional* id.  A per-CTA shared-memory cache of
+// key -> slot keeps global atomics down to O(distinct keys) per CTA.  The table
+// records the first (smallest) linear index of every key; canonical labels (the
+// reference numbers classes by first occurrence in column-major order) are the
+// ranks of those first indices and are computed on the table only -- O(dim) work,
+// not O(N^2) -- and applied lazily (fill LUT composition, label export).
+// HBM traffic of a pass: 8 B value + 4 B old id + 4 B new id = 16 B / entry.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "sdpsr_internal.cuh"
+
+namespace {
+
+constexpr int RT = 256;           // threads per CTA
+constexpr int EPT = 4;            // consecutive entries per thread per tile
+constexpr int TILE = RT * EPT;    // entries per tile
+constexpr int SC = 4096;          // slots of the per-CTA key cache
+constexpr int SC_LIMIT = SC * 5 / 8;
+constexpr uint32_t PROBE_LIMIT = 4096;
+constexpr int RANK_BRUTE_MAX = 16384;
+
+struct RefineArgs {
+  const uint32_t* lab_in;
+  const uint32_t* lab2;
+  const double* vals;
+  double* vals_out;
+  const double* lut;
+  const double* tpat;
+  const uint32_t* pid;
+  uint32_t* lab_out;
+  uint64_t total;
+  double atol;
+  double scale;
+  long long iscale;
+  int qbits;
+  int lbits;
+  int do_round;
+  int fillproj;
+  int use_cache;
+  int raw_bits;
+  uint64_t* gkeys;
+  uint32_t* gmin;
+  uint32_t* gocc;
+  uint32_t* gmeta;
+  uint32_t gmask;
+  uint32_t glimit;
+};
+
+__device__ __forceinline__ uint64_t mix64(uint64_t k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return k;
+}
+
+__device__ __forceinline__ uint64_t ld_vol64(const uint64_t* p) {
+  return *reinterpret_cast<const volatile uint64_t*>(p);
+}
+__device__ __forceinline__ uint32_t ld_vol32(const uint32_t* p) {
+  return *reinterpret_cast<const volatile uint32_t*>(p);
+}
+
+// _clamp_round! of one value (src/utils.jl:34-53) as an integer code:
+//   0                       if |a| < atol
+//   sign | biased exp | |q| otherwise, with a = x * 2^n, |x| in [0.5,1), q = trunc(scale*x).
+// The code is an injective function of the rounded value ldexp(q/scale, n); the one
+// non-canonical representation (|q| == scale, i.e. y == 1.0) is folded onto
+// (scale/2, n+1), which denotes the same double.  `rounded` receives the value the
+// reference would store.
+__device__ __forceinline__ uint64_t round_code(double a, double atol, double scale, long long iscale,
+                                               int qbits, double& rounded) {
+  if (fabs(a) < atol) {
+    rounded = 0.0;
+    return 0ull;
+  }
+  const uint64_t bits = (uint64_t)__double_as_longlong(a);
+  const uint64_t sign = bits >> 63;
+  uint32_t e = (uint32_t)(bits >> 52) & 0x7ffu;   // biased exponent, n = e - 1022
+  const double x = __longlong_as_double((long long)((bits & 0x800fffffffffffffull) | (0x3feull << 52)));
+  const double p = __dmul_rn(scale, x);            // one IEEE multiply, no FMA contraction
+  const long long q = __double2ll_rz(p);           // unsafe_trunc(Int, .)
+  rounded = ldexp(__ddiv_rn((double)q, scale), (int)e - 1022);
+  unsigned long long aq = (unsigned long long)(q < 0 ? -q : q);
+  if (aq == (unsigned long long)iscale) {          // y == 1.0: same double as (scale/2, n+1)
+    aq = (unsigned long long)(iscale >> 1);
+    e += 1;
+  }
+  return (sign << (11 + qbits)) | ((uint64_t)e << qbits) | aq;
+}
+
+__device__ __forceinline__ uint64_t raw_code(double v) {
+  uint64_t b = (uint64_t)__double_as_longlong(v);
+  if (v != v) b = 0x7ff8000000000000ull;           // isequal: all NaNs are one key
+  return b;                                         // +0.0 -> 0 (the zero key); -0.0 stays distinct
+}
+
+__device__ __forceinline__ uint32_t global_insert(const RefineArgs& a, uint64_t k, uint64_t h) {
+  uint32_t s = (uint32_t)(h >> 20) & a.gmask;
+  for (uint32_t probe = 0; probe < PROBE_LIMIT; ++probe) {
+    const uint64_t kk = ld_vol64(a.gkeys + s);
+    if (kk == k) return s + 1;
+    if (kk == KEY_EMPTY) {
+      const unsigned long long old =
+          atomicCAS(reinterpret_cast<unsigned long long*>(a.gkeys + s), KEY_EMPTY, (unsigned long long)k);
+      if (old == KEY_EMPTY) {
+        const uint32_t pos = atomicAdd(a.gmeta, 1u);
+        if (pos < a.glimit)
+          a.gocc[pos] = s;
+        else
+          a.gmeta[1] = 1u;                           // table too small: host grows it and reruns
+        return s + 1;
+      }
+      if (old == (unsigned long long)k) return s + 1;
+    }
+    s = (s + 1) & a.gmask;
+  }
+  a.gmeta[1] = 1u;
+  return 1u;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(RT) refine_kernel(const RefineArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* sgid = reinterpret_cast<uint32_t*>(skeys + SC);
+  uint32_t* smin = sgid + SC;
+  __shared__ uint32_t s_count;
+
+  for (int i = threadIdx.x; i < SC; i += RT) {
+    skeys[i] = KEY_EMPTY;
+    sgid[i] = 0u;
+    smin[i] = 0xffffffffu;
+  }
+  if (threadIdx.x == 0) s_count = 0u;
+  __syncthreads();
+
+  const uint64_t ntiles = (a.total + TILE - 1) / TILE;
+  uint32_t iter = 0;
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
+    if ((iter & 7u) == 7u) {                          // bounded work after a table overflow
+      if (__syncthreads_or((int)ld_vol32(a.gmeta + 1))) return;
+    }
+    const uint64_t base = tile * TILE + (uint64_t)threadIdx.x * EPT;
+    const bool active = base < a.total;               // total % EPT == 0: whole vector or nothing
+
+    uint64_t key[EPT];
+    uint32_t gid[EPT];
+    int pslot[EPT];
+    unsigned owner = 0u, pending = 0u;
+
+    if (active) {
+      uint4 l = make_uint4(0u, 0u, 0u, 0u);
+      if (a.lab_in) l = __ldcs(reinterpret_cast<const uint4*>(a.lab_in + base));
+      const uint32_t lv[EPT] = {l.x, l.y, l.z, l.w};
+      if (MODE == KM_PAIR) {
+        const uint4 m = __ldcs(reinterpret_cast<const uint4*>(a.lab2 + base));
+        const uint32_t mv[EPT] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) key[e] = ((uint64_t)mv[e] << a.lbits) | lv[e];
+      } else {
+        double v[EPT];
+        if (a.fillproj) {
+          const uint4 p = __ldcs(reinterpret_cast<const uint4*>(a.pid + base));
+          const uint32_t pv[EPT] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+          for (int e = 0; e < EPT; ++e) v[e] = __dsub_rn(__ldg(a.lut + lv[e]), __ldg(a.tpat + pv[e]));
+        } else {
+          const double2 v0 = __ldcs(reinterpret_cast<const double2*>(a.vals + base));
+          const double2 v1 = __ldcs(reinterpret_cast<const double2*>(a.vals + base + 2));
+          v[0] = v0.x; v[1] = v0.y; v[2] = v1.x; v[3] = v1.y;
+        }
+        double r[EPT];
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          uint64_t code;
+          if (a.do_round) {
+            code = round_code(v[e], a.atol, a.scale, a.iscale, a.qbits, r[e]);
+            if (MODE == KM_RAW) code = raw_code(r[e]);
+          } else {
+            r[e] = v[e];
+            code = a.raw_bits ? (uint64_t)__double_as_longlong(v[e]) : raw_code(v[e]);
+          }
+          key[e] = (MODE == KM_RAW) ? code : ((code << a.lbits) | lv[e]);
+        }
+        if (a.vals_out) {
+          __stcs(reinterpret_cast<double2*>(a.vals_out + base), make_double2(r[0], r[1]));
+          __stcs(reinterpret_cast<double2*>(a.vals_out + base + 2), make_double2(r[2], r[3]));
+        }
+      }
+
+      // ---- phase A: resolve keys against the CTA cache ------------------------
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const uint64_t k = key[e];
+        const uint32_t idx = (uint32_t)(base + e);
+        pslot[e] = -1;
+        gid[e] = 0u;
+        if (k == 0ull) continue;                        // the zero class keeps id 0
+        if (e > 0 && k == key[e - 1]) {                 // run of equal keys inside the thread
+          gid[e] = gid[e - 1];
+          pslot[e] = pslot[e - 1];
+          if (pslot[e] >= 0) pending |= 1u << e;
+          continue;
+        }
+        const uint64_t h = mix64(k);
+        if (!a.use_cache) {
+          const uint32_t g = global_insert(a, k, h);
+          atomicMin(a.gmin + (g - 1), idx);
+          gid[e] = g;
+          continue;
+        }
+        uint32_t s = (uint32_t)h & (SC - 1);
+        for (int probe = 0; probe < SC; ++probe) {
+          const uint64_t kk = *reinterpret_cast<volatile uint64_t*>(skeys + s);
+          if (kk == k) {
+            const uint32_t g = *reinterpret_cast<volatile uint32_t*>(sgid + s);
+            if (g != 0u) {
+              gid[e] = g;                               // steady state: one smem hit
+            } else {                                    // inserted during this tile by another thread
+              atomicMin(smin + s, idx);
+              pslot[e] = (int)s;
+              pending |= 1u << e;
+            }
+            break;
+          }
+          if (kk == KEY_EMPTY) {
+            if (*reinterpret_cast<volatile uint32_t*>(&s_count) >= (uint32_t)SC_LIMIT) {
+              const uint32_t g = global_insert(a, k, h);   // cache full: go to the global table
+              atomicMin(a.gmin + (g - 1), idx);
+              gid[e] = g;
+              break;
+            }
+            const unsigned long long old =
+                atomicCAS(reinterpret_cast<unsigned long long*>(skeys + s), KEY_EMPTY, (unsigned long long)k);
+            if (old == KEY_EMPTY || old == (unsigned long long)k) {
+              if (old == KEY_EMPTY) {
+                atomicAdd(&s_count, 1u);
+                owner |= 1u << e;
+              }
+              atomicMin(smin + s, idx);
+              pslot[e] = (int)s;
+              pending |= 1u << e;
+              break;
+            }
+          }
+          s = (s + 1) & (SC - 1);
+        }
+      }
+    }
+
+    // ---- phases B/C only when this tile met keys new to the CTA ---------------
+    if (__syncthreads_or((int)pending)) {
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        if (owner & (1u << e)) {
+          const uint32_t s = (uint32_t)pslot[e];
+          const uint32_t g = global_insert(a, key[e], mix64(key[e]));
+          atomicMin(a.gmin + (g - 1), smin[s]);
+          *reinterpret_cast<volatile uint32_t*>(sgid + s) = g;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < EPT; ++e)
+        if (pending & (1u << e)) gid[e] = *reinterpret_cast<volatile uint32_t*>(sgid + pslot[e]);
+    }
+    if (active) __stcs(reinterpret_cast<uint4*>(a.lab_out + base), make_uint4(gid[0], gid[1], gid[2], gid[3]));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// canonical ranking of a table: rank[slot+1] = 1 + #{keys whose first index is smaller}
+// ---------------------------------------------------------------------------
+__global__ void gather_minidx_kernel(const uint32_t* __restrict__ occ, const uint32_t* __restrict__ gmin,
+                                     uint32_t* __restrict__ mi, uint32_t count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) mi[i] = gmin[occ[i]];
+}
+
+__global__ void __launch_bounds__(256) rank_brute_kernel(const uint32_t* __restrict__ occ,
+                                                         const uint32_t* __restrict__ mi,
+                                                         uint32_t* __restrict__ rank, uint32_t count) {
+  __shared__ uint32_t tile[1024];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t mine = i < count ? mi[i] : 0u;
+  uint32_t r = 0;
+  for (uint32_t j0 = 0; j0 < count; j0 += 1024) {
+    for (uint32_t t = threadIdx.x; t < 1024; t += blockDim.x) tile[t] = (j0 + t < count) ? mi[j0 + t] : 0xffffffffu;
+    __syncthreads();
+    const uint32_t lim = min(1024u, count - j0);
+    for (uint32_t t = 0; t < lim; ++t) r += (tile[t] < mine) ? 1u : 0u;
+    __syncthreads();
+  }
+  if (i < count) rank[occ[i] + 1] = r + 1;
+}
+
+__global__ void bitmap_set_kernel(const uint32_t* __restrict__ occ, const uint32_t* __restrict__ gmin,
+                                  uint32_t* __restrict__ bitmap, uint32_t count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    const uint32_t idx = gmin[occ[i]];
+    atomicOr(bitmap + (idx >> 5), 1u << (idx & 31u));
+  }
+}
+
+// one CTA of 1024 threads per 1024 bitmap words: exclusive popcount prefix per word + block total
+__global__ void __launch_bounds__(1024) bitmap_scan_kernel(const uint32_t* __restrict__ bitmap,
+                                                           uint32_t* __restrict__ wordpre,
+                                                           uint32_t* __restrict__ blocksum, uint64_t nwords) {
+  __shared__ uint32_t wsum[32];
+  const uint64_t w = (uint64_t)blockIdx.x * 1024 + threadIdx.x;
+  const uint32_t c = w < nwords ? __popc(bitmap[w]) : 0u;
+  uint32_t incl = c;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t v = wsum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    wsum[lane] = v;   // inclusive over warps
+  }
+  __syncthreads();
+  const uint32_t warp_off = wid ? wsum[wid - 1] : 0u;
+  if (w < nwords) wordpre[w] = warp_off + incl - c;
+  if (threadIdx.x == 1023) blocksum[blockIdx.x] = warp_off + incl;
+}
+
+// single CTA: exclusive scan of the block totals in place
+__global__ void __launch_bounds__(1024) blocksum_scan_kernel(uint32_t* __restrict__ blocksum, uint32_t nblocks) {
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0u;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint32_t b0 = 0; b0 < nblocks; b0 += 1024) {
+    const uint32_t i = b0 + threadIdx.x;
+    const uint32_t c = i < nblocks ? blocksum[i] : 0u;
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t v = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+      }
+      wsum[lane] = v;
+    }
+    __syncthreads();
+    const uint32_t off = carry + (wid ? wsum[wid - 1] : 0u);
+    if (i < nblocks) blocksum[i] = off + incl - c;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = off + incl;
+    __syncthreads();
+  }
+}
+
+__global__ void bitmap_rank_kernel(const uint32_t* __restrict__ occ, const uint32_t* __restrict__ gmin,
+                                   const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ wordpre,
+                                   const uint32_t* __restrict__ blocksum, uint32_t* __restrict__ rank,
+                                   uint32_t count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    const uint32_t s = occ[i];
+    const uint32_t idx = gmin[s];
+    const uint32_t w = idx >> 5;
+    const uint32_t below = __popc(bitmap[w] & ((1u << (idx & 31u)) - 1u));
+    rank[s + 1] = blocksum[w >> 10] + wordpre[w] + below + 1u;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// fill! (src/partitions.jl:68-75): lut composition and the label -> value gather
+// ---------------------------------------------------------------------------
+__global__ void build_lut_kernel(const uint32_t* __restrict__ occ, const uint32_t* __restrict__ rank,
+                                 const double* __restrict__ values, double* __restrict__ lut, uint32_t count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) lut[0] = 0.0;
+  if (i < count) {
+    const uint32_t p = occ[i] + 1;
+    lut[p] = values[rank[p] - 1];
+  }
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(const uint32_t* __restrict__ labels,
+                                                   const double* __restrict__ lut, double* __restrict__ X,
+                                                   uint64_t total) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
+  for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; base < total; base += stride) {
+    const uint4 l = __ldcs(reinterpret_cast<const uint4*>(labels + base));
+    const double a = __ldg(lut + l.x), b = __ldg(lut + l.y), c = __ldg(lut + l.z), d = __ldg(lut + l.w);
+    __stcs(reinterpret_cast<double2*>(X + base), make_double2(a, b));
+    __stcs(reinterpret_cast<double2*>(X + base + 2), make_double2(c, d));
+  }
+}
+
+// canonical labels, unpadded: out[i + n*j] = rank[labels[i + ld*j]]
+__global__ void canonical_kernel(const uint32_t* __restrict__ labels, const uint32_t* __restrict__ rank,
+                                 uint32_t* __restrict__ out, int64_t n, int64_t ld) {
+  const int64_t j = blockIdx.y;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i + n * j] = rank[labels[i + ld * j]];
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+void sdpsr_table_free(KeyTable& t) {
+  cudaFree(t.keys);   // minidx lives in the same allocation
+  cudaFree(t.rank);
+  cudaFree(t.occ);
+  cudaFree(t.meta);
+  t = KeyTable();
+}
+
+int sdpsr_table_alloc(sdpsr_ctx* ctx, KeyTable& t, size_t cap) {
+  if (t.alloc >= cap && t.keys) {
+    t.cap = (uint32_t)cap;
+    t.minidx = reinterpret_cast<uint32_t*>(t.keys + t.cap);
+    return SDPSR_OK;
+  }
+  sdpsr_table_free(t);
+  // keys and minidx share one allocation so that a single memset(0xff) clears both
+  SDPSR_CUDA(cudaMalloc(&t.keys, cap * 12));
+  t.minidx = reinterpret_cast<uint32_t*>(t.keys + cap);
+  SDPSR_CUDA(cudaMalloc(&t.rank, (cap + 1) * sizeof(uint32_t)));
+  SDPSR_CUDA(cudaMalloc(&t.occ, cap * sizeof(uint32_t)));
+  SDPSR_CUDA(cudaMalloc(&t.meta, 4 * sizeof(uint32_t)));
+  t.alloc = cap;
+  t.cap = (uint32_t)cap;
+  return SDPSR_OK;
+}
+
+int sdpsr_round_params(sdpsr_ctx* ctx, double atol, double* scale, long long* iscale, int* qbits) {
+  SDPSR_REQUIRE(atol > 1e-300 && atol <= 0.1 && std::isfinite(atol), SDPSR_E_INVALID,
+                "atol must be in (1e-300, 0.1]");
+  const int sig = (int)std::floor(-std::log10(atol));   // src/utils.jl:37
+  SDPSR_REQUIRE(sig >= 1 && sig <= 15, SDPSR_E_INVALID, "floor(-log10(atol)) must be in 1..15");
+  long long s = 1;
+  for (int i = 0; i < sig; ++i) s *= 10;
+  *iscale = s;
+  *scale = (double)s;
+  *qbits = bits_for((uint64_t)s);
+  return SDPSR_OK;
+}
+
+static size_t initial_cap(sdpsr_ctx* ctx) {
+  if (ctx->flags & SDPSR_F_TINY_TABLE) return 64;
+  size_t want = next_pow2(2 * (uint64_t)ctx->elems);
+  return std::max<size_t>(64, std::min<size_t>(want, (size_t)1 << 20));
+}
+
+int sdpsr_rank_table(sdpsr_ctx* ctx, KeyTable& t) {
+  const uint32_t count = t.count;
+  Timed tm(ctx, SDPSR_K_RANK, (double)count * 8.0);
+  SDPSR_CUDA(cudaMemsetAsync(t.rank, 0, sizeof(uint32_t), ctx->stream));
+  if (count == 0) return SDPSR_OK;
+  const uint32_t* gmin = t.minidx;
+  const int blocks = (int)((count + 255) / 256);
+  const bool brute = count <= (uint32_t)RANK_BRUTE_MAX && !(ctx->flags & SDPSR_F_FORCE_BITMAP_RANK);
+  if (brute) {
+    if (ctx->rk_alloc < count) {
+      cudaFree(ctx->rk_mi);
+      ctx->rk_mi = nullptr;
+      const size_t want = std::max<size_t>(count, 4096);
+      SDPSR_CUDA(cudaMalloc(&ctx->rk_mi, want * sizeof(uint32_t)));
+      ctx->rk_alloc = want;
+    }
+    gather_minidx_kernel<<<blocks, 256, 0, ctx->stream>>>(t.occ, gmin, ctx->rk_mi, count);
+    rank_brute_kernel<<<blocks, 256, 0, ctx->stream>>>(t.occ, ctx->rk_mi, t.rank, count);
+    count_launch(ctx, 2);
+  } else {
+    const uint64_t nwords = (ctx->elems + 31) / 32;
+    const uint64_t nblk = (nwords + 1023) / 1024;
+    if (!ctx->bitmap) {
+      SDPSR_CUDA(cudaMalloc(&ctx->bitmap, nwords * 2 * sizeof(uint32_t)));   // bitmap + wordpre
+      SDPSR_CUDA(cudaMalloc(&ctx->bm_block, nblk * sizeof(uint32_t)));
+      ctx->bm_blocks = nblk;
+    }
+    uint32_t* wordpre = ctx->bitmap + nwords;
+    SDPSR_CUDA(cudaMemsetAsync(ctx->bitmap, 0, nwords * sizeof(uint32_t), ctx->stream));
+    bitmap_set_kernel<<<blocks, 256, 0, ctx->stream>>>(t.occ, gmin, ctx->bitmap, count);
+    bitmap_scan_kernel<<<(unsigned)nblk, 1024, 0, ctx->stream>>>(ctx->bitmap, wordpre, ctx->bm_block, nwords);
+    blocksum_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->bm_block, (uint32_t)nblk);
+    bitmap_rank_kernel<<<blocks, 256, 0, ctx->stream>>>(t.occ, gmin, ctx->bitmap, wordpre, ctx->bm_block, t.rank,
+                                                        count);
+    count_launch(ctx, 4);
+  }
+  SDPSR_CUDA(cudaGetLastError());
+  return SDPSR_OK;
+}
+
+int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
+  static bool attr_set = false;
+  const size_t smem = (size_t)SC * (8 + 4 + 4);
+  if (!attr_set) {
+    SDPSR_CUDA(cudaFuncSetAttribute(refine_kernel<KM_ROUND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDPSR_CUDA(cudaFuncSetAttribute(refine_kernel<KM_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDPSR_CUDA(cudaFuncSetAttribute(refine_kernel<KM_PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  KeyTable& told = ctx->tab[ctx->cur];
+  KeyTable& tnew = spec.table_override ? *spec.table_override : ctx->tab[ctx->cur ^ 1];
+
+  RefineArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.lab_in = spec.ignore_labels ? nullptr : ctx->labels;
+  a.lab2 = spec.lab2;
+  a.vals = spec.vals;
+  a.vals_out = spec.vals_out;
+  a.lut = spec.lut;
+  a.tpat = spec.tpat;
+  a.pid = spec.pid;
+  a.lab_out = spec.out_override ? spec.out_override : ctx->labels_alt;
+  a.total = ctx->elems;
+  a.atol = spec.atol;
+  a.do_round = spec.do_round ? 1 : 0;
+  a.fillproj = spec.fillproj ? 1 : 0;
+  a.raw_bits = spec.raw_bits ? 1 : 0;
+  a.use_cache = (ctx->flags & SDPSR_F_NO_SMEM_CACHE) ? 0 : 1;
+  a.lbits = spec.ignore_labels ? 1 : bits_for((uint64_t)told.cap);   // provisional ids are <= cap
+  if (spec.do_round && spec.mode != KM_PAIR) SDPSR_TRY(sdpsr_round_params(ctx, spec.atol, &a.scale, &a.iscale, &a.qbits));
+  if (spec.mode == KM_ROUND) {
+    SDPSR_REQUIRE(spec.do_round, SDPSR_E_INVALID, "KM_ROUND needs rounding");
+    SDPSR_REQUIRE(12 + a.qbits + a.lbits <= 64, SDPSR_E_UNSUPPORTED, "fused key does not fit 64 bits");
+  }
+
+  size_t cap = tnew.cap ? tnew.cap : initial_cap(ctx);
+  if (cap < initial_cap(ctx)) cap = initial_cap(ctx);
+  const size_t cap_max = std::max<size_t>(64, next_pow2(2 * (uint64_t)ctx->elems));
+  const uint64_t ntiles = (ctx->elems + TILE - 1) / TILE;
+  const int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * 3);
+
+  for (;;) {
+    SDPSR_TRY(sdpsr_table_alloc(ctx, tnew, cap));
+    SDPSR_CUDA(cudaMemsetAsync(tnew.keys, 0xff, (size_t)tnew.cap * 12, ctx->stream));
+    SDPSR_CUDA(cudaMemsetAsync(tnew.meta, 0, 4 * sizeof(uint32_t), ctx->stream));
+    a.gkeys = tnew.keys;
+    a.gmin = tnew.minidx;
+    a.gocc = tnew.occ;
+    a.gmeta = tnew.meta;
+    a.gmask = tnew.cap - 1;
+    a.glimit = tnew.cap / 2;
+    {
+      Timed tm(ctx, SDPSR_K_REFINE, (double)ctx->elems * 16.0);
+      switch (spec.mode) {
+        case KM_ROUND: refine_kernel<KM_ROUND><<<grid, RT, smem, ctx->stream>>>(a); break;
+        case KM_RAW: refine_kernel<KM_RAW><<<grid, RT, smem, ctx->stream>>>(a); break;
+        case KM_PAIR: refine_kernel<KM_PAIR><<<grid, RT, smem, ctx->stream>>>(a); break;
+      }
+      count_launch(ctx);
+    }
+    SDPSR_CUDA(cudaGetLastError());
+    uint32_t* hm = reinterpret_cast<uint32_t*>(ctx->h_pinned);
+    SDPSR_CUDA(cudaMemcpyAsync(hm, tnew.meta, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (hm[1] == 0u) {
+      tnew.count = hm[0];
+      break;
+    }
+    SDPSR_REQUIRE(cap < cap_max, SDPSR_E_ALLOC, "key table overflow at maximum capacity");
+    cap = std::min(cap * 4, cap_max);
+  }
+  SDPSR_TRY(sdpsr_rank_table(ctx, tnew));
+  if (!spec.out_override) {
+    std::swap(ctx->labels, ctx->labels_alt);
+    ctx->cur ^= 1;
+    ctx->dim = tnew.count;
+    ctx->x_is_fill = false;
+  }
+  if (dim) *dim = tnew.count;
+  return SDPSR_OK;
+}
+
+int sdpsr_ensure_tmp_labels(sdpsr_ctx* ctx) {
+  if (!ctx->labels_tmp) {
+    SDPSR_CUDA(cudaMalloc(&ctx->labels_tmp, ctx->elems * sizeof(uint32_t)));
+    SDPSR_CUDA(cudaMemsetAsync(ctx->labels_tmp, 0, ctx->elems * sizeof(uint32_t), ctx->stream));
+  }
+  return SDPSR_OK;
+}
+
+// S = refine!(S, Partition(round?(M))) for a device-resident padded matrix.
+// Fused single pass when the (id, value code) pair fits 64 bits, otherwise the
+// reference's own two steps: ids of Part(M) first, then the pair pass.
+int sdpsr_generic_refine_values(sdpsr_ctx* ctx, const double* dvals, double atol, bool do_round,
+                                double* vals_out, int64_t* dim) {
+  bool fused = do_round;
+  if (fused) {
+    double sc;
+    long long isc;
+    int qb;
+    SDPSR_TRY(sdpsr_round_params(ctx, atol, &sc, &isc, &qb));
+    fused = 12 + qb + bits_for((uint64_t)ctx->tab[ctx->cur].cap) <= 64;
+  }
+  RefineSpec sp;
+  sp.vals = dvals;
+  sp.vals_out = vals_out;
+  sp.atol = atol;
+  sp.do_round = do_round;
+  if (fused) {
+    sp.mode = KM_ROUND;
+    return sdpsr_refine_pass(ctx, sp, dim);
+  }
+  if (ctx->dim == 0 && ctx->tab[ctx->cur].count == 0) {   // empty S: Part(M) itself
+    sp.mode = KM_RAW;
+    sp.ignore_labels = true;
+    return sdpsr_refine_pass(ctx, sp, dim);
+  }
+  SDPSR_TRY(sdpsr_ensure_tmp_labels(ctx));
+  KeyTable scratch;
+  sp.mode = KM_RAW;
+  sp.ignore_labels = true;
+  sp.out_override = ctx->labels_tmp;
+  sp.table_override = &scratch;
+  int64_t d2 = 0;
+  int st = sdpsr_refine_pass(ctx, sp, &d2);
+  if (st == SDPSR_OK) {
+    RefineSpec pr;
+    pr.mode = KM_PAIR;
+    pr.lab2 = ctx->labels_tmp;
+    pr.do_round = false;
+    st = sdpsr_refine_pass(ctx, pr, dim);
+  }
+  sdpsr_table_free(scratch);
+  return st;
+}
+
+int sdpsr_upload_values(sdpsr_ctx* ctx, const double* values, int64_t len) {
+  if (ctx->values_alloc < (size_t)len) {
+    cudaFree(ctx->d_values);
+    ctx->d_values = nullptr;
+    const size_t want = std::max<size_t>((size_t)len, 4096);
+    SDPSR_CUDA(cudaMalloc(&ctx->d_values, want * sizeof(double)));
+    ctx->values_alloc = want;
+  }
+  if (len > 0)
+    SDPSR_CUDA(cudaMemcpyAsync(ctx->d_values, values, (size_t)len * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  return SDPSR_OK;
+}
+
+int sdpsr_build_lut(sdpsr_ctx* ctx, const double* d_values, int64_t len) {
+  KeyTable& t = ctx->tab[ctx->cur];
+  SDPSR_REQUIRE(len == (int64_t)t.count, SDPSR_E_INVALID, "length(values) != dim(P) (src/partitions.jl:69)");
+  const size_t need = (size_t)t.cap + 1;
+  if (ctx->lut_alloc < need) {
+    cudaFree(ctx->lut);
+    ctx->lut = nullptr;
+    SDPSR_CUDA(cudaMalloc(&ctx->lut, need * sizeof(double)));
+    ctx->lut_alloc = need;
+  }
+  const int blocks = (int)std::max<uint32_t>(1, (t.count + 255) / 256);
+  build_lut_kernel<<<blocks, 256, 0, ctx->stream>>>(t.occ, t.rank, d_values, ctx->lut, t.count);
+  count_launch(ctx);
+  SDPSR_CUDA(cudaGetLastError());
+  return SDPSR_OK;
+}
+
+int sdpsr_materialize_fill(sdpsr_ctx* ctx, double* dst) {
+  Timed tm(ctx, SDPSR_K_FILL, (double)ctx->elems * 12.0);
+  const uint64_t per = 256 * 4;
+  const int grid = (int)std::min<uint64_t>((ctx->elems + per - 1) / per, (uint64_t)ctx->sm_count * 8);
+  fill_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->labels, ctx->lut, dst, ctx->elems);
+  count_launch(ctx);
+  SDPSR_CUDA(cudaGetLastError());
+  return SDPSR_OK;
+}
+
+int sdpsr_canonical_labels(sdpsr_ctx* ctx, uint32_t* dst_unpadded) {
+  KeyTable& t = ctx->tab[ctx->cur];
+  dim3 grid((unsigned)std::min<int64_t>((ctx->n + 255) / 256, 64), (unsigned)ctx->n);
+  canonical_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->labels, t.rank, dst_unpadded, ctx->n, ctx->ld);
+  count_launch(ctx);
+  SDPSR_CUDA(cudaGetLastError());
+  return SDPSR_OK;
+}

@@ -1,0 +1,240 @@
+// Internal declarations shared by the translation units of libsdpsr_cuda.so.
+// Nothing here is part of the C ABI (include/sdpsr.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sdpsr.h"
+
+// --------------------------------------------------------------------------
+// error plumbing
+// --------------------------------------------------------------------------
+#define SDPSR_CUDA(call)                                                               \
+  do {                                                                                 \
+    cudaError_t _e = (call);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      return ctx->fail(SDPSR_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+    }                                                                                  \
+  } while (0)
+
+#define SDPSR_TRY(expr)          \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != SDPSR_OK) return _s; \
+  } while (0)
+
+#define SDPSR_REQUIRE(cond, code, msg)              \
+  do {                                              \
+    if (!(cond)) return ctx->fail((code), (msg));   \
+  } while (0)
+
+// --------------------------------------------------------------------------
+// key table: open-addressing hash  key -> (first occurrence idx, canonical rank)
+// A "provisional id" of an entry is slot+1 of its key (0 is reserved for the
+// zero key: old label 0 and value +0.0), see DESIGN.md "lazy canonical labels".
+// --------------------------------------------------------------------------
+constexpr uint64_t KEY_EMPTY = ~0ull;
+
+struct KeyTable {
+  uint64_t* keys = nullptr;    // [cap]      KEY_EMPTY when free
+  uint32_t* minidx = nullptr;  // [cap]      smallest padded linear index holding the key
+  uint32_t* rank = nullptr;    // [cap + 1]  canonical label of provisional id (rank[0] = 0)
+  uint32_t* occ = nullptr;     // [cap]      list of occupied slots, in claim order
+  uint32_t* meta = nullptr;    // [4]        {count, overflow, -, -}
+  uint32_t cap = 0;            // power of two
+  uint32_t count = 0;          // host copy of meta[0] after the pass == dim
+  size_t alloc = 0;            // allocated capacity
+};
+
+struct ConstraintSet {
+  int64_t m = 0;
+  int64_t nnz = 0;
+  // CSR of A on the device (column index = padded linear index)
+  int64_t* d_rowptr = nullptr;   // unused on device, kept for symmetry
+  uint32_t* d_col = nullptr;     // [nnz]
+  double* d_val = nullptr;       // [nnz]
+  uint32_t* d_chunk_row = nullptr;   // [nchunks] row of each reduction chunk
+  uint32_t* d_chunk_beg = nullptr;   // [nchunks+1] nnz range of each chunk
+  int64_t nchunks = 0;
+  double* d_partial = nullptr;   // [nchunks]
+  // per-entry pattern ids and the pattern table
+  uint32_t* d_pid = nullptr;     // [elems]  0 = entry touched by no constraint
+  int64_t npat = 0;              // patterns 1..npat
+  std::vector<int64_t> pat_ptr;  // [npat+2]
+  std::vector<int32_t> pat_row;
+  std::vector<double> pat_val;
+  std::vector<int64_t> pat_cnt;  // [npat+1]
+  std::vector<uint32_t> chunk_row;   // host copy
+  std::vector<double> gram_lu;   // m x m LU factors (row-major) of A A'
+  std::vector<int> gram_piv;
+  double* d_tpat = nullptr;      // [npat+1]
+  // host CSR copy (needed to read pattern columns)
+  std::vector<int64_t> h_rowptr;
+  std::vector<int64_t> h_col;    // unpadded linear index
+  std::vector<double> h_val;
+  bool ready = false;
+};
+
+struct EventPair {
+  cudaEvent_t a, b;
+  int family;
+  double work;
+};
+
+struct sdpsr_ctx {
+  int device = 0;
+  int64_t n = 0;        // matrix order N
+  int64_t ld = 0;       // leading dimension of every device matrix (N rounded up to 16)
+  size_t elems = 0;     // ld * n
+  uint32_t flags = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+
+  // Partition S: provisional ids, double buffered; tab[cur] maps them to canonical labels
+  uint32_t* labels = nullptr;
+  uint32_t* labels_alt = nullptr;
+  uint32_t* labels_tmp = nullptr;   // lazily allocated third buffer (generic two-step refine, IO)
+  KeyTable tab[2];
+  int cur = 0;
+  int64_t dim = 0;
+
+  double* X = nullptr;   // [elems]
+  double* X2 = nullptr;  // [elems]
+  double* Q = nullptr;   // lazily allocated (blockDiagonalize)
+  double* W = nullptr;
+  double* T = nullptr;   // scratch N x N (Q', products)
+  double* Qhat = nullptr;
+  int64_t qhat_cols = 0;
+  std::vector<int64_t> blk_sizes;
+  bool have_Q = false;
+
+  // fill state: lut[provisional id] for the last sdpsr_fill
+  double* lut = nullptr;
+  size_t lut_alloc = 0;
+  double* d_values = nullptr;   // staging for host coefficient vectors
+  size_t values_alloc = 0;
+  bool x_is_fill = false;       // X == fill(S, lut) and S unchanged since
+  bool x_valid = false;
+  bool x_symmetric = false;     // X known symmetric (labels transpose-invariant, symmetric constraints)
+
+  // ranking scratch
+  uint32_t* rk_mi = nullptr;    // dense minidx list
+  size_t rk_alloc = 0;
+  uint32_t* bitmap = nullptr;   // [elems/32] first-occurrence bitmap
+  uint32_t* bm_block = nullptr; // per-block popcount prefix
+  size_t bm_blocks = 0;
+
+  uint32_t* d_scalars = nullptr;   // small device scratch (64 words)
+  void* h_pinned = nullptr;        // small pinned host scratch (4 KB)
+
+  ConstraintSet cons;
+
+  // cusolver state (opaque here)
+  void* solver = nullptr;
+  void* solver_work = nullptr;
+  size_t solver_work_bytes = 0;
+  int* solver_info = nullptr;
+  void* solver_hwork = nullptr;
+  size_t solver_hwork_bytes = 0;
+
+  // comm (multi-GPU)
+  void* nccl = nullptr;
+  int nranks = 1, rank = 0;
+
+  // timing
+  std::vector<EventPair> ev_pending;
+  std::vector<cudaEvent_t> ev_pool;
+  double t_ms[SDPSR_K_COUNT] = {0};
+  int64_t t_launch[SDPSR_K_COUNT] = {0};
+  double t_work[SDPSR_K_COUNT] = {0};
+  int64_t launches = 0;
+
+  std::string err;
+
+  int fail(int code, const std::string& msg) {
+    err = msg;
+    return code;
+  }
+};
+
+// RAII-less timing helper: tic() before a kernel family, toc() after.
+struct Timed {
+  sdpsr_ctx* c;
+  int fam;
+  double work;
+  cudaEvent_t a = nullptr, b = nullptr;
+  Timed(sdpsr_ctx* ctx, int family, double work_);
+  ~Timed();
+};
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline uint32_t next_pow2(uint64_t x) {
+  uint64_t p = 1;
+  while (p < x) p <<= 1;
+  return (uint32_t)(p > 0x80000000ull ? 0x80000000ull : p);
+}
+static inline int bits_for(uint64_t maxval) {
+  int b = 1;
+  while ((maxval >> b) != 0) ++b;
+  return b;
+}
+
+// --------------------------------------------------------------------------
+// cross-TU entry points (host functions)
+// --------------------------------------------------------------------------
+// refine.cu
+enum KeyMode { KM_ROUND = 0, KM_RAW = 1, KM_PAIR = 2 };
+struct RefineSpec {
+  KeyMode mode = KM_ROUND;
+  const double* vals = nullptr;     // value source array (padded layout) or null
+  double* vals_out = nullptr;       // optional: write the rounded values here
+  const uint32_t* lab2 = nullptr;   // KM_PAIR: second provisional-id array
+  int lab2_bits = 0;                // (unused, informational)
+  bool fillproj = false;            // value = lut[label] - tpat[pid] instead of vals[idx]
+  const double* lut = nullptr;
+  const double* tpat = nullptr;
+  const uint32_t* pid = nullptr;
+  bool do_round = true;
+  bool raw_bits = false;            // KM_RAW: key = the 64 bits of vals[idx] verbatim (signatures, not floats)
+  double atol = 0;
+  bool ignore_labels = false;       // treat the current labels as all-zero (fresh partition)
+  uint32_t* out_override = nullptr; // write provisional ids here instead of labels_alt (no swap)
+  KeyTable* table_override = nullptr;
+};
+int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim);
+int sdpsr_generic_refine_values(sdpsr_ctx* ctx, const double* dvals, double atol, bool do_round,
+                                double* vals_out, int64_t* dim);
+int sdpsr_table_alloc(sdpsr_ctx* ctx, KeyTable& t, size_t cap);
+void sdpsr_table_free(KeyTable& t);
+int sdpsr_rank_table(sdpsr_ctx* ctx, KeyTable& t);
+int sdpsr_build_lut(sdpsr_ctx* ctx, const double* d_values, int64_t len);
+int sdpsr_materialize_fill(sdpsr_ctx* ctx, double* dst);
+int sdpsr_canonical_labels(sdpsr_ctx* ctx, uint32_t* dst_unpadded);
+int sdpsr_round_params(sdpsr_ctx* ctx, double atol, double* scale, long long* iscale, int* qbits);
+int sdpsr_ensure_tmp_labels(sdpsr_ctx* ctx);
+int sdpsr_upload_values(sdpsr_ctx* ctx, const double* values, int64_t len);
+
+// gemm_f64.cu :  C[M x Nc] = A[M x K] * B[K x Nc], all column-major with the given lds
+int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t ldb,
+                   double* C, int64_t ldc, int64_t M, int64_t Nc, int64_t K, bool symmetric_out);
+
+// project.cu
+int sdpsr_constraints_finalize(sdpsr_ctx* ctx);
+void sdpsr_constraints_free(sdpsr_ctx* ctx);
+int sdpsr_rowdots(sdpsr_ctx* ctx, const double* x_array, const double* lut, std::vector<double>& out);
+int sdpsr_solve_gram(sdpsr_ctx* ctx, std::vector<double>& rhs);
+int sdpsr_upload_tpat(sdpsr_ctx* ctx, const std::vector<double>& coef);
+int sdpsr_symmetric_check(sdpsr_ctx* ctx, int* is_sym);
+
+// blockdiag.cu
+void sdpsr_blockdiag_free(sdpsr_ctx* ctx);
+
+// comm.cu
+void sdpsr_comm_free(sdpsr_ctx* ctx);
+
+// launch bookkeeping
+static inline void count_launch(sdpsr_ctx* ctx, int k = 1) { ctx->launches += k; }

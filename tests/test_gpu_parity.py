@@ -1,0 +1,344 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via ctypes) against the CPU
+oracle on identical inputs and identical random coefficients.  Integer results
+(labels, dims, block sizes) must be bit-exact; block values within 1e-8 relative
+(the tolerance BASELINE.json's north_star states)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+import sdpsr_b200 as S
+from sdpsr_b200 import binding as B
+from sdpsr_b200 import problems as pr
+
+from conftest import GOLDEN, Coeffs
+
+pytestmark = pytest.mark.gpu
+
+ATOL = O.jordan.RTOL_DEFAULT
+FLAG_SETS = [0, B.F_TINY_TABLE, B.F_FORCE_BITMAP_RANK, B.F_NO_SMEM_CACHE,
+             B.F_TINY_TABLE | B.F_FORCE_BITMAP_RANK | B.F_NO_SMEM_CACHE]
+
+
+@pytest.fixture(scope="module")
+def vec():
+    with open(os.path.join(GOLDEN, "runtests_vectors.json")) as fh:
+        return json.load(fh)
+
+
+def oracle_refine_values(P, M, do_round=True):
+    Mr = O.clamp_round(M, ATOL) if do_round else M
+    P2 = O.partition_from_values(Mr)
+    return P2 if P is None else O.refine(P, P2)
+
+
+# ---------------------------------------------------------------------------------
+# refine / labels / fill
+# ---------------------------------------------------------------------------------
+def test_library_reports_device():
+    assert B.device_count() >= 1
+    assert B.load_library().sdpsr_version() >= 100
+
+
+@pytest.mark.parametrize("flags", FLAG_SETS)
+def test_runtests_label_vectors(vec, flags):
+    """test/runtests.jl:22-25 through set_labels / refine_labels / get_labels."""
+    P1, P2, P3 = (np.array(vec[k]) for k in ("P1", "P2", "P3_coarsest_P1_P2"))
+    with B.Context(3, 0, flags) as ctx:
+        assert ctx.set_labels(P1) == 3
+        assert np.array_equal(ctx.get_labels(), P1)
+        assert ctx.refine_labels(P2) == 6
+        assert np.array_equal(ctx.get_labels(), P3)
+        for dt in (np.uint8, np.uint16, np.uint32, np.uint64):
+            assert np.array_equal(ctx.get_labels(dt), P3)
+        assert ctx.zero_count() == 0
+
+
+@pytest.mark.parametrize("flags", FLAG_SETS)
+@pytest.mark.parametrize("n,nvals,seed", [(10, 10, 0), (10, 10, 1), (37, 5, 2), (64, 3000, 3), (129, 40, 4)])
+def test_partition_ctor_matches_oracle(n, nvals, seed, flags):
+    """test/runtests.jl:13-20: integer and float constructors, with and without zeros."""
+    rng = np.random.default_rng(seed)
+    M = rng.integers(0 if seed % 2 == 0 else 1, nvals + 1, size=(n, n))
+    want = O.partition_from_values(M)
+    with B.Context(n, 0, flags) as ctx:
+        assert ctx.set_labels(M) == want.nparts
+        assert np.array_equal(ctx.get_labels(), want.matrix)
+        ctx.reset()
+        assert ctx.refine_values(M.astype(np.float64), ATOL, do_round=False) == want.nparts
+        assert np.array_equal(ctx.get_labels(), want.matrix)
+        assert ctx.zero_count() == int((M == 0).sum())
+
+
+def adversarial_values(rng, n):
+    """Values that stress the truncation grid: powers of two, fractions one
+    ulp below 1, values around atol, both signs, wide exponent range, exact decimals."""
+    base = np.concatenate([
+        2.0 ** rng.integers(-40, 40, size=50),
+        np.nextafter(2.0 ** rng.integers(-20, 20, size=50), 0),
+        np.nextafter(2.0 ** rng.integers(-20, 20, size=50), np.inf),
+        np.array([ATOL, np.nextafter(ATOL, 0), np.nextafter(ATOL, 1), -ATOL, 1e-9, -1e-9, 0.0, 1 / 16, 0.3, 0.1, 1 / 3,
+                  0.99999995, 0.9999999, 0.5, 0.50000005, 1e300, -1e300, 1e-300, 123456.7, 1234567.8]),
+        rng.standard_normal(100) * 10.0 ** rng.integers(-6, 6, size=100),
+        np.round(rng.random(100), 7),
+    ])
+    base = np.concatenate([base, -base])
+    return rng.choice(base, size=(n, n))
+
+
+@pytest.mark.parametrize("flags", FLAG_SETS)
+@pytest.mark.parametrize("n,seed", [(16, 0), (33, 1), (100, 2)])
+def test_round_refine_chain_matches_oracle(n, seed, flags):
+    """refine!(S, Part(_clamp_round!(M))) repeatedly, with adversarial values."""
+    rng = np.random.default_rng(seed)
+    P = None
+    with B.Context(n, 0, flags) as ctx:
+        for step in range(4):
+            if step % 2 == 0:
+                M = adversarial_values(rng, n)
+            else:
+                M = rng.integers(0, 4, size=(n, n)) * 0.125 + rng.integers(0, 2, size=(n, n)) * 1e-9
+            d = ctx.refine_values(M, ATOL, do_round=True)
+            P = oracle_refine_values(P, M, True)
+            assert d == P.nparts, (step, d, P.nparts)
+            assert np.array_equal(ctx.get_labels(), P.matrix), f"labels differ at step {step}"
+
+
+@pytest.mark.parametrize("atol", [1e-3, 1e-5, 1.4901161193847656e-8, 1e-10, 1e-13])
+def test_round_refine_other_tolerances(atol):
+    """sigdigits = floor(-log10(atol)) other than 7, incl. grids too wide for the fused key."""
+    rng = np.random.default_rng(5)
+    n = 40
+    with B.Context(n, 0, 0) as ctx:
+        P = None
+        for step in range(3):
+            M = np.round(rng.random((n, n)), 3) + rng.integers(0, 3, size=(n, n)) * 1e-6
+            d = ctx.refine_values(M, atol, True)
+            Mr = O.clamp_round(M, atol)
+            P2 = O.partition_from_values(Mr)
+            P = P2 if P is None else O.refine(P, P2)
+            assert d == P.nparts
+            assert np.array_equal(ctx.get_labels(), P.matrix)
+
+
+def test_negative_zero_and_raw_bits():
+    M = np.array([[0.0, -0.0, 1.0], [1.0, 0.0, -0.0], [2.0, 2.0, 0.0]])
+    want = O.partition_from_values(M)
+    with B.Context(3) as ctx:
+        assert ctx.refine_values(M, ATOL, do_round=False) == want.nparts == 3
+        assert np.array_equal(ctx.get_labels(), want.matrix)
+
+
+@pytest.mark.parametrize("n", [3, 10, 31, 64, 100])
+def test_fill_matches_oracle(n):
+    rng = np.random.default_rng(n)
+    M = rng.integers(0, 7, size=(n, n))
+    P = O.partition_from_values(M)
+    r = rng.random(P.nparts)
+    with B.Context(n) as ctx:
+        ctx.set_labels(M)
+        ctx.fill(r)
+        X = ctx.get_matrix(B.MAT_X)
+    assert np.array_equal(X, O.fill(P, r))           # bit-exact gather
+
+
+def test_randomize_roundtrip(vec):
+    """test/runtests.jl:27: part(rndPart(P1)) == P1."""
+    P1 = S.Partition(np.array(vec["P1"]))
+    assert P1.nparts == 3
+    X = S.randomize(P1, Coeffs(3))
+    assert S.Partition(X) == P1
+
+
+def test_fill_length_is_checked():
+    with B.Context(4) as ctx:
+        ctx.set_labels(np.arange(16).reshape(4, 4) % 3)
+        with pytest.raises(B.SdpsrError) as e:
+            ctx.fill(np.ones(5))
+        assert e.value.code == B.E_INVALID
+
+
+def test_uint16_overflow_like_reference():
+    """labels that do not fit the requested width raise."""
+    n = 300
+    M = np.arange(n * n).reshape(n, n) + 1            # 90 000 classes > 65 535
+    with B.Context(n) as ctx:
+        assert ctx.set_labels(M) == n * n
+        with pytest.raises(B.SdpsrError) as e:
+            ctx.get_labels(np.uint16)
+        assert e.value.code == B.E_LABEL_OVERFLOW
+        L = ctx.get_labels(np.uint32)
+        assert np.array_equal(L, O.partition_from_values(M).matrix)
+
+
+# ---------------------------------------------------------------------------------
+# GEMM
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [3, 16, 31, 57, 128, 130, 256, 300, 515])
+def test_gemm_matches_fp64_reference(n):
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n))
+    Bm = rng.standard_normal((n, n))
+    with B.Context(n) as ctx:
+        ctx.set_matrix(B.MAT_X, A)
+        ctx.set_matrix(B.MAT_Q, Bm)
+        ctx.gemm(B.MAT_X, B.MAT_Q, B.MAT_X2)
+        Cm = ctx.get_matrix(B.MAT_X2)
+    ref = A @ Bm
+    scale = np.abs(A) @ np.abs(Bm)
+    assert np.max(np.abs(Cm - ref) / scale) < 1e-14      # fp64 tolerance: a few ulp of the sum of |terms|
+
+
+# ---------------------------------------------------------------------------------
+# admissible_subspace
+# ---------------------------------------------------------------------------------
+def small_problems():
+    return [pr.petersen(), pr.lovasz_er(3), pr.lovasz_er(5), pr.lovasz_er(7),
+            pr.qap_esc16j(os.path.join(GOLDEN, "esc16j.npz")), pr.hamming(2, 8), pr.hamming(3, 4),
+            pr.kneser(8, 3), pr.kneser(10, 4), pr.synthetic_product_scheme(3, 2, 8),
+            pr.synthetic_product_scheme(3, 3, 16)]
+
+
+@pytest.mark.parametrize("prob", small_problems(), ids=lambda p: p.name)
+@pytest.mark.parametrize("flags", [0, B.F_TINY_TABLE | B.F_FORCE_BITMAP_RANK])
+def test_admissible_subspace_labels_identical(prob, flags):
+    """Final partition identical (bit-exact canonical labels) and identical dim
+    trajectory, given the same random coefficients."""
+    co, cg = Coeffs(11), Coeffs(11)
+    Po, tr_o = O.admissible_subspace_trace(*prob, co)
+    tr_g = {}
+    Pg = S.admissible_subspace(*prob, rand=cg, flags=flags, trace=tr_g, keep_context=False)
+    assert tr_g["init"] == tr_o["init"]
+    assert tr_g["iters"] == tr_o["iters"]
+    assert cg.draws == co.draws                        # same rand() call sequence
+    assert Pg.nparts == Po.nparts == prob.expected_dim
+    assert np.array_equal(Pg.matrix, Po.matrix)
+
+
+@pytest.mark.parametrize("prob", [pr.lovasz_er(5), pr.qap_esc16j(os.path.join(GOLDEN, "esc16j.npz"))],
+                         ids=lambda p: p.name)
+def test_host_supplied_init_elements(prob):
+    """The Julia-wrapper route: CL and X0 computed by the host (the reference's own qr/craig)."""
+    CL, X0, _ = O.init_elements(*prob)
+    co, cg = Coeffs(5), Coeffs(5)
+    Po = O.admissible_subspace(*prob, co)
+    Pg = S.admissible_subspace(*prob, rand=cg, init_elements=(CL, X0), keep_context=False)
+    assert np.array_equal(Pg.matrix, Po.matrix)
+
+
+def test_dense_and_sparse_constraints_agree():
+    prob = pr.lovasz_er(5)
+    import scipy.sparse as sp
+    Pd = S.admissible_subspace(prob.C, prob.A, prob.b, rand=Coeffs(1), keep_context=False)
+    Ps = S.admissible_subspace(prob.C, sp.csr_matrix(prob.A), prob.b, rand=Coeffs(1), keep_context=False)
+    assert Pd == Ps
+    with B.Context(prob.n) as ctx:
+        csc = sp.csc_matrix(prob.A)
+        ctx.set_constraints_csc(2, csc.indptr, csc.indices, csc.data, 0)
+        assert ctx.constraint_patterns() == 2
+        assert ctx.init_partition(prob.C, prob.b, ATOL) == 2
+
+
+def test_uint16_default_label_type():
+    prob = pr.lovasz_er(3)
+    P = S.admissible_subspace(*prob, rand=Coeffs(2), label_dtype=np.uint16, keep_context=False)
+    assert P.matrix.dtype == np.uint16 and P.nparts == 12
+
+
+def test_medium_hamming_closed_form():
+    """H(3,8), N = 512: labels must equal Hamming distance + 1."""
+    prob = pr.hamming(3, 8)
+    P = S.admissible_subspace(*prob, rand=Coeffs(3))
+    assert P.nparts == 4
+    assert np.array_equal(P.matrix, pr.hamming_distance_matrix(3, 8).astype(np.uint32) + 1)
+    bd = S.blockDiagonalize(P, False, rand=Coeffs(4))
+    assert bd.blkSizes == [1, 1, 1, 1]
+    K = pr.krawtchouk(3, 8)
+    got = np.array([[bd.blks[i][k][0, 0] for k in range(4)] for i in range(4)])
+    for k in range(4):
+        assert min(np.abs(K - got[:, [k]]).max(axis=0)) < 1e-8 * np.abs(K).max()
+    P.release()
+
+
+# ---------------------------------------------------------------------------------
+# blockDiagonalize
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("prob", small_problems(), ids=lambda p: p.name)
+def test_block_diagonalize_matches_oracle(prob):
+    Po = O.admissible_subspace(*prob, Coeffs(21))
+    Pg = S.Partition(Po.nparts, Po.matrix.astype(np.uint32))
+    so, bo = O.blockDiagonalize(Po, Coeffs(22))
+    bd = S.blockDiagonalize(Pg, False, rand=Coeffs(22))
+    assert list(bd.blkSizes) == list(so)
+    assert sorted(bd.blkSizes) == prob.expected_blocks
+    for i in range(Po.nparts):
+        for k in range(len(so)):
+            ref = bo[i][k]
+            tol = 1e-8 * max(1.0, np.abs(ref).max())
+            assert np.abs(bd.blks[i][k] - ref).max() < tol, (i, k)
+    Pg.release()
+
+
+def test_diagonalize_default_atol_and_qhat(vec):
+    """diagonalize(Float64, P) as called in test/lovasz.jl:7 (atol = 1e-12*N)."""
+    prob = pr.lovasz_er(7)
+    P = S.admissible_subspace(*prob, rand=Coeffs(1))
+    Qhat = S.diagonalize(P, rand=Coeffs(2))
+    assert sorted(q.shape[1] for q in Qhat) == [2, 2, 2, 2, 3]
+    for q in Qhat:                                      # orthonormal columns
+        assert np.allclose(q.T @ q, np.eye(q.shape[1]), atol=1e-10)
+    blks = S.basis_image(Qhat, P)
+    ref = O.basis_image(Qhat, O.Partition(P.nparts, P.matrix.astype(np.int64)))
+    for i in range(P.nparts):
+        for k in range(len(Qhat)):
+            assert np.abs(blks[i][k] - ref[i][k]).max() < 1e-10
+    P.release()
+
+
+def test_real_path_rejects_nonsymmetric(vec):
+    """test/runtests.jl:50-56: cyclic C3 over the reals throws InvalidDecompositionField."""
+    P3 = S.Partition(np.array(vec["C3"]["matrix"]))
+    with pytest.raises(S.InvalidDecompositionField):
+        S.blockDiagonalize(P3, False, rand=Coeffs(1))
+
+
+def test_desymmetrize_identity(vec):
+    """test/runtests.jl:40."""
+    P1 = S.Partition(np.array(vec["P1"]))
+    got = S.unSymmetrize(P1, rand=Coeffs(7))
+    want = vec["unsymmetrize_P1"]
+    assert got.nparts == want["nparts"]
+    assert np.array_equal(got.matrix, np.array(want["matrix"]))
+    assert got == S.Partition(O.desymmetrize(O.partition_from_values(np.array(vec["P1"])), Coeffs(7)).matrix)
+
+
+def test_numerical_issues_fixture():
+    """test/numerical_issues.jl:91-94 (bounded to 100 trials): never inconsistent at atol 1e-7."""
+    Pm = np.load(os.path.join(GOLDEN, "numerical_issues_P.npy"))
+    P = S.Partition(Pm)
+    assert P.nparts == 1312
+    c = Coeffs(99)
+    from sdpsr_b200.api import eigen_decomposition
+    for _ in range(100):
+        vals, ptrs, kroot = eigen_decomposition(P, atol=1e-7, rand=c)
+    assert len(ptrs) - 1 == 64
+    assert sorted(np.bincount(kroot)[np.unique(kroot)]) == [16, 48]
+    P.release()
+
+
+def test_spectrum_invariant_gpu():
+    prob = pr.lovasz_er(7)
+    P = S.admissible_subspace(*prob, rand=Coeffs(8))
+    bd = S.blockDiagonalize(P, False, rand=Coeffs(9))
+    x = np.random.default_rng(0).random(P.nparts)
+    big = np.linalg.eigvalsh(np.concatenate([[0.0], x])[P.matrix])
+    mult = [int(P._ptrs[r + 1] - P._ptrs[r]) for r in dict.fromkeys(P._kroot.tolist())]
+    small = []
+    for k, s in enumerate(bd.blkSizes):
+        Mk = sum(x[i] * bd.blks[i][k] for i in range(P.nparts))
+        small += list(np.linalg.eigvalsh(Mk)) * mult[k]
+    assert np.allclose(sorted(small), big, atol=1e-9)
+    assert sorted(mult) == prob.expected_mult
+    P.release()
