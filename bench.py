@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- the Jordan-reduction hot path on B200 (driver contract in the task prompt).
+
+One "step" = one whole job: admissible_subspace(C, A, b) + blockDiagonalize(P) on the
+Theta' SDP of the Hamming graph H(7,4), N = 16384 (BASELINE.json configs[3]; no binomial
+equals 16384, so the Hamming scheme with exactly N = 16384 is used -- SURVEY.md 8(d) cfg 4).
+
+  value   wall seconds per job with C resident in HBM and results left on the device
+  e2e     the same job through the public API with HOST buffers: context creation, H2D of C
+          from pinned memory, D2H of the label matrix and the blocks
+  roofline       dominant kernel (FP64 DMMA GEMM) vs the FP64 tensor peak measured live with
+                 cuBLAS DGEMM (MEASURED_PEAKS.json has no FP64 entry)
+  roofline_hbm   the refine pass (16 B/entry) vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline   the CPU oracle (a port of the reference; Julia is not installable here) timed
+                 on the host cores on a bounded sample and extrapolated -- reported, not a target
+
+`--impl reference` times only that CPU arm and prints its own line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "admissible_subspace+blockDiagonalize wall s"
+ATOL = 1.4901161193847656e-8
+
+WORKLOADS = {
+    # name: (d, q) of the Hamming graph H(d,q)
+    "theta-H(7,4)-N16384": (7, 4),
+    "theta-H(4,8)-N4096": (4, 8),
+    "theta-H(6,4)-N4096": (6, 4),
+    "theta-H(5,4)-N1024": (5, 4),
+    "theta-H(3,4)-N64": (3, 4),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sdpsr", choices=["sdpsr", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("SDPSR_BENCH_WORKLOAD", "theta-H(7,4)-N16384"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=25.0)
+    return ap.parse_args()
+
+
+class Coeffs:
+    """The random coefficient vectors, drawn once with default_rng(20260101) in the reference's
+    draw order and fed identically to every arm."""
+
+    def __init__(self, seed=20260101):
+        self.rng = np.random.default_rng(seed)
+
+    def __call__(self, n):
+        return self.rng.random(int(n))
+
+
+# ----------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------
+# the job
+# ----------------------------------------------------------------------------------
+def job_resident(S, B, ctx, prob, C_dev, seed=20260101):
+    """Whole job with C already in HBM and the partition left on the device."""
+    rand = Coeffs(seed)
+    tr = {}
+    P = S.admissible_subspace(C_dev, prob.A, prob.b, rand=rand, ctx=ctx, fetch_labels=False, trace=tr)
+    bd = S.blockDiagonalize(P, False, rand=rand)
+    return P.nparts, list(bd.blkSizes), tr
+
+
+def job_e2e(S, B, prob, C_pinned, labels_pinned, seed=20260101):
+    """The public API with host buffers: the call a user makes."""
+    rand = Coeffs(seed)
+    P = S.admissible_subspace(C_pinned, prob.A, prob.b, rand=rand, labels_out=labels_pinned)
+    bd = S.blockDiagonalize(P, False, rand=rand)
+    launches = P._ctx.launch_count()
+    P.release()
+    return P.nparts, list(bd.blkSizes), launches
+
+
+# ----------------------------------------------------------------------------------
+# CPU arm: the oracle (a port of the reference) on the host cores, bounded sample
+# ----------------------------------------------------------------------------------
+def cpu_reference_estimate(workload, budget_s=25.0, iters=None):
+    """Time the CPU restatement of the reference on bounded pieces of THIS workload and
+    extrapolate to the whole job.  Pieces (all at the full N):
+       refine : oracle/partition_ref.c (single thread, like Julia) on a column block
+       gemm   : OpenBLAS dgemm (all threads) on a column block of X*X
+       fill   : numpy gather on a column block
+       eigen  : LAPACK dsyevd at N/4 (O(n^3) -> x64), all threads
+    """
+    import oracle as O
+    from oracle import cref
+    import sdpsr_b200 as S
+    from sdpsr_b200 import problems as pr
+    try:
+        from threadpoolctl import threadpool_info
+        blas_threads = max([d.get("num_threads", 1) for d in threadpool_info()] or [1])
+    except Exception:
+        blas_threads = os.cpu_count() or 1
+    d, q = WORKLOADS[workload]
+    N = q ** d
+    rng = np.random.default_rng(0)
+    D = pr.hamming_distance_matrix(d, q)
+    r = rng.random(d + 1)
+    frac = budget_s / 25.0
+    cb = int(max(16, min(N, (1024 if N >= 8192 else N) * frac)))          # column block
+    t = {}
+    # fill on a column block
+    lab = (D[:, :cb].astype(np.uint64) + 1)
+    t0 = time.perf_counter()
+    Xb = np.concatenate([[0.0], r])[lab]
+    t["fill"] = (time.perf_counter() - t0) * (N / cb)
+    # gemm on a column block (needs the full X once)
+    X = np.concatenate([[0.0], r])[D.astype(np.int64) + 1]
+    gb = int(max(16, min(N, (512 if N >= 8192 else N) * frac)))
+    t0 = time.perf_counter()
+    X2b = X @ X[:, :gb]
+    t["gemm"] = (time.perf_counter() - t0) * (N / gb)
+    # refine on a column block: round + Dict pass + refine!  (src/partitions.jl:173-174)
+    labF = np.asfortranarray(lab[:, :gb])
+    t0 = time.perf_counter()
+    cref.round_refine(labF, d + 1, np.asfortranarray(X2b), ATOL)
+    t["refine"] = (time.perf_counter() - t0) * (N / gb)
+    # eigen at N/4 of a scheme element of the same family, scaled by 4^3
+    ds = max(1, d - (2 if q == 4 else 1)) if N > 1024 else d
+    Ds = pr.hamming_distance_matrix(ds, q)
+    Xs = np.concatenate([[0.0], rng.random(ds + 1)])[Ds.astype(np.int64) + 1]
+    t0 = time.perf_counter()
+    np.linalg.eigh(Xs)
+    t["eig"] = (time.perf_counter() - t0) * (N / Xs.shape[0]) ** 3
+    del X, X2b, Xs
+    # assemble the whole job: per-iteration cost = fill + project(~fill) + 2 refines + gemm
+    n_iter = iters if iters is not None else d // 2 + 1   # Theta' of H(d,q): observed d/2+1 passes (H(4,8): 3, H(7,4): 4)
+    per_iter = 2 * t["fill"] + 2 * t["refine"] + t["gemm"]
+    adm = 2 * t["refine"] + n_iter * per_iter                      # init: Part(CL), refine!(., Part(X0))
+    blk = t["eig"] + 2 * t["gemm"] + 2 * t["fill"] + t["refine"]   # eigen, Q'AQ, fills, basis_image ~ one pass
+    total = adm + blk
+    sample = (f"refine+fill on {gb}/{cb} of {N} columns (C, 1 thread), dgemm N x N x {gb} (OpenBLAS, "
+              f"{blas_threads} threads), dsyevd at n={4 ** ds if q == 4 else q ** ds} scaled by n^3; "
+              f"extrapolated to {n_iter} iterations + blockDiagonalize")
+    return {"value": total, "unit": "s", "cores": blas_threads, "kind": "port", "sample": sample,
+            "phases_s": {k: round(v, 3) for k, v in t.items()}, "iterations": n_iter,
+            "refine_passes_per_s": 1.0 / t["refine"], "fp64_tflops": 2.0 * N ** 3 / t["gemm"] / 1e12}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload not in WORKLOADS:
+        raise SystemExit(f"unknown workload {args.workload}; choose from {list(WORKLOADS)}")
+    d, q = WORKLOADS[args.workload]
+    N = q ** d
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        K, W = max(1, args.steps), max(0, args.warmup)
+        ests = []
+        for i in range(min(W, 1) + K):
+            e = cpu_reference_estimate(args.workload, budget_s=max(5.0, args.cpu_budget_s / max(1, K)))
+            if i >= min(W, 1):
+                ests.append(e)
+        best = min(ests, key=lambda e: e["value"])
+        line = {"impl": "reference", "metric": METRIC, "value": best["value"], "unit": "s", "n_gpus": args.gpus,
+                "steps": K, "warmup": W, "ms_per_step": best["value"] * 1e3, "higher_is_better": False,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "N": N, "m": 2, "timing": "host wall clock, CPU only"},
+                "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": best["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "phases_s": best["phases_s"], "refine_passes_per_s": best["refine_passes_per_s"],
+                "fp64_tflops": best["fp64_tflops"]}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import sdpsr_b200 as S
+    from sdpsr_b200 import binding as B
+    from sdpsr_b200 import problems as pr
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    prob = pr.hamming(d, q, sparse=True)
+    C_pinned_t = torch.ones(N * N, dtype=torch.float64).pin_memory()
+    C_pinned = C_pinned_t.numpy()
+    labels_pinned_t = torch.empty(N * N, dtype=torch.int32).pin_memory()
+    labels_pinned = labels_pinned_t.numpy().view(np.uint32).reshape(N, N, order="F")
+    C_dev = C_pinned_t.cuda(non_blocking=False)
+    torch.cuda.synchronize()
+
+    ctx = B.Context(N, local, B.F_TIMING)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    # ---- FP64 tensor peak, measured live (cuBLAS DGEMM) ---------------------------------
+    def dgemm_peak(n=8192, reps=3):
+        A = torch.randn(n, n, dtype=torch.float64, device="cuda")
+        Cm = torch.empty_like(A)
+        torch.matmul(A, A, out=Cm)
+        best = 1e30
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            torch.matmul(A, A, out=Cm)
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return 2.0 * n ** 3 / best / 1e9
+    fp64_peak = dgemm_peak(min(8192, max(1024, N)))
+
+    # ---- resident arm ---------------------------------------------------------------------
+    for _ in range(args.warmup):
+        dim, sizes, tr = job_resident(S, B, ctx, prob, C_dev)
+    barrier()
+    ctx.timing_reset()
+    l0 = ctx.launch_count()
+    clocks = ClockSampler(local)
+    clocks.start()
+    evs = []
+    barrier()
+    for _ in range(args.steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        dim, sizes, tr = job_resident(S, B, ctx, prob, C_dev)
+        b.record(stream)
+        evs.append((a, b))
+    barrier()
+    ms_res = sum(a.elapsed_time(b) for a, b in evs)
+    launches = ctx.launch_count() - l0
+    tim = ctx.timing()
+
+    # ---- e2e arm: public API, host buffers ------------------------------------------------
+    for _ in range(min(args.warmup, 1)):
+        job_e2e(S, B, prob, C_pinned, labels_pinned)
+    barrier()
+    evs = []
+    for _ in range(args.steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        dim_e, sizes_e, l_e2e = job_e2e(S, B, prob, C_pinned, labels_pinned)
+        b.record(stream)
+        evs.append((a, b))
+    barrier()
+    ms_e2e = sum(a.elapsed_time(b) for a, b in evs)
+    clk = clocks.stop()
+    assert dim_e == dim and sizes_e == sizes
+    assert dim == prob.expected_dim and sorted(sizes) == prob.expected_blocks, (dim, sizes)
+
+    t = torch.tensor([ms_res, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_res, ms_e2e = (float(x) for x in t.tolist())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    K = args.steps
+    sec_res, sec_e2e = ms_res / K / 1e3, ms_e2e / K / 1e3
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    g, rf = tim["gemm"], tim["refine"]
+    gemm_tf = g["work"] / g["ms"] / 1e9 if g["ms"] else None
+    ref_gbs = rf["work"] / rf["ms"] / 1e6 if rf["ms"] else None
+    h2d = N * N * 8 + int(prob.A.data.nbytes + prob.A.indices.astype(np.int64).nbytes + prob.A.indptr.nbytes)
+    d2h = N * N * 4 + N * 8 + dim * len(sizes) * 8
+    line = {
+        "metric": METRIC, "value": sec_res, "unit": "s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": ms_res / K, "higher_is_better": False,
+        "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "N": N, "m": 2, "dim": dim, "blocks": sizes,
+                   "iterations": tr.get("iterations"), "atol": ATOL,
+                   "l2": "inputs larger than L2 (X is %.1f GB)" % (N * N * 8 / 1e9),
+                   "parallelism": "replicas" if world > 1 else "single GPU"},
+        "e2e": {"value": sec_e2e, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": {"bound": "tensor", "kernel": "gemm_f64_kernel (DMMA.8x8x4)", "achieved": gemm_tf,
+                     "peak": fp64_peak / 1e3, "unit": "TFLOP/s", "frac": (gemm_tf / (fp64_peak / 1e3)) if gemm_tf else None,
+                     "traffic": traffic.get("gemm_f64_kernel"),
+                     "peak_source": "cuBLAS DGEMM measured live in this run (MEASURED_PEAKS.json has no FP64 "
+                                    "entry); nominal FP64 tensor 40 TFLOP/s",
+                     "launches": g["launches"], "ms_per_launch": g["ms"] / max(1, g["launches"])},
+        "roofline_hbm": {"bound": "hbm", "kernel": "refine_kernel", "achieved": ref_gbs, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": (ref_gbs / hbm_peak) if ref_gbs else None,
+                         "traffic": traffic.get("refine_kernel"), "peak_source": hbm_src,
+                         "launches": rf["launches"], "ms_per_launch": rf["ms"] / max(1, rf["launches"])},
+        "refine_passes_per_s": (1e3 * rf["launches"] / rf["ms"]) if rf["ms"] else None,
+        "fp64_tflops": gemm_tf,
+        "kernel_ms_per_step": {k: v["ms"] / K for k, v in tim.items() if v["launches"]},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            cb = cpu_reference_estimate(args.workload, budget_s=args.cpu_budget_s, iters=tr.get("iterations"))
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["phases_s"] = cb["phases_s"]
+        except Exception as e:  # the baseline is reported, never required
+            line["cpu_baseline"] = {"value": None, "unit": "s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

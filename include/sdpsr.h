@@ -191,6 +191,10 @@ int sdpsr_gemm(sdpsr_ctx* ctx, int a, int b, int c);
 int sdpsr_timing_reset(sdpsr_ctx* ctx);
 int sdpsr_timing_get(sdpsr_ctx* ctx, int family, double* total_ms, int64_t* launches,
                      double* work);
+/* Run all further work of this context on the caller's CUDA stream (a cudaStream_t passed as
+ * void*; NULL = the legacy default stream).  Calls stay blocking.  Lets a host framework order
+ * and time the engine's kernels with its own events.                                          */
+int sdpsr_set_stream(sdpsr_ctx* ctx, void* cuda_stream);
 /* total number of kernels launched by this context since creation */
 int sdpsr_launch_count(sdpsr_ctx* ctx, int64_t* launches);
 

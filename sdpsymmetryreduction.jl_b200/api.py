@@ -67,7 +67,7 @@ class Partition:
         self.device = device
         if len(args) == 2:
             self.nparts = int(args[0])
-            self.matrix = np.asarray(args[1])
+            self.matrix = None if args[1] is None else np.asarray(args[1])   # None: device-resident only
         elif len(args) == 1:
             M = np.asarray(args[0])
             n = M.shape[0]
@@ -142,7 +142,8 @@ def admissible_subspace(C, A, b, *, verbose: bool = False, atol: float = RTOL_DE
                         rand: Optional[Callable] = None, snap_decimals: Optional[int] = 12,
                         device: int = 0, flags: int = 0, label_dtype=np.uint32,
                         init_elements=None, trace: Optional[dict] = None,
-                        keep_context: bool = True, ctx: Optional[B.Context] = None) -> Partition:
+                        keep_context: bool = True, ctx: Optional[B.Context] = None,
+                        labels_out=None, fetch_labels: bool = True) -> Partition:
     """Optimal admissible partition subspace of  min <C,x>, A x = b, Mat(x) psd
     (src/partitions.jl:77-190).
 
@@ -156,7 +157,7 @@ def admissible_subspace(C, A, b, *, verbose: bool = False, atol: float = RTOL_DE
     Cv = C
     if hasattr(C, "todense"):
         Cv = np.asarray(C.todense()).reshape(-1)
-    nn = int(np.prod(Cv.shape))
+    nn = int(Cv.numel()) if hasattr(Cv, "numel") else int(np.prod(np.shape(Cv)))
     n = math.isqrt(nn)
     if n * n != nn:
         raise AssertionError("n^2 == length(C)")                    # :118
@@ -199,7 +200,10 @@ def admissible_subspace(C, A, b, *, verbose: bool = False, atol: float = RTOL_DE
         trace["iterations"] = it
         trace["t_total"] = time.perf_counter() - t0
     try:
-        labels = ctx.get_labels(label_dtype)
+        if not fetch_labels:          # caller keeps the partition on the device
+            labels = None
+        else:
+            labels = ctx.get_labels(label_dtype, out=labels_out)
     except B.SdpsrError as e:
         if e.code == B.E_LABEL_OVERFLOW:
             raise OverflowError("InexactError: label does not fit " + str(np.dtype(label_dtype))) from e
@@ -351,10 +355,10 @@ def diagonalize(P: Partition, *, verbose: bool = False, atol: Optional[float] = 
         raise NotImplementedError(
             "complex path (SURVEY.md 8(f) rank 1) is not built yet; desymmetrize() is available")
     rand = rand or _default_rand()
-    n = P.matrix.shape[0]
+    ctx = ctx or P._context()
+    n = ctx.n
     if atol is None:
         atol = 1e-12 * n
-    ctx = ctx or P._context()
     t = time.perf_counter()
     vals, ptrs, kroot = eigen_decomposition(P, atol=atol, rand=rand, ctx=ctx)
     if verbose:
@@ -399,8 +403,8 @@ def blockDiagonalize(P: Partition, verbose: bool = True, *, epsilon: float = RTO
         raise NotImplementedError(
             "complex path (SURVEY.md 8(f) rank 1) is not built yet; desymmetrize() is available")
     rand = rand or _default_rand()
-    n = P.matrix.shape[0]
     ctx = P._context()
+    n = ctx.n
     sizes = diagonalize(P, verbose=verbose, atol=epsilon, rand=rand, fetch=False, ctx=ctx)
     check_block_sizes(sizes, P, False)
     t = time.perf_counter()

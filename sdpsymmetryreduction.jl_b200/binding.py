@@ -79,6 +79,7 @@ _SIGNATURES = {
     "sdpsr_timing_reset": ([_p], C.c_int),
     "sdpsr_timing_get": ([_p, C.c_int, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(C.c_double)], C.c_int),
     "sdpsr_launch_count": ([_p, C.POINTER(_i64)], C.c_int),
+    "sdpsr_set_stream": ([_p, _p], C.c_int),
     "sdpsr_comm_unique_id": ([_p], C.c_int),
     "sdpsr_comm_init": ([_p, C.c_int, C.c_int, _p], C.c_int),
     "sdpsr_comm_info": ([_p, C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
@@ -372,6 +373,10 @@ class Context:
             self._check(self.lib.sdpsr_timing_get(self._h, fam, C.byref(ms), C.byref(n), C.byref(w)))
             out[name] = {"ms": ms.value, "launches": n.value, "work": w.value}
         return out
+
+    def set_stream(self, cuda_stream: int):
+        """Run on the caller's stream (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
+        self._check(self.lib.sdpsr_set_stream(self._h, _p(cuda_stream)))
 
     def launch_count(self) -> int:
         v = _i64(0)

@@ -259,6 +259,10 @@ void sdpsr_blockdiag_free(sdpsr_ctx* ctx) {
   ctx->Q = ctx->W = ctx->T = ctx->Qhat = nullptr;
 }
 
+void sdpsr_blockdiag_rebind(sdpsr_ctx* ctx) {
+  if (ctx->solver) cusolverDnSetStream(reinterpret_cast<Solver*>(ctx->solver)->h, ctx->stream);
+}
+
 #define CTX_ENTER()                 \
   if (!ctx) return SDPSR_E_INVALID; \
   if (cudaSetDevice(ctx->device) != cudaSuccess) return ctx->fail(SDPSR_E_CUDA, "cudaSetDevice failed")

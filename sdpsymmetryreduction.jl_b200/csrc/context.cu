@@ -188,7 +188,7 @@ extern "C" int sdpsr_destroy(sdpsr_ctx* ctx) {
   cudaFree(ctx->bm_block);
   cudaFree(ctx->d_scalars);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return SDPSR_OK;
 }
@@ -474,6 +474,19 @@ extern "C" int sdpsr_timing_get(sdpsr_ctx* ctx, int family, double* total_ms, in
   if (total_ms) *total_ms = ctx->t_ms[family];
   if (launches) *launches = ctx->t_launch[family];
   if (work) *work = ctx->t_work[family];
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_set_stream(sdpsr_ctx* ctx, void* cuda_stream) {
+  CTX_ENTER();
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  drain_events(ctx);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->own_stream = false;
+  ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  if (ctx->solver) {           // cuSOLVER handle is bound lazily; rebind on next sdpsr_eig
+    sdpsr_blockdiag_rebind(ctx);
+  }
   return SDPSR_OK;
 }
 

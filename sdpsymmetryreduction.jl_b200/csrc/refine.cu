@@ -30,7 +30,7 @@ constexpr int RT = 256;           // threads per CTA
 constexpr int EPT = 4;            // consecutive entries per thread per tile
 constexpr int TILE = RT * EPT;    // entries per tile
 constexpr int SC = 4096;          // slots of the per-CTA key cache
-constexpr int SC_LIMIT = SC * 5 / 8;
+constexpr int SC_LIMIT = SC * 3 / 4;
 constexpr uint32_t PROBE_LIMIT = 4096;
 constexpr int RANK_BRUTE_MAX = 16384;
 
@@ -84,6 +84,7 @@ __device__ __forceinline__ uint32_t ld_vol32(const uint32_t* p) {
 // non-canonical representation (|q| == scale, i.e. y == 1.0) is folded onto
 // (scale/2, n+1), which denotes the same double.  `rounded` receives the value the
 // reference would store.
+template <bool NEED_VALUE>
 __device__ __forceinline__ uint64_t round_code(double a, double atol, double scale, long long iscale,
                                                int qbits, double& rounded) {
   if (fabs(a) < atol) {
@@ -96,7 +97,14 @@ __device__ __forceinline__ uint64_t round_code(double a, double atol, double sca
   const double x = __longlong_as_double((long long)((bits & 0x800fffffffffffffull) | (0x3feull << 52)));
   const double p = __dmul_rn(scale, x);            // one IEEE multiply, no FMA contraction
   const long long q = __double2ll_rz(p);           // unsafe_trunc(Int, .)
-  rounded = ldexp(__ddiv_rn((double)q, scale), (int)e - 1022);
+  if (NEED_VALUE) {
+    // ldexp(q/scale, n) with n = e - 1022: y in [0.5, 1] and e is a normal exponent, so scaling
+    // by 2^n is an exact exponent adjustment (done in two exact steps to stay in range)
+    const double y = __ddiv_rn((double)q, scale);
+    const int n = (int)e - 1022;
+    const int n1 = n / 2, n2 = n - n1;
+    rounded = y * __longlong_as_double((long long)(1023 + n1) << 52) * __longlong_as_double((long long)(1023 + n2) << 52);
+  }
   unsigned long long aq = (unsigned long long)(q < 0 ? -q : q);
   if (aq == (unsigned long long)iscale) {          // y == 1.0: same double as (scale/2, n+1)
     aq = (unsigned long long)(iscale >> 1);
@@ -135,153 +143,161 @@ __device__ __forceinline__ uint32_t global_insert(const RefineArgs& a, uint64_t 
   return 1u;
 }
 
+// One cache slot: {key, provisional id, tile of insertion}; 16 bytes, read with one LDS.128.
+struct __align__(16) CacheSlot {
+  uint64_t key;
+  uint32_t gid;     // 0 while the inserting thread has not published yet
+  uint32_t tile;    // CTA tile during which the key entered this cache
+};
+
+struct Entry4 {
+  uint4 lab;
+  uint4 aux;        // KM_PAIR: second ids; fill-projection: pattern ids
+  double v[EPT];
+};
+
 template <int MODE>
+__device__ __forceinline__ void load_entries(const RefineArgs& a, uint64_t base, Entry4& e) {
+  e.lab = make_uint4(0u, 0u, 0u, 0u);
+  if (a.lab_in) e.lab = __ldcs(reinterpret_cast<const uint4*>(a.lab_in + base));
+  if (MODE == KM_PAIR) {
+    e.aux = __ldcs(reinterpret_cast<const uint4*>(a.lab2 + base));
+  } else if (a.fillproj) {
+    e.aux = __ldcs(reinterpret_cast<const uint4*>(a.pid + base));
+  } else {
+    const double2 v0 = __ldcs(reinterpret_cast<const double2*>(a.vals + base));
+    const double2 v1 = __ldcs(reinterpret_cast<const double2*>(a.vals + base + 2));
+    e.v[0] = v0.x; e.v[1] = v0.y; e.v[2] = v1.x; e.v[3] = v1.y;
+  }
+}
+
+// Keep the first occurrence: the table entry only ever decreases, so a stale (larger) read
+// merely costs one redundant atomic.
+__device__ __forceinline__ void note_first(const RefineArgs& a, uint32_t g, uint32_t idx) {
+  if (idx < ld_vol32(a.gmin + (g - 1))) atomicMin(a.gmin + (g - 1), idx);
+}
+
+// The pass is barrier-free.  A thread resolves a key in the CTA cache with one 16-byte shared
+// load; on a miss it goes to the global table itself and then publishes (key, id, tile) to the
+// cache.  First-occurrence bookkeeping: a CTA walks its tiles in increasing index order, so a
+// hit on a slot inserted during an EARLIER tile has a larger index than the inserter's and
+// needs no update; a hit from the same or an earlier tile (warps of a CTA may be a tile
+// apart) updates the global minimum itself.
+template <int MODE, bool WRITEBACK>
 __global__ void __launch_bounds__(RT) refine_kernel(const RefineArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw);
-  uint32_t* sgid = reinterpret_cast<uint32_t*>(skeys + SC);
-  uint32_t* smin = sgid + SC;
+  CacheSlot* cache = reinterpret_cast<CacheSlot*>(smem_raw);
   __shared__ uint32_t s_count;
 
   for (int i = threadIdx.x; i < SC; i += RT) {
-    skeys[i] = KEY_EMPTY;
-    sgid[i] = 0u;
-    smin[i] = 0xffffffffu;
+    cache[i].key = KEY_EMPTY;
+    cache[i].gid = 0u;
+    cache[i].tile = 0xffffffffu;
   }
   if (threadIdx.x == 0) s_count = 0u;
   __syncthreads();
 
   const uint64_t ntiles = (a.total + TILE - 1) / TILE;
+  uint64_t tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  Entry4 cur, nxt;
+  uint64_t base = tile * TILE + (uint64_t)threadIdx.x * EPT;
+  if (base < a.total) load_entries<MODE>(a, base, cur);
   uint32_t iter = 0;
-  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
-    if ((iter & 7u) == 7u) {                          // bounded work after a table overflow
-      if (__syncthreads_or((int)ld_vol32(a.gmeta + 1))) return;
-    }
-    const uint64_t base = tile * TILE + (uint64_t)threadIdx.x * EPT;
-    const bool active = base < a.total;               // total % EPT == 0: whole vector or nothing
 
-    uint64_t key[EPT];
-    uint32_t gid[EPT];
-    int pslot[EPT];
-    unsigned owner = 0u, pending = 0u;
+  for (; tile < ntiles; tile += gridDim.x, ++iter) {
+    base = tile * TILE + (uint64_t)threadIdx.x * EPT;
+    const bool active = base < a.total;               // total % EPT == 0: whole vector or nothing
+    // prefetch the next tile's operands before touching this one (memory-level parallelism)
+    const uint64_t nbase = (tile + gridDim.x) * TILE + (uint64_t)threadIdx.x * EPT;
+    if (tile + gridDim.x < ntiles && nbase < a.total) load_entries<MODE>(a, nbase, nxt);
+    if ((iter & 15u) == 15u && ld_vol32(a.gmeta + 1)) return;   // table overflowed: host reruns
 
     if (active) {
-      uint4 l = make_uint4(0u, 0u, 0u, 0u);
-      if (a.lab_in) l = __ldcs(reinterpret_cast<const uint4*>(a.lab_in + base));
-      const uint32_t lv[EPT] = {l.x, l.y, l.z, l.w};
+      const uint32_t lv[EPT] = {cur.lab.x, cur.lab.y, cur.lab.z, cur.lab.w};
+      const uint32_t av[EPT] = {cur.aux.x, cur.aux.y, cur.aux.z, cur.aux.w};
+      uint64_t key[EPT];
       if (MODE == KM_PAIR) {
-        const uint4 m = __ldcs(reinterpret_cast<const uint4*>(a.lab2 + base));
-        const uint32_t mv[EPT] = {m.x, m.y, m.z, m.w};
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) key[e] = ((uint64_t)mv[e] << a.lbits) | lv[e];
+        for (int e = 0; e < EPT; ++e) key[e] = ((uint64_t)av[e] << a.lbits) | lv[e];
       } else {
-        double v[EPT];
-        if (a.fillproj) {
-          const uint4 p = __ldcs(reinterpret_cast<const uint4*>(a.pid + base));
-          const uint32_t pv[EPT] = {p.x, p.y, p.z, p.w};
-#pragma unroll
-          for (int e = 0; e < EPT; ++e) v[e] = __dsub_rn(__ldg(a.lut + lv[e]), __ldg(a.tpat + pv[e]));
-        } else {
-          const double2 v0 = __ldcs(reinterpret_cast<const double2*>(a.vals + base));
-          const double2 v1 = __ldcs(reinterpret_cast<const double2*>(a.vals + base + 2));
-          v[0] = v0.x; v[1] = v0.y; v[2] = v1.x; v[3] = v1.y;
-        }
         double r[EPT];
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
+          const double v = a.fillproj ? __dsub_rn(__ldg(a.lut + lv[e]), __ldg(a.tpat + av[e])) : cur.v[e];
           uint64_t code;
           if (a.do_round) {
-            code = round_code(v[e], a.atol, a.scale, a.iscale, a.qbits, r[e]);
+            code = round_code<WRITEBACK || MODE == KM_RAW>(v, a.atol, a.scale, a.iscale, a.qbits, r[e]);
             if (MODE == KM_RAW) code = raw_code(r[e]);
           } else {
-            r[e] = v[e];
-            code = a.raw_bits ? (uint64_t)__double_as_longlong(v[e]) : raw_code(v[e]);
+            r[e] = v;
+            code = a.raw_bits ? (uint64_t)__double_as_longlong(v) : raw_code(v);
           }
           key[e] = (MODE == KM_RAW) ? code : ((code << a.lbits) | lv[e]);
         }
-        if (a.vals_out) {
+        if (WRITEBACK) {
           __stcs(reinterpret_cast<double2*>(a.vals_out + base), make_double2(r[0], r[1]));
           __stcs(reinterpret_cast<double2*>(a.vals_out + base + 2), make_double2(r[2], r[3]));
         }
       }
 
-      // ---- phase A: resolve keys against the CTA cache ------------------------
+      uint32_t gid[EPT];
+      const uint32_t mytile = (uint32_t)iter;
 #pragma unroll
       for (int e = 0; e < EPT; ++e) {
         const uint64_t k = key[e];
         const uint32_t idx = (uint32_t)(base + e);
-        pslot[e] = -1;
         gid[e] = 0u;
         if (k == 0ull) continue;                        // the zero class keeps id 0
-        if (e > 0 && k == key[e - 1]) {                 // run of equal keys inside the thread
+        if (e > 0 && k == key[e - 1]) {                 // run of equal keys: first one did the work
           gid[e] = gid[e - 1];
-          pslot[e] = pslot[e - 1];
-          if (pslot[e] >= 0) pending |= 1u << e;
           continue;
         }
-        const uint64_t h = mix64(k);
-        if (!a.use_cache) {
-          const uint32_t g = global_insert(a, k, h);
-          atomicMin(a.gmin + (g - 1), idx);
-          gid[e] = g;
-          continue;
-        }
-        uint32_t s = (uint32_t)h & (SC - 1);
-        for (int probe = 0; probe < SC; ++probe) {
-          const uint64_t kk = *reinterpret_cast<volatile uint64_t*>(skeys + s);
-          if (kk == k) {
-            const uint32_t g = *reinterpret_cast<volatile uint32_t*>(sgid + s);
-            if (g != 0u) {
-              gid[e] = g;                               // steady state: one smem hit
-            } else {                                    // inserted during this tile by another thread
-              atomicMin(smin + s, idx);
-              pslot[e] = (int)s;
-              pending |= 1u << e;
-            }
-            break;
-          }
-          if (kk == KEY_EMPTY) {
-            if (*reinterpret_cast<volatile uint32_t*>(&s_count) >= (uint32_t)SC_LIMIT) {
-              const uint32_t g = global_insert(a, k, h);   // cache full: go to the global table
-              atomicMin(a.gmin + (g - 1), idx);
-              gid[e] = g;
-              break;
-            }
-            const unsigned long long old =
-                atomicCAS(reinterpret_cast<unsigned long long*>(skeys + s), KEY_EMPTY, (unsigned long long)k);
-            if (old == KEY_EMPTY || old == (unsigned long long)k) {
-              if (old == KEY_EMPTY) {
-                atomicAdd(&s_count, 1u);
-                owner |= 1u << e;
+        const uint64_t hf = k * 0x9e3779b97f4a7c15ull;  // Fibonacci hash for the cache
+        uint32_t s = (uint32_t)(hf >> 40) & (SC - 1);
+        uint32_t g = 0u;
+        int free_slot = -1;
+        if (a.use_cache) {
+#pragma unroll 1
+          for (int probe = 0; probe < 32; ++probe) {
+            uint4 raw;   // one LDS.128 (volatile: other warps publish concurrently)
+            asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w)
+                         : "r"((uint32_t)__cvta_generic_to_shared(&cache[s])));
+            const uint64_t kk = ((uint64_t)raw.y << 32) | raw.x;
+            if (kk == k) {
+              if (raw.z != 0u) {
+                g = raw.z;
+                if (mytile <= raw.w) note_first(a, g, idx);
               }
-              atomicMin(smin + s, idx);
-              pslot[e] = (int)s;
-              pending |= 1u << e;
+              break;                                    // gid still 0: publisher in flight -> miss path
+            }
+            if (kk == KEY_EMPTY) {
+              free_slot = (int)s;
               break;
             }
+            s = (s + 1) & (SC - 1);
           }
-          s = (s + 1) & (SC - 1);
         }
-      }
-    }
-
-    // ---- phases B/C only when this tile met keys new to the CTA ---------------
-    if (__syncthreads_or((int)pending)) {
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        if (owner & (1u << e)) {
-          const uint32_t s = (uint32_t)pslot[e];
-          const uint32_t g = global_insert(a, key[e], mix64(key[e]));
-          atomicMin(a.gmin + (g - 1), smin[s]);
-          *reinterpret_cast<volatile uint32_t*>(sgid + s) = g;
+        if (g == 0u) {
+          g = global_insert(a, k, mix64(k));
+          note_first(a, g, idx);
+          if (free_slot >= 0 && *reinterpret_cast<volatile uint32_t*>(&s_count) < (uint32_t)SC_LIMIT) {
+            const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&cache[free_slot].key),
+                                                     KEY_EMPTY, (unsigned long long)k);
+            if (old == KEY_EMPTY) {
+              // publish id and tile with one 8-byte store: readers see both or neither
+              *reinterpret_cast<volatile unsigned long long*>(&cache[free_slot].gid) =
+                  ((unsigned long long)mytile << 32) | g;
+              atomicAdd(&s_count, 1u);
+            }
+          }
         }
+        gid[e] = g;
       }
-      __syncthreads();
-#pragma unroll
-      for (int e = 0; e < EPT; ++e)
-        if (pending & (1u << e)) gid[e] = *reinterpret_cast<volatile uint32_t*>(sgid + pslot[e]);
+      __stcs(reinterpret_cast<uint4*>(a.lab_out + base), make_uint4(gid[0], gid[1], gid[2], gid[3]));
     }
-    if (active) __stcs(reinterpret_cast<uint4*>(a.lab_out + base), make_uint4(gid[0], gid[1], gid[2], gid[3]));
+    cur = nxt;
   }
 }
 
@@ -526,11 +542,13 @@ int sdpsr_rank_table(sdpsr_ctx* ctx, KeyTable& t) {
 
 int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
   static bool attr_set = false;
-  const size_t smem = (size_t)SC * (8 + 4 + 4);
+  const size_t smem = (size_t)SC * 16;
   if (!attr_set) {
-    SDPSR_CUDA(cudaFuncSetAttribute(refine_kernel<KM_ROUND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SDPSR_CUDA(cudaFuncSetAttribute(refine_kernel<KM_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SDPSR_CUDA(cudaFuncSetAttribute(refine_kernel<KM_PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDPSR_CUDA(cudaFuncSetAttribute(refine_kernel<KM_ROUND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDPSR_CUDA(cudaFuncSetAttribute(refine_kernel<KM_ROUND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDPSR_CUDA(cudaFuncSetAttribute(refine_kernel<KM_RAW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDPSR_CUDA(cudaFuncSetAttribute(refine_kernel<KM_RAW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDPSR_CUDA(cudaFuncSetAttribute(refine_kernel<KM_PAIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   KeyTable& told = ctx->tab[ctx->cur];
@@ -577,10 +595,17 @@ int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
     a.glimit = tnew.cap / 2;
     {
       Timed tm(ctx, SDPSR_K_REFINE, (double)ctx->elems * 16.0);
+      const bool wb = a.vals_out != nullptr;
       switch (spec.mode) {
-        case KM_ROUND: refine_kernel<KM_ROUND><<<grid, RT, smem, ctx->stream>>>(a); break;
-        case KM_RAW: refine_kernel<KM_RAW><<<grid, RT, smem, ctx->stream>>>(a); break;
-        case KM_PAIR: refine_kernel<KM_PAIR><<<grid, RT, smem, ctx->stream>>>(a); break;
+        case KM_ROUND:
+          if (wb) refine_kernel<KM_ROUND, true><<<grid, RT, smem, ctx->stream>>>(a);
+          else refine_kernel<KM_ROUND, false><<<grid, RT, smem, ctx->stream>>>(a);
+          break;
+        case KM_RAW:
+          if (wb) refine_kernel<KM_RAW, true><<<grid, RT, smem, ctx->stream>>>(a);
+          else refine_kernel<KM_RAW, false><<<grid, RT, smem, ctx->stream>>>(a);
+          break;
+        case KM_PAIR: refine_kernel<KM_PAIR, false><<<grid, RT, smem, ctx->stream>>>(a); break;
       }
       count_launch(ctx);
     }

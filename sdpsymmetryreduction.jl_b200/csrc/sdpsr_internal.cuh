@@ -92,6 +92,7 @@ struct sdpsr_ctx {
   size_t elems = 0;     // ld * n
   uint32_t flags = 0;
   cudaStream_t stream = nullptr;
+  bool own_stream = true;
   int sm_count = 148;
 
   // Partition S: provisional ids, double buffered; tab[cur] maps them to canonical labels
@@ -232,6 +233,7 @@ int sdpsr_symmetric_check(sdpsr_ctx* ctx, int* is_sym);
 
 // blockdiag.cu
 void sdpsr_blockdiag_free(sdpsr_ctx* ctx);
+void sdpsr_blockdiag_rebind(sdpsr_ctx* ctx);
 
 // comm.cu
 void sdpsr_comm_free(sdpsr_ctx* ctx);
