@@ -189,7 +189,7 @@ def cpu_reference_estimate(workload, budget_s=25.0, iters=None):
     cref.round_refine(labF, d + 1, np.asfortranarray(X2b), ATOL)
     t["refine"] = (time.perf_counter() - t0) * (N / gb)
     # eigen at N/4 of a scheme element of the same family, scaled by 4^3
-    ds = max(1, d - (2 if q == 4 else 1)) if N > 1024 else d
+    ds = d - 1 if N > 1024 else d          # same family, N/q vertices
     Ds = pr.hamming_distance_matrix(ds, q)
     Xs = np.concatenate([[0.0], rng.random(ds + 1)])[Ds.astype(np.int64) + 1]
     t0 = time.perf_counter()
@@ -203,7 +203,7 @@ def cpu_reference_estimate(workload, budget_s=25.0, iters=None):
     blk = t["eig"] + 2 * t["gemm"] + 2 * t["fill"] + t["refine"]   # eigen, Q'AQ, fills, basis_image ~ one pass
     total = adm + blk
     sample = (f"refine+fill on {gb}/{cb} of {N} columns (C, 1 thread), dgemm N x N x {gb} (OpenBLAS, "
-              f"{blas_threads} threads), dsyevd at n={4 ** ds if q == 4 else q ** ds} scaled by n^3; "
+              f"{blas_threads} threads), dsyevd at n={q ** ds} scaled by n^3; "
               f"extrapolated to {n_iter} iterations + blockDiagonalize")
     return {"value": total, "unit": "s", "cores": blas_threads, "kind": "port", "sample": sample,
             "phases_s": {k: round(v, 3) for k, v in t.items()}, "iterations": n_iter,
@@ -281,7 +281,7 @@ def main():
             b.record()
             torch.cuda.synchronize()
             best = min(best, a.elapsed_time(b))
-        return 2.0 * n ** 3 / best / 1e9
+        return 2.0 * n ** 3 / best / 1e9          # TFLOP/s
     fp64_peak = dgemm_peak(min(8192, max(1024, N)))
 
     # ---- resident arm ---------------------------------------------------------------------
@@ -362,7 +362,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"bound": "tensor", "kernel": "gemm_f64_kernel (DMMA.8x8x4)", "achieved": gemm_tf,
-                     "peak": fp64_peak / 1e3, "unit": "TFLOP/s", "frac": (gemm_tf / (fp64_peak / 1e3)) if gemm_tf else None,
+                     "peak": fp64_peak, "unit": "TFLOP/s", "frac": (gemm_tf / fp64_peak) if gemm_tf else None,
                      "traffic": traffic.get("gemm_f64_kernel"),
                      "peak_source": "cuBLAS DGEMM measured live in this run (MEASURED_PEAKS.json has no FP64 "
                                     "entry); nominal FP64 tensor 40 TFLOP/s",

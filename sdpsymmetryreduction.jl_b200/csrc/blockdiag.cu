@@ -363,7 +363,8 @@ extern "C" int sdpsr_block_norms(sdpsr_ctx* ctx, const double* r2, int64_t len, 
   if (ld != n) SDPSR_CUDA(cudaMemsetAsync(ctx->X2, 0, ctx->elems * 8, ctx->stream));
   transpose_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(ctx->Q, ctx->X2, n, ld);
   count_launch(ctx);
-  SDPSR_TRY(sdpsr_gemm_f64(ctx, ctx->X2, ld, ctx->T, ld, ctx->W, ld, ld, n, n, false));
+  // W = Q' (A2 Q) is symmetric (A2 is: sdpsr_eig checked the partition): lower tiles + mirror
+  SDPSR_TRY(sdpsr_gemm_f64(ctx, ctx->X2, ld, ctx->T, ld, ctx->W, ld, ld, n, n, !(ctx->flags & SDPSR_F_NO_SYRK)));
   // block maxima
   uint32_t *d_space = nullptr, *d_sdim = nullptr;
   unsigned long long* d_norms = nullptr;

@@ -428,8 +428,12 @@ extern "C" int sdpsr_square_round_refine(sdpsr_ctx* ctx, double atol, int64_t* d
     SDPSR_TRY(sdpsr_materialize_fill(ctx, ctx->X));
     // S is unchanged, so X stays a valid fill; keep the flag for a later projection
   }
+  // X symmetric (bit for bit) => X*X symmetric: compute the lower tiles only and mirror them,
+  // which also makes X2 exactly symmetric (SYRK-style, half the flops)
+  int sym = 0;
+  if (!(ctx->flags & SDPSR_F_NO_SYRK)) SDPSR_TRY(sdpsr_matrix_symmetric(ctx, ctx->X, &sym));
   SDPSR_TRY(sdpsr_gemm_f64(ctx, ctx->X, ctx->ld, ctx->X, ctx->ld, ctx->X2, ctx->ld, ctx->ld, ctx->n, ctx->n,
-                           false));
+                           sym != 0));
   SDPSR_TRY(sdpsr_generic_refine_values(ctx, ctx->X2, atol, true, nullptr, dim));
   return finish(ctx);
 }

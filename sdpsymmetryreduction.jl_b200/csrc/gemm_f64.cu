@@ -288,7 +288,8 @@ int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B
   const bool lower = symmetric_out && M >= Nc && tiles_m == tiles_n;
   const int64_t ntiles = lower ? (int64_t)tiles_m * (tiles_m + 1) / 2 : (int64_t)tiles_m * tiles_n;
   {
-    Timed tm(ctx, SDPSR_K_GEMM, (lower ? 1.0 : 2.0) * (double)M * (double)Nc * (double)K);
+    // work = flops issued: the lower-triangle launch covers ntiles full 128x128 tiles
+    Timed tm(ctx, SDPSR_K_GEMM, lower ? 2.0 * (double)ntiles * BM * BN * (double)K : 2.0 * (double)M * (double)Nc * (double)K);
     gemm_f64_kernel<<<(unsigned)ntiles, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, C, ldc, (int)M, (int)Nc, (int)K,
                                                                            tiles_m, tiles_n, lower ? 1 : 0);
     count_launch(ctx);

@@ -155,7 +155,44 @@ __global__ void __launch_bounds__(256) symcheck_kernel(const uint32_t* __restric
   }
 }
 
+__global__ void __launch_bounds__(256) symcheck_f64_kernel(const double* __restrict__ x, int64_t n, int64_t ld,
+                                                           uint32_t* __restrict__ bad) {
+  __shared__ double t[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t bi = blockIdx.x, bj = blockIdx.y;
+  if (bi < bj) return;
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = bj * 32 + tx, j = bi * 32 + r;
+    t[r][tx] = (i < n && j < n) ? x[i + ld * j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = bi * 32 + tx, j = bj * 32 + r;
+    if (i < n && j < n &&
+        __double_as_longlong(x[i + ld * j]) != __double_as_longlong(t[tx][r]))
+      *bad = 1u;
+  }
+}
+
 }  // namespace
+
+// 1 iff the device matrix is bit-for-bit symmetric (decides the half-GEMM for X*X)
+int sdpsr_matrix_symmetric(sdpsr_ctx* ctx, const double* x, int* is_sym) {
+  uint32_t* bad = ctx->d_scalars + 9;
+  SDPSR_CUDA(cudaMemsetAsync(bad, 0, sizeof(uint32_t), ctx->stream));
+  const unsigned nb = (unsigned)((ctx->n + 31) / 32);
+  {
+    Timed tm(ctx, SDPSR_K_MISC, (double)ctx->elems * 8.0);
+    symcheck_f64_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(x, ctx->n, ctx->ld, bad);
+    count_launch(ctx);
+  }
+  SDPSR_CUDA(cudaGetLastError());
+  uint32_t* hb = reinterpret_cast<uint32_t*>(ctx->h_pinned) + 33;
+  SDPSR_CUDA(cudaMemcpyAsync(hb, bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  *is_sym = (*hb == 0u) ? 1 : 0;
+  return SDPSR_OK;
+}
 
 // ---------------------------------------------------------------------------
 void sdpsr_constraints_free(sdpsr_ctx* ctx) {

@@ -230,6 +230,7 @@ int sdpsr_rowdots(sdpsr_ctx* ctx, const double* x_array, const double* lut, std:
 int sdpsr_solve_gram(sdpsr_ctx* ctx, std::vector<double>& rhs);
 int sdpsr_upload_tpat(sdpsr_ctx* ctx, const std::vector<double>& coef);
 int sdpsr_symmetric_check(sdpsr_ctx* ctx, int* is_sym);
+int sdpsr_matrix_symmetric(sdpsr_ctx* ctx, const double* x, int* is_sym);
 
 // blockdiag.cu
 void sdpsr_blockdiag_free(sdpsr_ctx* ctx);

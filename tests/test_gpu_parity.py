@@ -342,3 +342,57 @@ def test_spectrum_invariant_gpu():
     assert np.allclose(sorted(small), big, atol=1e-9)
     assert sorted(mult) == prob.expected_mult
     P.release()
+
+
+# ---------------------------------------------------------------------------------
+# half-GEMM for symmetric X (SYRK-style) and stream hand-over
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [57, 130, 300, 515])
+def test_symmetric_square_uses_half_gemm_and_matches(n):
+    rng = np.random.default_rng(n)
+    L = rng.integers(0, 9, size=(n, n))
+    L = np.minimum(L, L.T)
+    P = O.partition_from_values(L)
+    r = rng.random(P.nparts)
+    X = O.fill(P, r)
+    ref = X @ X
+    outs = []
+    for flags in (0, B.F_NO_SYRK):
+        with B.Context(n, 0, flags) as ctx:
+            ctx.set_labels(L)
+            ctx.fill(r)
+            d = ctx.square_round_refine(ATOL)
+            X2 = ctx.get_matrix(B.MAT_X2)
+            outs.append((d, ctx.get_labels(), X2))
+    assert np.max(np.abs(outs[0][2] - ref)) < 1e-12 * np.abs(ref).max()
+    assert np.array_equal(outs[0][2], outs[0][2].T)                  # mirrored: exactly symmetric
+    want = O.refine(P, O.partition_from_values(O.clamp_round(ref, ATOL)))
+    for d, lab, _ in outs:
+        assert d == want.nparts and np.array_equal(lab, want.matrix)
+
+
+def test_nonsymmetric_square_falls_back_to_full_gemm():
+    n = 150
+    rng = np.random.default_rng(1)
+    L = rng.integers(1, 6, size=(n, n))
+    P = O.partition_from_values(L)
+    r = rng.random(P.nparts)
+    X = O.fill(P, r)
+    with B.Context(n) as ctx:
+        ctx.set_labels(L)
+        ctx.fill(r)
+        ctx.square_round_refine(ATOL)
+        X2 = ctx.get_matrix(B.MAT_X2)
+    assert np.max(np.abs(X2 - X @ X)) < 1e-12 * np.abs(X @ X).max()
+
+
+def test_caller_stream():
+    import torch
+    prob = pr.lovasz_er(5)
+    with B.Context(prob.n) as ctx:
+        s = torch.cuda.Stream()
+        ctx.set_stream(s.cuda_stream)
+        P = S.admissible_subspace(*prob, rand=Coeffs(3), ctx=ctx)
+        assert P.nparts == 15
+        bd = S.blockDiagonalize(P, False, rand=Coeffs(4))
+        assert sorted(bd.blkSizes) == [2, 2, 2, 3]
