@@ -306,6 +306,7 @@ extern "C" int sdpsr_eig(sdpsr_ctx* ctx, const double* r1, int64_t len, double* 
   }
   Solver* s = reinterpret_cast<Solver*>(ctx->solver);
   size_t wdev = 0, whost = 0;
+  if (ctx->rank == 0)
   SDPSR_REQUIRE(cusolverDnXsyevd_bufferSize(s->h, s->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, ctx->n,
                                             CUDA_R_64F, ctx->Q, ctx->ld, CUDA_R_64F, s->d_vals, CUDA_R_64F, &wdev,
                                             &whost) == CUSOLVER_STATUS_SUCCESS,
@@ -322,8 +323,8 @@ extern "C" int sdpsr_eig(sdpsr_ctx* ctx, const double* r1, int64_t len, double* 
     SDPSR_REQUIRE(ctx->solver_hwork != nullptr, SDPSR_E_ALLOC, "host workspace allocation failed");
     ctx->solver_hwork_bytes = whost;
   }
-  cusolverStatus_t st;
-  {
+  cusolverStatus_t st = CUSOLVER_STATUS_SUCCESS;
+  if (ctx->rank == 0) {          // multi-GPU: one rank factorises, all receive (identical Q everywhere)
     Timed tm(ctx, SDPSR_K_EIG, 0.0);
     st = cusolverDnXsyevd(s->h, s->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, ctx->n, CUDA_R_64F, ctx->Q,
                           ctx->ld, CUDA_R_64F, s->d_vals, CUDA_R_64F, ctx->solver_work, wdev, ctx->solver_hwork, whost,
@@ -331,6 +332,12 @@ extern "C" int sdpsr_eig(sdpsr_ctx* ctx, const double* r1, int64_t len, double* 
   }
   SDPSR_REQUIRE(st == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
                 "cusolverDnXsyevd failed (status " + std::to_string((int)st) + ")");
+  if (ctx->nranks > 1) {
+    if (ctx->rank != 0) SDPSR_CUDA(cudaMemsetAsync(ctx->solver_info, 0, sizeof(int), ctx->stream));
+    SDPSR_TRY(sdpsr_comm_bcast(ctx, ctx->Q, ctx->elems * sizeof(double), 0));
+    SDPSR_TRY(sdpsr_comm_bcast(ctx, s->d_vals, (size_t)ctx->n * sizeof(double), 0));
+    SDPSR_TRY(sdpsr_comm_bcast(ctx, ctx->solver_info, sizeof(int), 0));
+  }
   int* hinfo = reinterpret_cast<int*>(ctx->h_pinned) + 64;
   SDPSR_CUDA(cudaMemcpyAsync(hinfo, ctx->solver_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   SDPSR_CUDA(cudaMemcpyAsync(vals, s->d_vals, (size_t)ctx->n * sizeof(double), cudaMemcpyDefault, ctx->stream));
@@ -358,13 +365,14 @@ extern "C" int sdpsr_block_norms(sdpsr_ctx* ctx, const double* r2, int64_t len, 
   // A2 = fill(S, r2) -> X ; T = A2 * Q ; X2 = Q' ; W = Q' * T            (:203)
   SDPSR_TRY(fill_into(ctx, r2, len, ctx->X));
   ctx->x_valid = false;
-  SDPSR_TRY(sdpsr_gemm_f64(ctx, ctx->X, ld, ctx->Q, ld, ctx->T, ld, ld, n, n, false));
+  SDPSR_TRY(sdpsr_gemm_f64(ctx, ctx->X, ld, ctx->Q, ld, ctx->T, ld, ld, n, n, false, /*shard=*/true));
   const unsigned nb = (unsigned)((n + 31) / 32);
   if (ld != n) SDPSR_CUDA(cudaMemsetAsync(ctx->X2, 0, ctx->elems * 8, ctx->stream));
   transpose_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(ctx->Q, ctx->X2, n, ld);
   count_launch(ctx);
   // W = Q' (A2 Q) is symmetric (A2 is: sdpsr_eig checked the partition): lower tiles + mirror
-  SDPSR_TRY(sdpsr_gemm_f64(ctx, ctx->X2, ld, ctx->T, ld, ctx->W, ld, ld, n, n, !(ctx->flags & SDPSR_F_NO_SYRK)));
+  SDPSR_TRY(sdpsr_gemm_f64(ctx, ctx->X2, ld, ctx->T, ld, ctx->W, ld, ld, n, n, !(ctx->flags & SDPSR_F_NO_SYRK),
+                           /*shard=*/true));
   // block maxima
   uint32_t *d_space = nullptr, *d_sdim = nullptr;
   unsigned long long* d_norms = nullptr;

@@ -3,6 +3,7 @@
 // this is new surface.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstring>
 
 #include "sdpsr_internal.cuh"
@@ -22,6 +23,9 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool ok = false;
 };
@@ -41,14 +45,61 @@ NcclApi& api() {
   a.AllGather = (decltype(a.AllGather))dlsym(a.lib, "ncclAllGather");
   a.AllReduce = (decltype(a.AllReduce))dlsym(a.lib, "ncclAllReduce");
   a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
-  a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.AllReduce;
+  a.Broadcast = (decltype(a.Broadcast))dlsym(a.lib, "ncclBroadcast");
+  a.GroupStart = (decltype(a.GroupStart))dlsym(a.lib, "ncclGroupStart");
+  a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.lib, "ncclGroupEnd");
+  a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.AllReduce && a.Broadcast &&
+         a.GroupStart && a.GroupEnd;
   return a;
 }
 
 }  // namespace
 
+constexpr int NCCL_UINT8 = 1, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_MAX = 2;
+
+#define NCCL_TRY(call)                                                                               \
+  do {                                                                                               \
+    ncclResult_t _r = (call);                                                                        \
+    if (_r != 0)                                                                                     \
+      return ctx->fail(SDPSR_E_NCCL, std::string(#call) + ": " +                                     \
+                                         (api().GetErrorString ? api().GetErrorString(_r) : "?"));  \
+  } while (0)
+
+// Tile-column tn (columns [tn*tile_cols, ...)) of the column-major matrix C is owned by rank
+// tn % nranks; it is one contiguous slab.  One grouped launch broadcasts every slab from its owner.
+int sdpsr_comm_exchange_tilecols(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t ncols, int tile_cols,
+                                 int ntilecols) {
+  if (ctx->nranks <= 1) return SDPSR_OK;
+  Timed tm(ctx, SDPSR_K_MISC, (double)ldc * (double)ncols * 8.0);
+  NCCL_TRY(api().GroupStart());
+  for (int tn = 0; tn < ntilecols; ++tn) {
+    const int64_t c0 = (int64_t)tn * tile_cols;
+    const int64_t w = std::min<int64_t>(tile_cols, ncols - c0);
+    double* slab = C + ldc * c0;
+    NCCL_TRY(api().Broadcast(slab, slab, (size_t)(ldc * w), NCCL_FLOAT64, tn % ctx->nranks, (ncclComm_t)ctx->nccl,
+                             ctx->stream));
+  }
+  NCCL_TRY(api().GroupEnd());
+  return SDPSR_OK;
+}
+
+int sdpsr_comm_bcast(sdpsr_ctx* ctx, void* buf, size_t bytes, int root) {
+  if (ctx->nranks <= 1) return SDPSR_OK;
+  NCCL_TRY(api().Broadcast(buf, buf, bytes, NCCL_UINT8, root, (ncclComm_t)ctx->nccl, ctx->stream));
+  return SDPSR_OK;
+}
+
+int sdpsr_comm_allreduce_max_u64(sdpsr_ctx* ctx, unsigned long long* buf, size_t count) {
+  if (ctx->nranks <= 1) return SDPSR_OK;
+  NCCL_TRY(api().AllReduce(buf, buf, count, NCCL_UINT64, NCCL_MAX, (ncclComm_t)ctx->nccl, ctx->stream));
+  return SDPSR_OK;
+}
+
 void sdpsr_comm_free(sdpsr_ctx* ctx) {
   if (ctx->nccl && api().ok) api().CommDestroy((ncclComm_t)ctx->nccl);
+  cudaFree(ctx->d_tiles);
+  ctx->d_tiles = nullptr;
+  ctx->tile_alloc = 0;
   ctx->nccl = nullptr;
   ctx->nranks = 1;
   ctx->rank = 0;

@@ -433,7 +433,7 @@ extern "C" int sdpsr_square_round_refine(sdpsr_ctx* ctx, double atol, int64_t* d
   int sym = 0;
   if (!(ctx->flags & SDPSR_F_NO_SYRK)) SDPSR_TRY(sdpsr_matrix_symmetric(ctx, ctx->X, &sym));
   SDPSR_TRY(sdpsr_gemm_f64(ctx, ctx->X, ctx->ld, ctx->X, ctx->ld, ctx->X2, ctx->ld, ctx->ld, ctx->n, ctx->n,
-                           sym != 0));
+                           sym != 0, /*shard=*/true));
   SDPSR_TRY(sdpsr_generic_refine_values(ctx, ctx->X2, atol, true, nullptr, dim));
   return finish(ctx);
 }
@@ -452,7 +452,8 @@ extern "C" int sdpsr_product_round_refine(sdpsr_ctx* ctx, const double* rx, cons
   SDPSR_TRY(sdpsr_build_lut(ctx, ctx->d_values, len));
   SDPSR_TRY(sdpsr_materialize_fill(ctx, ctx->X));
   ctx->x_valid = true;
-  SDPSR_TRY(sdpsr_gemm_f64(ctx, ctx->X, ctx->ld, Y, ctx->ld, ctx->X2, ctx->ld, ctx->ld, ctx->n, ctx->n, false));
+  SDPSR_TRY(sdpsr_gemm_f64(ctx, ctx->X, ctx->ld, Y, ctx->ld, ctx->X2, ctx->ld, ctx->ld, ctx->n, ctx->n, false,
+                           /*shard=*/true));
   SDPSR_TRY(sdpsr_generic_refine_values(ctx, ctx->X2, atol, true, nullptr, dim));
   return finish(ctx);
 }

@@ -85,7 +85,8 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
 // tiles are mirrored into the upper triangle by mirror_kernel afterwards.
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                double* __restrict__ C, int64_t ldc, int M, int Nc, int K, int tiles_m, int tiles_n, int lower) {
+                double* __restrict__ C, int64_t ldc, int M, int Nc, int K, int tiles_m, int tiles_n, int lower,
+                const int2* __restrict__ tile_list) {
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;       // SWIZZLE_128B atoms are 1 KB
   const uint32_t bar_full = base + STAGES * STAGE_BYTES;
@@ -96,7 +97,11 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   // ---- tile coordinates -----------------------------------------------------
   int tm, tn;
-  if (!lower) {
+  if (tile_list) {               // multi-GPU: this rank's share of the tiles
+    const int2 t = tile_list[blockIdx.x];
+    tm = t.x;
+    tn = t.y;
+  } else if (!lower) {
     const int pid = blockIdx.x;
     const int per_group = RASTER_GROUP * tiles_m;
     const int g = pid / per_group;
@@ -268,8 +273,17 @@ int make_map(sdpsr_ctx* ctx, CUtensorMap* map, const double* ptr, int64_t rows, 
 
 }  // namespace
 
+// Tiles of the (possibly lower-triangular) product owned by `rank` of `nranks`: tile-COLUMNS are dealt
+// round-robin (tn % nranks == rank), which balances the triangle and keeps every owned slab contiguous
+// in column-major storage.  Mirrored in sdpsymmetryreduction.jl_b200/sharding.py (CPU-tested).
+static void owned_tiles(int tiles_m, int tiles_n, bool lower, int nranks, int rank, std::vector<int2>& out) {
+  out.clear();
+  for (int tn = rank; tn < tiles_n; tn += nranks)
+    for (int tm = lower ? tn : 0; tm < tiles_m; ++tm) out.push_back(make_int2(tm, tn));
+}
+
 int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
-                   int64_t ldc, int64_t M, int64_t Nc, int64_t K, bool symmetric_out) {
+                   int64_t ldc, int64_t M, int64_t Nc, int64_t K, bool symmetric_out, bool shard) {
   SDPSR_REQUIRE(M > 0 && Nc > 0 && K > 0, SDPSR_E_INVALID, "empty GEMM");
   SDPSR_REQUIRE(lda % 2 == 0 && ldb % 2 == 0, SDPSR_E_INVALID, "leading dimensions must be even (16-byte TMA strides)");
   SDPSR_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0), SDPSR_E_INVALID, "operands must be 16-byte aligned");
@@ -286,18 +300,41 @@ int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B
   const int tiles_m = (int)((M + BM - 1) / BM);
   const int tiles_n = (int)((Nc + BN - 1) / BN);
   const bool lower = symmetric_out && M >= Nc && tiles_m == tiles_n;
-  const int64_t ntiles = lower ? (int64_t)tiles_m * (tiles_m + 1) / 2 : (int64_t)tiles_m * tiles_n;
+  int64_t ntiles = lower ? (int64_t)tiles_m * (tiles_m + 1) / 2 : (int64_t)tiles_m * tiles_n;
+  const bool sharded = shard && ctx->nranks > 1;
+  const int2* d_tiles = nullptr;
+  if (sharded) {
+    std::vector<int2> tiles;
+    owned_tiles(tiles_m, tiles_n, lower, ctx->nranks, ctx->rank, tiles);
+    ntiles = (int64_t)tiles.size();
+    if (ctx->tile_alloc < tiles.size()) {
+      cudaFree(ctx->d_tiles);
+      ctx->d_tiles = nullptr;
+      SDPSR_CUDA(cudaMalloc(&ctx->d_tiles, std::max<size_t>(tiles.size(), 1024) * sizeof(int2)));
+      ctx->tile_alloc = std::max<size_t>(tiles.size(), 1024);
+    }
+    if (ntiles) SDPSR_CUDA(cudaMemcpyAsync(ctx->d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));     // `tiles` dies at scope end
+    d_tiles = reinterpret_cast<const int2*>(ctx->d_tiles);
+  }
   {
     // work = flops issued: the lower-triangle launch covers ntiles full 128x128 tiles
-    Timed tm(ctx, SDPSR_K_GEMM, lower ? 2.0 * (double)ntiles * BM * BN * (double)K : 2.0 * (double)M * (double)Nc * (double)K);
-    gemm_f64_kernel<<<(unsigned)ntiles, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, C, ldc, (int)M, (int)Nc, (int)K,
-                                                                           tiles_m, tiles_n, lower ? 1 : 0);
-    count_launch(ctx);
-    if (lower) {
-      dim3 g((unsigned)((Nc + 31) / 32), (unsigned)((Nc + 31) / 32));
-      mirror_lower_kernel<<<g, 256, 0, ctx->stream>>>(C, ldc, (int)Nc);
+    Timed tm(ctx, SDPSR_K_GEMM, (lower || sharded) ? 2.0 * (double)ntiles * BM * BN * (double)K
+                                                   : 2.0 * (double)M * (double)Nc * (double)K);
+    if (ntiles) {
+      gemm_f64_kernel<<<(unsigned)ntiles, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, C, ldc, (int)M, (int)Nc, (int)K,
+                                                                             tiles_m, tiles_n, lower ? 1 : 0, d_tiles);
       count_launch(ctx);
     }
+  }
+  SDPSR_CUDA(cudaGetLastError());
+  // every rank receives the tile-columns it does not own (grouped NCCL broadcasts over NVLink)
+  if (sharded) SDPSR_TRY(sdpsr_comm_exchange_tilecols(ctx, C, ldc, Nc, BN, tiles_n));
+  if (lower) {
+    Timed tm(ctx, SDPSR_K_MISC, (double)M * (double)Nc * 8.0);
+    dim3 g((unsigned)((Nc + 31) / 32), (unsigned)((Nc + 31) / 32));
+    mirror_lower_kernel<<<g, 256, 0, ctx->stream>>>(C, ldc, (int)Nc);
+    count_launch(ctx);
   }
   SDPSR_CUDA(cudaGetLastError());
   return SDPSR_OK;

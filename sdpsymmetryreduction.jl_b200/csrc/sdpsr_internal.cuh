@@ -145,6 +145,8 @@ struct sdpsr_ctx {
   // comm (multi-GPU)
   void* nccl = nullptr;
   int nranks = 1, rank = 0;
+  void* d_tiles = nullptr;      // this rank's (tm, tn) tile list for sharded GEMMs
+  size_t tile_alloc = 0;
 
   // timing
   std::vector<EventPair> ev_pending;
@@ -221,7 +223,8 @@ int sdpsr_upload_values(sdpsr_ctx* ctx, const double* values, int64_t len);
 
 // gemm_f64.cu :  C[M x Nc] = A[M x K] * B[K x Nc], all column-major with the given lds
 int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t ldb,
-                   double* C, int64_t ldc, int64_t M, int64_t Nc, int64_t K, bool symmetric_out);
+                   double* C, int64_t ldc, int64_t M, int64_t Nc, int64_t K, bool symmetric_out,
+                   bool shard = false);
 
 // project.cu
 int sdpsr_constraints_finalize(sdpsr_ctx* ctx);
@@ -238,6 +241,9 @@ void sdpsr_blockdiag_rebind(sdpsr_ctx* ctx);
 
 // comm.cu
 void sdpsr_comm_free(sdpsr_ctx* ctx);
+int sdpsr_comm_exchange_tilecols(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t ncols, int tile_cols, int ntilecols);
+int sdpsr_comm_bcast(sdpsr_ctx* ctx, void* buf, size_t bytes, int root);
+int sdpsr_comm_allreduce_max_u64(sdpsr_ctx* ctx, unsigned long long* buf, size_t count);
 
 // launch bookkeeping
 static inline void count_launch(sdpsr_ctx* ctx, int k = 1) { ctx->launches += k; }

@@ -1,0 +1,83 @@
+"""CPU tests of the multi-GPU host logic (world_size 2, gloo): the tile deal covers every tile
+exactly once and is balanced, and the exchange protocol (owner broadcasts each tile-column,
+everyone mirrors the lower triangle) reassembles the full product on every rank."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from sdpsr_b200 import sharding as sh
+
+
+@pytest.mark.parametrize("n", [100, 128, 1000, 4096, 16384, 15504])
+@pytest.mark.parametrize("nranks", [1, 2, 4, 8])
+@pytest.mark.parametrize("lower", [False, True])
+def test_tile_deal_partitions_the_tiles(n, nranks, lower):
+    t = sh.num_tiles(n)
+    seen = set()
+    for r in range(nranks):
+        for tile in sh.owned_tiles(t, t, lower, nranks, r):
+            assert tile not in seen
+            assert sh.owner_of_tile_column(tile[1], nranks) == r
+            seen.add(tile)
+    want = {(tm, tn) for tn in range(t) for tm in range(tn if lower else 0, t)}
+    assert seen == want
+    counts = sh.work_balance(n, lower, nranks)
+    if t >= 8 * nranks:                       # enough tile-columns: within 15 % of perfect balance
+        assert max(counts) <= 1.15 * sum(counts) / nranks + 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, tile, lower, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(0)
+    L = rng.integers(0, 5, size=(n, n))
+    if lower:
+        L = np.minimum(L, L.T)
+    X = np.array([0.0, 0.3, 0.7, 0.11, 0.9])[L]
+    t = (n + tile - 1) // tile
+    C = np.zeros((n, n), order="F")
+    for tm, tn in sh.owned_tiles(t, t, lower, world, rank):          # this rank's share of X*X
+        r0, c0 = tm * tile, tn * tile
+        C[r0:r0 + tile, c0:c0 + tile] = X[r0:r0 + tile, :] @ X[:, c0:c0 + tile]
+    for tn in range(t):                                              # grouped broadcasts, one per slab
+        slab = torch.from_numpy(np.ascontiguousarray(C[:, tn * tile:(tn + 1) * tile]))
+        dist.broadcast(slab, src=sh.owner_of_tile_column(tn, world))
+        C[:, tn * tile:(tn + 1) * tile] = slab.numpy()
+    if lower:                                                        # mirror_lower_kernel
+        iu = np.triu_indices(n, 1)
+        C[iu] = C.T[iu]
+    ref = X @ X
+    ok = np.allclose(C, ref, rtol=1e-13, atol=1e-13)
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(int(flag.item()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("lower", [False, True])
+def test_exchange_protocol_gloo_world2(lower):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 150, 32, lower, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) == 1
