@@ -28,14 +28,14 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    box = [B.Context.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(box, src=0)
     results = []
     probs = [pr.lovasz_er(7), pr.qap_esc16j(os.path.join("tests", "golden", "esc16j.npz")), pr.kneser(10, 4),
              pr.hamming(3, 8), pr.synthetic_product_scheme(3, 3, 16), pr.hamming(5, 4)]
     ok_all = True
     for prob in probs:
         ctx = B.Context(prob.n, local, 0)
+        box = [B.Context.comm_unique_id() if rank == 0 else None]     # one NCCL id per communicator
+        dist.broadcast_object_list(box, src=0)
         ctx.comm_init(world, rank, box[0])
         assert ctx.comm_info() == (world, rank)
         Pg = S.admissible_subspace(*prob, rand=Coeffs(11), ctx=ctx)
@@ -50,7 +50,7 @@ def main():
                       for i in range(Po.nparts) for k in range(len(so)))
         ok = same_labels and same_sizes and err < 1e-8 and Pg.nparts == prob.expected_dim
         # every rank must hold the same labels
-        t = torch.from_numpy(Pg.matrix.astype(np.int64)).cuda()
+        t = torch.from_numpy(np.ascontiguousarray(Pg.matrix.astype(np.int64))).cuda()
         t0 = t.clone()
         dist.broadcast(t0, src=0)
         ok = ok and bool(torch.equal(t, t0))
