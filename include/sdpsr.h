@@ -180,6 +180,13 @@ int sdpsr_set_qhat(sdpsr_ctx* ctx, const double* qhat, const int64_t* blk_sizes,
  * with |entries| < atol clamped to 0.  out_len must be dim * sum(s_k^2).              */
 int sdpsr_basis_image(sdpsr_ctx* ctx, double atol, double* out, int64_t out_len);
 
+/* ------------------------------------------------------ reduced SDP assembly
+ * The step right after the path (README.md:57-60, test/sd_problems.jl:32-37):
+ *   newA = A * PMat  (m x dim, column-major),  newC = C' * PMat  (dim),
+ * PMat[:, i] = vec(S .== i+1).  Either output may be NULL.  Sums are accumulated with
+ * floating-point atomics (order not fixed; exact for the 0/1 data of the reference's problems). */
+int sdpsr_reduce_problem(sdpsr_ctx* ctx, const double* C, double* newA, double* newC);
+
 /* -------------------------------------------------------------- plumbing */
 int sdpsr_get_matrix(sdpsr_ctx* ctx, int which, double* out);       /* N x N doubles */
 int sdpsr_set_matrix(sdpsr_ctx* ctx, int which, const double* in);  /* N x N doubles */

@@ -20,6 +20,7 @@ from .api import (  # noqa: F401
     diagonalize,
     dim,
     randomize,
+    reduce_problem,
     refine,
     unSymmetrize,
 )

@@ -412,3 +412,26 @@ def blockDiagonalize(P: Partition, verbose: bool = True, *, epsilon: float = RTO
     if verbose:
         log.info("Calculating image of the basis of the algebra... %.3fs", time.perf_counter() - t)
     return BlockDiagonalization([int(s) for s in sizes], blks)
+
+
+# ----------------------------------------------------------------------------
+# consumers of the path
+# ----------------------------------------------------------------------------
+def reduce_problem(P: Partition, C, A, b):
+    """The reduced SDP data of README.md:57-60 / test/sd_problems.jl:32-37:
+    ``newA = A*PMat``, ``newB = b``, ``newC = C'*PMat`` with ``PMat[:, i] = vec(P.matrix .== i+1)``."""
+    ctx = P._context()
+    if not getattr(ctx, "_constraints_set", False):
+        ctx.set_constraints(A)
+    Cv = np.asarray(C.todense()).reshape(-1) if hasattr(C, "todense") else C
+    newA, newC = ctx.reduce_problem(Cv, A.shape[0])
+    return newA, np.asarray(b, dtype=np.float64).copy(), newC
+
+
+def _constraints(P: Partition):
+    """``_constraints(P)`` (src/diagonalize.jl:42-50): for every class the 0-based column-major linear
+    indices of its entries, ascending.  Pure host bookkeeping on the exported label matrix."""
+    flat = np.asarray(P.matrix).reshape(-1, order="F")
+    order = np.argsort(flat, kind="stable")
+    bounds = np.searchsorted(flat[order], np.arange(1, P.nparts + 2))
+    return [order[bounds[i]:bounds[i + 1]].astype(np.uint32) for i in range(P.nparts)]

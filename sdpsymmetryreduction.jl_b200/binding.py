@@ -73,6 +73,7 @@ _SIGNATURES = {
     "sdpsr_get_qhat": ([_p, _p, _i64], C.c_int),
     "sdpsr_set_qhat": ([_p, _p, _p, _i64], C.c_int),
     "sdpsr_basis_image": ([_p, C.c_double, _p, _i64], C.c_int),
+    "sdpsr_reduce_problem": ([_p, _p, _p, _p], C.c_int),
     "sdpsr_get_matrix": ([_p, C.c_int, _p], C.c_int),
     "sdpsr_set_matrix": ([_p, C.c_int, _p], C.c_int),
     "sdpsr_gemm": ([_p, C.c_int, C.c_int, C.c_int], C.c_int),
@@ -189,6 +190,7 @@ class Context:
             Af = np.asfortranarray(A)       # Julia Matrix layout: m x N^2 column-major
             self._check(self.lib.sdpsr_set_constraints_dense(self._h, m, Af.ctypes.data))
         self.m = m
+        self._constraints_set = True
 
     def set_constraints_csc(self, m, colptr, rowval, nzval, index_base=0):
         colptr = np.ascontiguousarray(colptr, dtype=np.int64)
@@ -348,6 +350,18 @@ class Context:
                 off += s * s
             blks.append(row)
         return blks
+
+    def reduce_problem(self, Cvec, m: int, want_A: bool = True, want_C: bool = True):
+        """(A * PMat, C' * PMat) for the context's partition (README.md:57-60)."""
+        d = self.dim()
+        newA = np.zeros((m, d), dtype=np.float64, order="F") if want_A else None
+        newC = np.zeros(d, dtype=np.float64) if want_C else None
+        if isinstance(Cvec, np.ndarray):
+            Cvec = _f64(Cvec).reshape(-1)
+        self._check(self.lib.sdpsr_reduce_problem(self._h, _ptr(Cvec) if want_C else None,
+                                                  newA.ctypes.data if want_A else None,
+                                                  newC.ctypes.data if want_C else None))
+        return newA, newC
 
     # -- matrices / tools --------------------------------------------------------------
     def get_matrix(self, which: int) -> np.ndarray:

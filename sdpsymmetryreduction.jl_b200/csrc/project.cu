@@ -155,6 +155,68 @@ __global__ void __launch_bounds__(256) symcheck_kernel(const uint32_t* __restric
   }
 }
 
+// Reduced-SDP assembly (README.md:57-60, test/sd_problems.jl:32-37): sums over the classes of S.
+constexpr int RB_MAX = 4096;   // classes binned in shared memory per CTA
+
+// newA[k + m*(c-1)] += val for every stored entry of row k whose class is c
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const uint32_t* __restrict__ col, const double* __restrict__ val,
+                                                          const uint32_t* __restrict__ chunk_row,
+                                                          const uint32_t* __restrict__ chunk_beg,
+                                                          const uint32_t* __restrict__ chunk_end,
+                                                          const uint32_t* __restrict__ labels,
+                                                          const uint32_t* __restrict__ rank, int64_t m, int64_t d,
+                                                          double* __restrict__ newA) {
+  extern __shared__ double bins[];
+  const bool use_smem = d <= RB_MAX;
+  if (use_smem) {
+    for (int64_t i = threadIdx.x; i < d; i += blockDim.x) bins[i] = 0.0;
+    __syncthreads();
+  }
+  const uint32_t c = blockIdx.x;
+  const int64_t k = chunk_row[c];
+  for (uint32_t i = chunk_beg[c] + threadIdx.x; i < chunk_end[c]; i += blockDim.x) {
+    const uint32_t cls = rank[labels[col[i]]];
+    if (cls == 0u) continue;
+    if (use_smem)
+      atomicAdd(&bins[cls - 1], val[i]);
+    else
+      atomicAdd(&newA[k + m * (int64_t)(cls - 1)], val[i]);
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < d; i += blockDim.x)
+      if (bins[i] != 0.0) atomicAdd(&newA[k + m * i], bins[i]);
+  }
+}
+
+// newC[c-1] += C[idx] for every entry of class c
+__global__ void __launch_bounds__(256) reduce_objective_kernel(const double* __restrict__ Cv,
+                                                               const uint32_t* __restrict__ labels,
+                                                               const uint32_t* __restrict__ rank, uint64_t total,
+                                                               int64_t d, double* __restrict__ newC) {
+  extern __shared__ double bins[];
+  const bool use_smem = d <= RB_MAX;
+  if (use_smem) {
+    for (int64_t i = threadIdx.x; i < d; i += blockDim.x) bins[i] = 0.0;
+    __syncthreads();
+  }
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t cls = rank[labels[i]];
+    if (cls == 0u) continue;
+    const double v = Cv[i];
+    if (v == 0.0) continue;
+    if (use_smem)
+      atomicAdd(&bins[cls - 1], v);
+    else
+      atomicAdd(&newC[cls - 1], v);
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < d; i += blockDim.x)
+      if (bins[i] != 0.0) atomicAdd(&newC[i], bins[i]);
+  }
+}
+
 __global__ void __launch_bounds__(256) symcheck_f64_kernel(const double* __restrict__ x, int64_t n, int64_t ld,
                                                            uint32_t* __restrict__ bad) {
   __shared__ double t[32][33];
@@ -645,4 +707,47 @@ extern "C" int sdpsr_init_partition(sdpsr_ctx* ctx, const double* C, const doubl
   ctx->x_valid = false;
   ctx->x_is_fill = false;
   return finish(ctx);
+}
+
+// newA = A * PMat (m x dim, column-major), newC = C' * PMat (dim)   (README.md:57-60)
+extern "C" int sdpsr_reduce_problem(sdpsr_ctx* ctx, const double* C, double* newA, double* newC) {
+  CTX_ENTER();
+  ConstraintSet& c = ctx->cons;
+  SDPSR_REQUIRE(newA == nullptr || c.ready, SDPSR_E_STATE, "constraints not set (sdpsr_set_constraints_*)");
+  const int64_t d = ctx->dim, m = c.m;
+  if (d == 0) return SDPSR_OK;
+  KeyTable& t = ctx->tab[ctx->cur];
+  const size_t smem = d <= RB_MAX ? (size_t)d * sizeof(double) : 0;
+  double* dA = nullptr;
+  double* dC = nullptr;
+  int st = SDPSR_OK;
+  if (newA) {
+    SDPSR_CUDA(cudaMalloc(&dA, (size_t)m * d * sizeof(double)));
+    SDPSR_CUDA(cudaMemsetAsync(dA, 0, (size_t)m * d * sizeof(double), ctx->stream));
+    if (c.nchunks) {
+      reduce_rows_kernel<<<(unsigned)c.nchunks, 256, smem, ctx->stream>>>(c.d_col, c.d_val, c.d_chunk_row, c.d_chunk_beg,
+                                                                          c.d_chunk_beg + c.nchunks, ctx->labels, t.rank,
+                                                                          m, d, dA);
+      count_launch(ctx);
+    }
+    if (cudaMemcpyAsync(newA, dA, (size_t)m * d * sizeof(double), cudaMemcpyDefault, ctx->stream) != cudaSuccess)
+      st = ctx->fail(SDPSR_E_CUDA, "copy of newA failed");
+  }
+  if (newC && st == SDPSR_OK) {
+    SDPSR_REQUIRE(C != nullptr, SDPSR_E_INVALID, "C is NULL");
+    if (ctx->ld != ctx->n) cudaMemsetAsync(ctx->X2, 0, ctx->elems * 8, ctx->stream);
+    cudaMemcpy2DAsync(ctx->X2, (size_t)ctx->ld * 8, C, (size_t)ctx->n * 8, (size_t)ctx->n * 8, (size_t)ctx->n,
+                      cudaMemcpyDefault, ctx->stream);
+    cudaMalloc(&dC, (size_t)d * sizeof(double));
+    cudaMemsetAsync(dC, 0, (size_t)d * sizeof(double), ctx->stream);
+    const int grid = (int)std::min<uint64_t>((ctx->elems + 255) / 256, (uint64_t)ctx->sm_count * 4);
+    reduce_objective_kernel<<<grid, 256, smem, ctx->stream>>>(ctx->X2, ctx->labels, t.rank, ctx->elems, d, dC);
+    count_launch(ctx);
+    if (cudaMemcpyAsync(newC, dC, (size_t)d * sizeof(double), cudaMemcpyDefault, ctx->stream) != cudaSuccess)
+      st = ctx->fail(SDPSR_E_CUDA, "copy of newC failed");
+  }
+  const int fin = finish(ctx);
+  cudaFree(dA);
+  cudaFree(dC);
+  return st != SDPSR_OK ? st : fin;
 }

@@ -249,12 +249,14 @@ def qap_esc16j(npz_path: str) -> SDPProblem:
 # synthetic permutation-symmetric SDP (BASELINE.json configs[4])
 # ----------------------------------------------------------------------------
 def synthetic_product_scheme(fields: int = 3, bits: int = 5, m: int = 64, seed: int = 1234,
-                             sparse: bool = True) -> SDPProblem:
+                             sparse: bool = True, keep_orbitals: bool = True,
+                             chunk_cols: int = 2048) -> SDPProblem:
     """Vertices Z_2^(fields*bits); orbital of (u,v) = per-field popcounts of u^v,
     conjugated by a random vertex permutation (SURVEY.md 8(d) cfg 5).
 
     The closure must recover exactly the (bits+1)^fields orbitals; all blocks
-    are 1x1.
+    are 1x1.  Built in column chunks so that N = 32768 needs ~20 GB of host memory
+    instead of ~60.
     """
     from math import comb
     nb = fields * bits
@@ -263,37 +265,56 @@ def synthetic_product_scheme(fields: int = 3, bits: int = 5, m: int = 64, seed: 
     perm = rng.permutation(N)
     norb = (bits + 1) ** fields
     cvals = rng.integers(1, 10, size=norb).astype(np.float64)
-
     u = perm.astype(np.int64)
-    x = u[:, None] ^ u[None, :]
-    orb = np.zeros((N, N), dtype=np.int32)
-    for f in range(fields):
-        fld = (x >> (f * bits)) & ((1 << bits) - 1)
-        orb = orb * (bits + 1) + _popcount64(fld).astype(np.int32)
-    del x
-    # orbital sizes and the m smallest (stable; the identity orbital 0 is first)
-    sizes = np.bincount(orb.reshape(-1), minlength=norb)
+
+    def orbital_block(c0, c1):
+        """orbital ids of rows 0..N-1 x columns c0..c1-1, shape (N, c1-c0)"""
+        x = u[:, None] ^ u[None, c0:c1]
+        o = np.zeros(x.shape, dtype=np.int32)
+        for f in range(fields):
+            fld = (x >> (f * bits)) & ((1 << bits) - 1)
+            o = o * (bits + 1) + _popcount64(fld).astype(np.int32)
+        return o
+
+    # orbital sizes: every row of the orbital matrix has the same histogram (vertex-transitive)
+    sizes = np.bincount(orbital_block(0, 1).reshape(-1), minlength=norb).astype(np.int64) * N
     order = np.argsort(sizes, kind="stable")
     assert order[0] == 0
     m = min(m, norb)
     chosen = order[:m]
-    orbF = orb.reshape(-1, order="F")
-    C = cvals[orbF]
-    b = np.zeros(m)
-    b[0] = 1.0
     sel = np.full(norb, -1, dtype=np.int64)
     sel[chosen] = np.arange(m)
-    rowid = sel[orbF]
-    nz = np.flatnonzero(rowid >= 0)
-    o = np.argsort(rowid[nz], kind="stable")
-    cols = nz[o]
-    counts = np.bincount(rowid[nz], minlength=m)
+
+    C = np.empty(N * N, dtype=np.float64)
+    orb_full = np.empty((N, N), dtype=np.int32, order="F") if keep_orbitals else None
+    per_row = [[] for _ in range(m)]
+    for c0 in range(0, N, chunk_cols):
+        c1 = min(N, c0 + chunk_cols)
+        o = orbital_block(c0, c1)
+        oF = o.reshape(-1, order="F")                        # column-major inside the chunk
+        C[c0 * N:c1 * N] = cvals[oF]
+        if keep_orbitals:
+            orb_full[:, c0:c1] = o
+        rowid = sel[oF]
+        nz = np.flatnonzero(rowid >= 0)
+        rid = rowid[nz]
+        oo = np.argsort(rid, kind="stable")
+        nz, rid = nz[oo], rid[oo]
+        bounds = np.searchsorted(rid, np.arange(m + 1))
+        for k in range(m):
+            if bounds[k + 1] > bounds[k]:
+                per_row[k].append(nz[bounds[k]:bounds[k + 1]].astype(np.int64) + c0 * N)
+    cols = [np.concatenate(r) if r else np.zeros(0, dtype=np.int64) for r in per_row]
+    counts = np.array([c.size for c in cols], dtype=np.int64)
     indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-    A = sp.csr_matrix((np.ones(cols.size), cols.astype(np.int64), indptr), shape=(m, N * N))
+    allcols = np.concatenate(cols) if cols else np.zeros(0, dtype=np.int64)
+    A = sp.csr_matrix((np.ones(allcols.size), allcols, indptr), shape=(m, N * N))
+    b = np.zeros(m)
+    b[0] = 1.0
     if not sparse:
         A = A.toarray()
     mult = sorted(int(np.prod([comb(bits, j) for j in js]))
                   for js in itertools.product(range(bits + 1), repeat=fields))
     return SDPProblem(name=f"synthetic-{fields}xH({bits},2)-m{m}", C=C, A=A, b=b, n=N,
                       expected_dim=norb, expected_blocks=[1] * norb, expected_mult=mult,
-                      meta={"orbitals": orb})
+                      meta={"orbitals": orb_full})

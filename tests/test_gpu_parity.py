@@ -396,3 +396,29 @@ def test_caller_stream():
         assert P.nparts == 15
         bd = S.blockDiagonalize(P, False, rand=Coeffs(4))
         assert sorted(bd.blkSizes) == [2, 2, 2, 3]
+
+
+# ---------------------------------------------------------------------------------
+# reduced-SDP assembly (README.md:57-60) and _constraints
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("prob", [pr.lovasz_er(5), pr.qap_esc16j(os.path.join(GOLDEN, "esc16j.npz")),
+                                  pr.synthetic_product_scheme(3, 2, 8)], ids=lambda p: p.name)
+def test_reduce_problem_matches_pmat(prob):
+    import scipy.sparse as sp
+    P = S.admissible_subspace(*prob, rand=Coeffs(4))
+    newA, newB, newC = S.reduce_problem(P, prob.C, prob.A, prob.b)
+    flat = P.matrix.reshape(-1, order="F").astype(np.int64)
+    keep = flat > 0
+    PMat = sp.csr_matrix((np.ones(int(keep.sum())), (np.flatnonzero(keep), flat[keep] - 1)),
+                         shape=(prob.n ** 2, P.nparts))
+    wantA = np.asarray((sp.csr_matrix(prob.A) @ PMat).todense())
+    wantC = np.asarray(PMat.T @ np.asarray(prob.C, dtype=np.float64)).reshape(-1)
+    assert np.allclose(newA, wantA, rtol=1e-13, atol=1e-13)
+    assert np.allclose(newC, wantC, rtol=1e-13, atol=1e-13)
+    assert np.array_equal(newB, prob.b)
+    from sdpsr_b200.api import _constraints
+    cs = _constraints(P)
+    assert sum(len(c) for c in cs) == int(keep.sum())
+    for i in (0, P.nparts - 1):
+        assert np.array_equal(cs[i], np.flatnonzero(flat == i + 1))
+    P.release()
