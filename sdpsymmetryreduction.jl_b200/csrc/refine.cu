@@ -26,10 +26,10 @@
 
 namespace {
 
-constexpr int RT = 256;           // threads per CTA
+constexpr int RT = 768;           // threads per CTA (one CTA per SM shares one key cache)
 constexpr int EPT = 4;            // consecutive entries per thread per tile
 constexpr int TILE = RT * EPT;    // entries per tile
-constexpr int SC = 4096;          // slots of the per-CTA key cache
+constexpr int SC = 8192;          // slots of the per-CTA key cache (128 KB)
 constexpr int SC_LIMIT = SC / 2;      // keys cached per CTA; the rest always go to the global table
 constexpr int CACHE_PROBES = 8;       // linear-probe window of the cache (lookups and inserts)
 constexpr uint32_t PROBE_LIMIT = 4096;
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(RT) refine_kernel(const RefineArgs a) {
 // miss path is out of line.
 // ---------------------------------------------------------------------------
 template <bool WRITEBACK, bool FILLPROJ>
-__global__ void __launch_bounds__(RT, 3) refine_fast_kernel(const RefineArgs a) {
+__global__ void __launch_bounds__(RT, 1) refine_fast_kernel(const RefineArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CacheSlot* cache = reinterpret_cast<CacheSlot*>(smem_raw);
   __shared__ uint32_t s_count;
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(RT, 3) refine_fast_kernel(const RefineArgs a) 
         const bool same = e > 0 && khi[e] == khi[e - 1] && klo[e] == klo[e - 1];
         const bool need = (khi[e] | klo[e]) != 0u && !same;
         uint32_t g = same ? gid[e - 1] : 0u;
-        uint32_t s = (((klo[e] * 0x9e3779b1u) ^ (khi[e] * 0x85ebca77u)) >> 20) & (SC - 1);
+        uint32_t s = (((klo[e] * 0x9e3779b1u) ^ (khi[e] * 0x85ebca77u)) >> 19) & (SC - 1);
         int free_slot = -1;
         if (need && use_cache) {
 #pragma unroll 1
@@ -750,7 +750,7 @@ int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
   if (cap < initial_cap(ctx)) cap = initial_cap(ctx);
   const size_t cap_max = std::max<size_t>(64, next_pow2(2 * (uint64_t)ctx->elems));
   const uint64_t ntiles = (ctx->elems + TILE - 1) / TILE;
-  const int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * 3);
+  const int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count);
 
   for (;;) {
     SDPSR_TRY(sdpsr_table_alloc(ctx, tnew, cap));
