@@ -180,6 +180,20 @@ int sdpsr_set_qhat(sdpsr_ctx* ctx, const double* qhat, const int64_t* blk_sizes,
  * with |entries| < atol clamped to 0.  out_len must be dim * sum(s_k^2).              */
 int sdpsr_basis_image(sdpsr_ctx* ctx, double atol, double* out, int64_t out_len);
 
+/* ---------------------------------------------------------------- complex path
+ * diagonalize(ComplexF64, P) (src/diagonalize.jl:25-40, src/compat.jl:46-68) for partitions that are
+ * not transpose-invariant.  Complex vectors are interleaved (re, im) doubles; `len`/`out_len` count
+ * complex numbers.  Call order and host-side steps are those of the real path; the general
+ * eigensolver is cuSOLVER Xgeev, eigenvalues sorted by (re, im) like Julia's `eigen`.             */
+int sdpsr_eig_complex(sdpsr_ctx* ctx, const double* r1, int64_t len, double* vals /* 2N */);
+int sdpsr_block_norms_complex(sdpsr_ctx* ctx, const double* r2, int64_t len, const int64_t* ptrs,
+                              int64_t nptr, double* norms);
+int sdpsr_irreducible_complex(sdpsr_ctx* ctx, const double* r3, int64_t len, const int64_t* ptrs,
+                              int64_t nptr, const int64_t* kroot, double atol, int64_t* blk_sizes,
+                              int64_t* nblk);
+int sdpsr_get_qhat_complex(sdpsr_ctx* ctx, double* qhat, int64_t len);
+int sdpsr_basis_image_complex(sdpsr_ctx* ctx, double atol, double* out, int64_t out_len);
+
 /* ------------------------------------------------------ reduced SDP assembly
  * The step right after the path (README.md:57-60, test/sd_problems.jl:32-37):
  *   newA = A * PMat  (m x dim, column-major),  newC = C' * PMat  (dim),

@@ -351,10 +351,9 @@ def diagonalize(P: Partition, *, verbose: bool = False, atol: Optional[float] = 
                 rand: Optional[Callable] = None, complex: bool = False,
                 fetch: bool = True, ctx: Optional[B.Context] = None):
     """``diagonalize(Float64, P)`` (src/diagonalize.jl:25-40): list of N x s_k matrices Q_hat."""
-    if complex:
-        raise NotImplementedError(
-            "complex path (SURVEY.md 8(f) rank 1) is not built yet; desymmetrize() is available")
     rand = rand or _default_rand()
+    if complex:
+        return _diagonalize_complex(P, verbose=verbose, atol=atol, rand=rand, fetch=fetch)
     ctx = ctx or P._context()
     n = ctx.n
     if atol is None:
@@ -399,10 +398,9 @@ def blockDiagonalize(P: Partition, verbose: bool = True, *, epsilon: float = RTO
                      complex: bool = False, rand: Optional[Callable] = None):
     """src/compat.jl:26-68.  Returns ``(blkSizes, blks)``; ``blks[i][k]`` is the image of
     the basis element ``P.matrix == i+1`` in block k."""
-    if complex:
-        raise NotImplementedError(
-            "complex path (SURVEY.md 8(f) rank 1) is not built yet; desymmetrize() is available")
     rand = rand or _default_rand()
+    if complex:
+        return _block_diagonalize_complex(P, verbose, epsilon, rand)
     ctx = P._context()
     n = ctx.n
     sizes = diagonalize(P, verbose=verbose, atol=epsilon, rand=rand, fetch=False, ctx=ctx)
@@ -411,6 +409,52 @@ def blockDiagonalize(P: Partition, verbose: bool = True, *, epsilon: float = RTO
     blks = ctx.basis_image(sizes, 1e-12 * n, dim=P.nparts)      # atol default, not epsilon (Appendix C)
     if verbose:
         log.info("Calculating image of the basis of the algebra... %.3fs", time.perf_counter() - t)
+    return BlockDiagonalization([int(s) for s in sizes], blks)
+
+
+# ----------------------------------------------------------------------------
+# complex path: src/diagonalize.jl:25-40 with T = ComplexF64
+# ----------------------------------------------------------------------------
+def _crand(rand):
+    """``rand(ComplexF64, k)``: re and im uniform in [0,1), taken pairwise from ``rand``."""
+    def f(k):
+        z = np.asarray(rand(2 * int(k)), dtype=np.float64)
+        return z[0::2] + 1j * z[1::2]
+    return f
+
+
+def _diagonalize_complex(P: Partition, *, verbose=False, atol=None, rand=None, fetch=True):
+    n = P.matrix.shape[0]
+    if atol is None:
+        atol = 1e-12 * n
+    Pd = desymmetrize(P, verbose=verbose, rand=rand)                 # default atol        (:26-28)
+    ctx = Pd._context()
+    crand = _crand(rand)
+    vals = ctx.eig_complex(crand(Pd.nparts))                         # src/eigen_decomposition.jl:242-254
+    ptrs = eigen_clusters(vals, atol)
+    norms = ctx.block_norms_complex(crand(Pd.nparts), ptrs)          # :259, :203-204
+    kroot = _isomorphism_classes(norms, atol)
+    sizes = ctx.irreducible_complex(crand(Pd.nparts), ptrs, kroot, atol)   # :306, clamptol! src/diagonalize.jl:39
+    Pd._blk_sizes, Pd._ptrs, Pd._kroot = sizes, ptrs, kroot
+    P._complex_partition = Pd
+    if not fetch:
+        return sizes
+    return ctx.get_qhat_complex(sizes)
+
+
+def _block_diagonalize_complex(P: Partition, verbose, epsilon, rand):
+    """``blockDiagonalize(ComplexF64, P)`` (src/compat.jl:46-68)."""
+    sizes = _diagonalize_complex(P, verbose=verbose, atol=epsilon, rand=rand, fetch=False)
+    Pd = P._complex_partition
+    # the reference desymmetrizes once more, with atol = epsilon (src/compat.jl:54-57); both runs
+    # converge to the same canonical partition w.p. 1, and the draws are consumed as there
+    P2 = desymmetrize(P, verbose=verbose, atol=epsilon, rand=rand)
+    check_block_sizes(sizes, P2, True)
+    if P2.nparts != Pd.nparts or not np.array_equal(P2.matrix, Pd.matrix):
+        raise NumericalInconsistency("desymmetrize did not reproduce its own partition; try again")
+    P2.release()
+    n = P.matrix.shape[0]
+    blks = Pd._context().basis_image_complex(sizes, 1e-12 * n, dim=Pd.nparts)
     return BlockDiagonalization([int(s) for s in sizes], blks)
 
 

@@ -74,6 +74,11 @@ _SIGNATURES = {
     "sdpsr_set_qhat": ([_p, _p, _p, _i64], C.c_int),
     "sdpsr_basis_image": ([_p, C.c_double, _p, _i64], C.c_int),
     "sdpsr_reduce_problem": ([_p, _p, _p, _p], C.c_int),
+    "sdpsr_eig_complex": ([_p, _p, _i64, _p], C.c_int),
+    "sdpsr_block_norms_complex": ([_p, _p, _i64, _p, _i64, _p], C.c_int),
+    "sdpsr_irreducible_complex": ([_p, _p, _i64, _p, _i64, _p, C.c_double, _p, C.POINTER(_i64)], C.c_int),
+    "sdpsr_get_qhat_complex": ([_p, _p, _i64], C.c_int),
+    "sdpsr_basis_image_complex": ([_p, C.c_double, _p, _i64], C.c_int),
     "sdpsr_get_matrix": ([_p, C.c_int, _p], C.c_int),
     "sdpsr_set_matrix": ([_p, C.c_int, _p], C.c_int),
     "sdpsr_gemm": ([_p, C.c_int, C.c_int, C.c_int], C.c_int),
@@ -341,6 +346,58 @@ class Context:
         sq = int(sum(int(s) * int(s) for s in sizes))
         out = np.zeros(d * sq, dtype=np.float64)
         self._check(self.lib.sdpsr_basis_image(self._h, float(atol), out.ctypes.data, out.size))
+        blks = []
+        for i in range(d):
+            row, off = [], i * sq
+            for s in sizes:
+                s = int(s)
+                row.append(out[off:off + s * s].reshape(s, s, order="F").copy())
+                off += s * s
+            blks.append(row)
+        return blks
+
+    # -- complex path (interleaved re/im == numpy complex128 memory layout) ----------------------
+    def eig_complex(self, r1) -> np.ndarray:
+        r1 = np.ascontiguousarray(r1, dtype=np.complex128)
+        vals = np.empty(self.n, dtype=np.complex128)
+        self._check(self.lib.sdpsr_eig_complex(self._h, r1.ctypes.data, r1.size, vals.ctypes.data))
+        return vals
+
+    def block_norms_complex(self, r2, ptrs) -> np.ndarray:
+        r2 = np.ascontiguousarray(r2, dtype=np.complex128)
+        ptrs = np.ascontiguousarray(ptrs, dtype=np.int64)
+        ne = ptrs.size - 1
+        norms = np.zeros((ne, ne), dtype=np.float64, order="F")
+        self._check(self.lib.sdpsr_block_norms_complex(self._h, r2.ctypes.data, r2.size, ptrs.ctypes.data, ptrs.size,
+                                                       norms.ctypes.data))
+        return norms
+
+    def irreducible_complex(self, r3, ptrs, kroot, atol: float):
+        r3 = np.ascontiguousarray(r3, dtype=np.complex128)
+        ptrs = np.ascontiguousarray(ptrs, dtype=np.int64)
+        kroot = np.ascontiguousarray(kroot, dtype=np.int64)
+        sizes = np.zeros(ptrs.size - 1, dtype=np.int64)
+        nblk = _i64(0)
+        self._check(self.lib.sdpsr_irreducible_complex(self._h, r3.ctypes.data, r3.size, ptrs.ctypes.data, ptrs.size,
+                                                       kroot.ctypes.data, float(atol), sizes.ctypes.data,
+                                                       C.byref(nblk)))
+        return sizes[:nblk.value].copy()
+
+    def get_qhat_complex(self, sizes) -> list:
+        S = int(np.sum(sizes))
+        buf = np.empty((self.n, S), dtype=np.complex128, order="F")
+        self._check(self.lib.sdpsr_get_qhat_complex(self._h, buf.ctypes.data, buf.size))
+        out, c = [], 0
+        for s in sizes:
+            out.append(np.ascontiguousarray(buf[:, c:c + int(s)]))
+            c += int(s)
+        return out
+
+    def basis_image_complex(self, sizes, atol: float, dim: Optional[int] = None) -> list:
+        d = self.dim() if dim is None else dim
+        sq = int(sum(int(s) * int(s) for s in sizes))
+        out = np.zeros(d * sq, dtype=np.complex128)
+        self._check(self.lib.sdpsr_basis_image_complex(self._h, float(atol), out.ctypes.data, out.size))
         blks = []
         for i in range(d):
             row, off = [], i * sq

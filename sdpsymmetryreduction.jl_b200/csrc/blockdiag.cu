@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict
 
 // norms[i + ne*j] = max |W[a,b]| over a in E_i, b in E_j, for i <= j with equal dimensions.
 // Non-negative doubles order like their bit patterns, so atomicMax on the bits is exact.
-__global__ void __launch_bounds__(256) block_max_kernel(const double* __restrict__ W, int64_t n, int64_t ld,
+__global__ void __launch_bounds__(256) block_max_kernel(const double* __restrict__ W, const double* __restrict__ Wim,
+                                                        int64_t n, int64_t ld,
                                                         const uint32_t* __restrict__ space,
                                                         const uint32_t* __restrict__ sdim, int64_t ne,
                                                         unsigned long long* __restrict__ norms) {
@@ -50,7 +51,8 @@ __global__ void __launch_bounds__(256) block_max_kernel(const double* __restrict
     if (valid) {
       si = space[a];
       if (si <= sj && sdim[si] == sdim[sj])
-        bits = (unsigned long long)__double_as_longlong(fabs(W[a + ld * b]));
+        bits = (unsigned long long)__double_as_longlong(
+            Wim ? hypot(W[a + ld * b], Wim[a + ld * b]) : fabs(W[a + ld * b]));   // abs(::Complex) = hypot
       else
         si = 0xfffffffeu;
     }
@@ -253,6 +255,13 @@ void sdpsr_blockdiag_free(sdpsr_ctx* ctx) {
   cudaFree(ctx->W);
   cudaFree(ctx->T);
   cudaFree(ctx->Qhat);
+  cudaFree(ctx->Xi);
+  cudaFree(ctx->X2i);
+  cudaFree(ctx->Qi);
+  cudaFree(ctx->Wi);
+  cudaFree(ctx->Ti);
+  cudaFree(ctx->Qhat_i);
+  ctx->Xi = ctx->X2i = ctx->Qi = ctx->Wi = ctx->Ti = ctx->Qhat_i = nullptr;
   ctx->solver_work = nullptr;
   ctx->solver_info = nullptr;
   ctx->solver_hwork = nullptr;
@@ -344,6 +353,7 @@ extern "C" int sdpsr_eig(sdpsr_ctx* ctx, const double* r1, int64_t len, double* 
   SDPSR_TRY(finish(ctx));
   SDPSR_REQUIRE(*hinfo == 0, SDPSR_E_CUSOLVER, "syevd did not converge (info = " + std::to_string(*hinfo) + ")");
   ctx->have_Q = true;
+  ctx->q_complex = false;
   return SDPSR_OK;
 }
 
@@ -385,7 +395,7 @@ extern "C" int sdpsr_block_norms(sdpsr_ctx* ctx, const double* r2, int64_t len, 
   {
     Timed tm(ctx, SDPSR_K_MISC, (double)ctx->elems * 8.0);
     block_max_kernel<<<dim3((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)n), 256, 0, ctx->stream>>>(
-        ctx->W, n, ld, d_space, d_sdim, ne, d_norms);
+        ctx->W, nullptr, n, ld, d_space, d_sdim, ne, d_norms);
     count_launch(ctx);
   }
   SDPSR_CUDA(cudaGetLastError());
@@ -664,4 +674,632 @@ extern "C" int sdpsr_basis_image(sdpsr_ctx* ctx, double atol, double* out, int64
   SDPSR_TRY(status);
   SDPSR_CUDA(cudaMemcpy(out, result.data(), result.size() * 8, cudaMemcpyDefault));
   return finish(ctx);
+}
+
+
+// =============================================================================================
+// Complex path: diagonalize(ComplexF64, P) of src/diagonalize.jl:25-40 for
+// partitions that are not transpose-invariant.  Complex matrices are kept as split re/im planes so
+// that every product runs on the real DMMA GEMM (4 real GEMMs with +/- accumulation); the general
+// eigensolver is cuSOLVER Xgeev (library, like syevd on the real path).
+// =============================================================================================
+#include <cuComplex.h>
+
+namespace {
+
+__global__ void interleave_kernel(const double* __restrict__ re, const double* __restrict__ im,
+                                  cuDoubleComplex* __restrict__ z, uint64_t total) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
+    z[i] = make_cuDoubleComplex(re[i], im[i]);
+}
+
+// Q[:, c] = VR[:, order[c]] scaled to unit 2-norm (LAPACK's zgeev convention), split into planes
+__global__ void __launch_bounds__(256) gather_unit_columns_kernel(const cuDoubleComplex* __restrict__ VR, int64_t n,
+                                                                  int64_t ld, const int64_t* __restrict__ order,
+                                                                  double* __restrict__ Qr, double* __restrict__ Qi) {
+  __shared__ double ws[8];
+  __shared__ double inv;
+  const int64_t c = blockIdx.x;
+  const cuDoubleComplex* src = VR + ld * order[c];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += src[i].x * src[i].x + src[i].y * src[i].y;
+  for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += ws[w];
+    inv = t > 0.0 ? 1.0 / sqrt(t) : 0.0;
+  }
+  __syncthreads();
+  for (int64_t i = threadIdx.x; i < ld; i += blockDim.x) {
+    const bool in = i < n;
+    Qr[i + ld * c] = in ? src[i].x * inv : 0.0;
+    Qi[i + ld * c] = in ? src[i].y * inv : 0.0;
+  }
+}
+
+__global__ void scale_kernel(double* __restrict__ x, uint64_t total, double f) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
+    x[i] *= f;
+}
+
+// out[pair*maxm + t] = sum_r conj(Q[r, qcol+t]) * V[r, vcol]      (Q_j^H v)
+__global__ void __launch_bounds__(256) cpair_dot_kernel(const double* __restrict__ Qr, const double* __restrict__ Qi,
+                                                        const double* __restrict__ Vr, const double* __restrict__ Vi,
+                                                        int64_t n, int64_t ld, const int64_t* __restrict__ qcol,
+                                                        const int64_t* __restrict__ vcol,
+                                                        const int64_t* __restrict__ mult, int64_t maxm,
+                                                        double* __restrict__ out_r, double* __restrict__ out_i) {
+  __shared__ double wr[8], wi[8];
+  const int64_t pair = blockIdx.y, t = blockIdx.x;
+  if (t >= mult[pair]) return;
+  const int64_t qc = ld * (qcol[pair] + t), vc = ld * vcol[pair];
+  double sr = 0.0, si = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double ar = Qr[qc + i], ai = Qi[qc + i], br = Vr[vc + i], bi = Vi[vc + i];
+    sr += ar * br + ai * bi;       // conj(a) * b
+    si += ar * bi - ai * br;
+  }
+  for (int o = 16; o; o >>= 1) {
+    sr += __shfl_down_sync(0xffffffffu, sr, o);
+    si += __shfl_down_sync(0xffffffffu, si, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    wr[threadIdx.x >> 5] = sr;
+    wi[threadIdx.x >> 5] = si;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tr = 0.0, ti = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      tr += wr[w];
+      ti += wi[w];
+    }
+    out_r[pair * maxm + t] = tr;
+    out_i[pair * maxm + t] = ti;
+  }
+}
+
+// Qhat[:, dst] = Q[:, qcol .. qcol+mult) * (u / ||w||)
+__global__ void __launch_bounds__(256) cpair_combine_kernel(const double* __restrict__ Qr, const double* __restrict__ Qi,
+                                                            int64_t n, int64_t ld, const int64_t* __restrict__ qcol,
+                                                            const int64_t* __restrict__ mult, int64_t maxm,
+                                                            const double* __restrict__ ur, const double* __restrict__ ui,
+                                                            const double* __restrict__ wr, const double* __restrict__ wi,
+                                                            const int64_t* __restrict__ dst, double* __restrict__ Hr,
+                                                            double* __restrict__ Hi) {
+  const int64_t pair = blockIdx.y;
+  const int64_t mlt = mult[pair];
+  double nrm2 = 0.0;
+  for (int64_t t = 0; t < mlt; ++t)
+    nrm2 += wr[pair * maxm + t] * wr[pair * maxm + t] + wi[pair * maxm + t] * wi[pair * maxm + t];
+  const double inv = 1.0 / sqrt(nrm2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double sr = 0.0, si = 0.0;
+    for (int64_t t = 0; t < mlt; ++t) {
+      const double qr = Qr[i + ld * (qcol[pair] + t)], qi = Qi[i + ld * (qcol[pair] + t)];
+      const double cr = ur[pair * maxm + t] * inv, ci = ui[pair * maxm + t] * inv;
+      sr += qr * cr - qi * ci;
+      si += qr * ci + qi * cr;
+    }
+    Hr[i + ld * dst[pair]] = sr;
+    Hi[i + ld * dst[pair]] = si;
+  }
+}
+
+__global__ void cclamp_kernel(double* __restrict__ xr, double* __restrict__ xi, uint64_t total, double atol) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
+    if (hypot(xr[i], xi[i]) < atol) {
+      xr[i] = 0.0;
+      xi[i] = 0.0;
+    }
+}
+
+// partial[chunk][p] = sum over entries (r,c) of conj(Qt[r][ca[p]]) * Qt[c][cb[p]]   (Q^H B Q)
+__global__ void __launch_bounds__(256) cbasis_partial_kernel(const uint32_t* __restrict__ rows,
+                                                             const uint32_t* __restrict__ cols,
+                                                             const unsigned long long* __restrict__ chunk_beg,
+                                                             const unsigned long long* __restrict__ chunk_end,
+                                                             const double* __restrict__ Qtr, const double* __restrict__ Qti,
+                                                             int64_t S, const int* __restrict__ ca,
+                                                             const int* __restrict__ cb, int npairs,
+                                                             double* __restrict__ part_r, double* __restrict__ part_i) {
+  __shared__ int sa[BI_PAIRS], sb[BI_PAIRS];
+  __shared__ double red[8][BI_PAIRS];
+  if (threadIdx.x < BI_PAIRS) {
+    sa[threadIdx.x] = threadIdx.x < npairs ? ca[threadIdx.x] : 0;
+    sb[threadIdx.x] = threadIdx.x < npairs ? cb[threadIdx.x] : 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned long long e0 = chunk_beg[blockIdx.x], e1 = chunk_end[blockIdx.x];
+  for (int part = 0; part < 2; ++part) {            // real part, then imaginary part (keeps registers low)
+    double acc[BI_PAIRS];
+#pragma unroll
+    for (int p = 0; p < BI_PAIRS; ++p) acc[p] = 0.0;
+    for (unsigned long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+      const int64_t r = rows[e], c = cols[e];
+#pragma unroll
+      for (int p = 0; p < BI_PAIRS; ++p)
+        if (p < npairs) {
+          const double ar = Qtr[S * r + sa[p]], ai = Qti[S * r + sa[p]];
+          const double br = Qtr[S * c + sb[p]], bi = Qti[S * c + sb[p]];
+          acc[p] += part == 0 ? (ar * br + ai * bi) : (ar * bi - ai * br);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < BI_PAIRS; ++p) {
+      double v = acc[p];
+      for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) red[wid][p] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < npairs) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+      (part == 0 ? part_r : part_i)[(int64_t)blockIdx.x * BI_PAIRS + threadIdx.x] = t;
+    }
+    __syncthreads();
+  }
+}
+
+int ensure_planes(sdpsr_ctx* ctx) {
+  SDPSR_TRY(ensure_buffer(ctx, &ctx->Q));
+  SDPSR_TRY(ensure_buffer(ctx, &ctx->W));
+  SDPSR_TRY(ensure_buffer(ctx, &ctx->T));
+  SDPSR_TRY(ensure_buffer(ctx, &ctx->Xi));
+  SDPSR_TRY(ensure_buffer(ctx, &ctx->X2i));
+  SDPSR_TRY(ensure_buffer(ctx, &ctx->Qi));
+  SDPSR_TRY(ensure_buffer(ctx, &ctx->Wi));
+  SDPSR_TRY(ensure_buffer(ctx, &ctx->Ti));
+  return SDPSR_OK;
+}
+
+// fill(S, r) for complex r (interleaved re/im) into two planes
+int cfill_into(sdpsr_ctx* ctx, const double* r, int64_t len, double* dre, double* dim_) {
+  SDPSR_REQUIRE(len == ctx->dim, SDPSR_E_INVALID, "length(values) != dim(P) (src/partitions.jl:69)");
+  SDPSR_REQUIRE(r != nullptr || len == 0, SDPSR_E_INVALID, "coefficient vector is NULL");
+  std::vector<double> re((size_t)len), im((size_t)len);
+  for (int64_t i = 0; i < len; ++i) {
+    re[(size_t)i] = r[2 * i];
+    im[(size_t)i] = r[2 * i + 1];
+  }
+  SDPSR_TRY(sdpsr_upload_values(ctx, re.data(), len));
+  SDPSR_TRY(sdpsr_build_lut(ctx, ctx->d_values, len));
+  SDPSR_TRY(sdpsr_materialize_fill(ctx, dre));
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  SDPSR_TRY(sdpsr_upload_values(ctx, im.data(), len));
+  SDPSR_TRY(sdpsr_build_lut(ctx, ctx->d_values, len));
+  SDPSR_TRY(sdpsr_materialize_fill(ctx, dim_));
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->x_is_fill = false;
+  ctx->x_valid = false;
+  return SDPSR_OK;
+}
+
+// C = A * B for split-plane complex matrices (M = ld rows, K = n): 4 real DMMA GEMMs
+int cgemm(sdpsr_ctx* ctx, const double* Ar, const double* Ai, const double* Br, const double* Bi, double* Cr,
+          double* Ci, int64_t ncols) {
+  const int64_t ld = ctx->ld, n = ctx->n;
+  SDPSR_TRY(sdpsr_gemm_f64(ctx, Ar, ld, Br, ld, Cr, ld, ld, ncols, n, false, false, 0));
+  SDPSR_TRY(sdpsr_gemm_f64(ctx, Ai, ld, Bi, ld, Cr, ld, ld, ncols, n, false, false, -1));
+  SDPSR_TRY(sdpsr_gemm_f64(ctx, Ar, ld, Bi, ld, Ci, ld, ld, ncols, n, false, false, 0));
+  SDPSR_TRY(sdpsr_gemm_f64(ctx, Ai, ld, Br, ld, Ci, ld, ld, ncols, n, false, false, +1));
+  return SDPSR_OK;
+}
+
+// (Or, Oi) = (Ir, Ii)^H
+int cadjoint(sdpsr_ctx* ctx, const double* Ir, const double* Ii, double* Or, double* Oi) {
+  const int64_t n = ctx->n, ld = ctx->ld;
+  const unsigned nb = (unsigned)((n + 31) / 32);
+  if (ld != n) {
+    SDPSR_CUDA(cudaMemsetAsync(Or, 0, ctx->elems * 8, ctx->stream));
+    SDPSR_CUDA(cudaMemsetAsync(Oi, 0, ctx->elems * 8, ctx->stream));
+  }
+  transpose_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(Ir, Or, n, ld);
+  transpose_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(Ii, Oi, n, ld);
+  const int grid = (int)std::min<uint64_t>((ctx->elems + 255) / 256, (uint64_t)ctx->sm_count * 8);
+  scale_kernel<<<grid, 256, 0, ctx->stream>>>(Oi, ctx->elems, -1.0);
+  count_launch(ctx, 3);
+  SDPSR_CUDA(cudaGetLastError());
+  return SDPSR_OK;
+}
+
+}  // namespace
+
+// A = fill(S, r1) (complex); (vals, Q) = eigen(A), values sorted by (re, im) like Julia's eigsortby
+extern "C" int sdpsr_eig_complex(sdpsr_ctx* ctx, const double* r1, int64_t len, double* vals) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(vals != nullptr, SDPSR_E_INVALID, "vals is NULL");
+  SDPSR_REQUIRE(ctx->nranks == 1, SDPSR_E_UNSUPPORTED, "the complex path is single-GPU");
+  SDPSR_TRY(ensure_planes(ctx));
+  const int64_t n = ctx->n, ld = ctx->ld;
+  SDPSR_TRY(cfill_into(ctx, r1, len, ctx->X, ctx->Xi));
+  if (!ctx->solver) {
+    Solver* s = new Solver();
+    ctx->solver = s;
+    SDPSR_REQUIRE(cusolverDnCreate(&s->h) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER, "cusolverDnCreate failed");
+    SDPSR_REQUIRE(cusolverDnSetStream(s->h, ctx->stream) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
+                  "cusolverDnSetStream failed");
+    SDPSR_REQUIRE(cusolverDnCreateParams(&s->params) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
+                  "cusolverDnCreateParams failed");
+    SDPSR_CUDA(cudaMalloc(&s->d_vals, (size_t)ctx->n * sizeof(double)));
+    SDPSR_CUDA(cudaMalloc(&ctx->solver_info, sizeof(int)));
+  }
+  Solver* s = reinterpret_cast<Solver*>(ctx->solver);
+  cuDoubleComplex *Az = nullptr, *VR = nullptr, *Wz = nullptr;
+  void* dwork = nullptr;
+  void* hwork = nullptr;
+  int64_t* d_order = nullptr;
+  int status = SDPSR_OK;
+  auto cleanup = [&]() {
+    cudaFree(Az);
+    cudaFree(VR);
+    cudaFree(Wz);
+    cudaFree(dwork);
+    cudaFree(d_order);
+    free(hwork);
+  };
+  do {
+    if (cudaMalloc(&Az, ctx->elems * 16) != cudaSuccess || cudaMalloc(&VR, ctx->elems * 16) != cudaSuccess ||
+        cudaMalloc(&Wz, (size_t)n * 16) != cudaSuccess || cudaMalloc(&d_order, (size_t)n * 8) != cudaSuccess) {
+      status = ctx->fail(SDPSR_E_ALLOC, "complex eigensolver buffers");
+      break;
+    }
+    const int grid = (int)std::min<uint64_t>((ctx->elems + 255) / 256, (uint64_t)ctx->sm_count * 8);
+    interleave_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->X, ctx->Xi, Az, ctx->elems);
+    count_launch(ctx);
+    size_t wd = 0, wh = 0;
+    if (cusolverDnXgeev_bufferSize(s->h, s->params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_VECTOR, n, CUDA_C_64F,
+                                   Az, ld, CUDA_C_64F, Wz, CUDA_C_64F, nullptr, ld, CUDA_C_64F, VR, ld, CUDA_C_64F, &wd,
+                                   &wh) != CUSOLVER_STATUS_SUCCESS) {
+      status = ctx->fail(SDPSR_E_CUSOLVER, "cusolverDnXgeev_bufferSize failed");
+      break;
+    }
+    if (cudaMalloc(&dwork, std::max<size_t>(wd, 16)) != cudaSuccess) {
+      status = ctx->fail(SDPSR_E_ALLOC, "geev workspace");
+      break;
+    }
+    hwork = malloc(std::max<size_t>(wh, 16));
+    cusolverStatus_t st;
+    {
+      Timed tm(ctx, SDPSR_K_EIG, 0.0);
+      st = cusolverDnXgeev(s->h, s->params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_VECTOR, n, CUDA_C_64F, Az, ld,
+                           CUDA_C_64F, Wz, CUDA_C_64F, nullptr, ld, CUDA_C_64F, VR, ld, CUDA_C_64F, dwork, wd, hwork, wh,
+                           ctx->solver_info);
+    }
+    if (st != CUSOLVER_STATUS_SUCCESS) {
+      status = ctx->fail(SDPSR_E_CUSOLVER, "cusolverDnXgeev failed (status " + std::to_string((int)st) + ")");
+      break;
+    }
+    std::vector<double> w((size_t)2 * n);
+    int hinfo = 0;
+    cudaMemcpyAsync(w.data(), Wz, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(&hinfo, ctx->solver_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      status = ctx->fail(SDPSR_E_CUDA, "geev synchronisation failed");
+      break;
+    }
+    if (hinfo != 0) {
+      status = ctx->fail(SDPSR_E_CUSOLVER, "geev did not converge (info = " + std::to_string(hinfo) + ")");
+      break;
+    }
+    std::vector<int64_t> order((size_t)n);
+    for (int64_t i = 0; i < n; ++i) order[(size_t)i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+      if (w[2 * a] != w[2 * b]) return w[2 * a] < w[2 * b];
+      return w[2 * a + 1] < w[2 * b + 1];
+    });
+    for (int64_t i = 0; i < n; ++i) {
+      vals[2 * i] = w[2 * (size_t)order[(size_t)i]];
+      vals[2 * i + 1] = w[2 * (size_t)order[(size_t)i] + 1];
+    }
+    cudaMemcpyAsync(d_order, order.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    gather_unit_columns_kernel<<<(unsigned)n, 256, 0, ctx->stream>>>(VR, n, ld, d_order, ctx->Q, ctx->Qi);
+    count_launch(ctx);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+      status = ctx->fail(SDPSR_E_CUDA, "eigenvector gather failed");
+  } while (0);
+  cleanup();
+  SDPSR_TRY(status);
+  ctx->have_Q = true;
+  ctx->q_complex = true;
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_block_norms_complex(sdpsr_ctx* ctx, const double* r2, int64_t len, const int64_t* ptrs,
+                                         int64_t nptr, double* norms) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(ctx->have_Q && ctx->q_complex, SDPSR_E_STATE, "sdpsr_block_norms_complex must follow sdpsr_eig_complex");
+  SDPSR_REQUIRE(ptrs && nptr >= 2 && norms, SDPSR_E_INVALID, "bad eigenspace pointers");
+  const int64_t ne = nptr - 1, n = ctx->n, ld = ctx->ld;
+  SDPSR_REQUIRE(ptrs[0] == 0 && ptrs[ne] == n, SDPSR_E_INVALID, "ptrs must run from 0 to N");
+  std::vector<uint32_t> space((size_t)n), sdim((size_t)ne);
+  for (int64_t e = 0; e < ne; ++e) {
+    SDPSR_REQUIRE(ptrs[e + 1] > ptrs[e], SDPSR_E_INVALID, "ptrs must be strictly increasing");
+    sdim[(size_t)e] = (uint32_t)(ptrs[e + 1] - ptrs[e]);
+    for (int64_t a = ptrs[e]; a < ptrs[e + 1]; ++a) space[(size_t)a] = (uint32_t)e;
+  }
+  SDPSR_TRY(cfill_into(ctx, r2, len, ctx->X, ctx->Xi));                          // A2
+  SDPSR_TRY(cgemm(ctx, ctx->X, ctx->Xi, ctx->Q, ctx->Qi, ctx->T, ctx->Ti, n));   // T = A2 Q
+  SDPSR_TRY(cadjoint(ctx, ctx->Q, ctx->Qi, ctx->X2, ctx->X2i));                  // Q'
+  SDPSR_TRY(cgemm(ctx, ctx->X2, ctx->X2i, ctx->T, ctx->Ti, ctx->W, ctx->Wi, n)); // W = Q' T
+  uint32_t *d_space = nullptr, *d_sdim = nullptr;
+  unsigned long long* d_norms = nullptr;
+  SDPSR_CUDA(cudaMalloc(&d_space, (size_t)n * 4));
+  SDPSR_CUDA(cudaMalloc(&d_sdim, (size_t)ne * 4));
+  SDPSR_CUDA(cudaMalloc(&d_norms, (size_t)ne * ne * 8));
+  SDPSR_CUDA(cudaMemcpyAsync(d_space, space.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  SDPSR_CUDA(cudaMemcpyAsync(d_sdim, sdim.data(), (size_t)ne * 4, cudaMemcpyHostToDevice, ctx->stream));
+  SDPSR_CUDA(cudaMemsetAsync(d_norms, 0, (size_t)ne * ne * 8, ctx->stream));
+  block_max_kernel<<<dim3((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)n), 256, 0, ctx->stream>>>(
+      ctx->W, ctx->Wi, n, ld, d_space, d_sdim, ne, d_norms);
+  count_launch(ctx);
+  SDPSR_CUDA(cudaGetLastError());
+  SDPSR_CUDA(cudaMemcpyAsync(norms, d_norms, (size_t)ne * ne * 8, cudaMemcpyDefault, ctx->stream));
+  int st = finish(ctx);
+  cudaFree(d_space);
+  cudaFree(d_sdim);
+  cudaFree(d_norms);
+  SDPSR_TRY(st);
+  for (int64_t j = 0; j < ne; ++j)
+    for (int64_t i = 0; i < j; ++i) norms[j + ne * i] = norms[i + ne * j];
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_irreducible_complex(sdpsr_ctx* ctx, const double* r3, int64_t len, const int64_t* ptrs,
+                                         int64_t nptr, const int64_t* kroot, double atol, int64_t* blk_sizes,
+                                         int64_t* nblk) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(ctx->have_Q && ctx->q_complex, SDPSR_E_STATE, "sdpsr_irreducible_complex must follow sdpsr_eig_complex");
+  SDPSR_REQUIRE(ptrs && nptr >= 2 && kroot && blk_sizes && nblk, SDPSR_E_INVALID, "bad arguments");
+  const int64_t ne = nptr - 1, n = ctx->n, ld = ctx->ld;
+  std::vector<std::vector<int64_t>> classes;
+  std::vector<int64_t> class_of((size_t)ne, -1);
+  for (int64_t e = 0; e < ne; ++e) {
+    const int64_t r = kroot[e];
+    SDPSR_REQUIRE(r >= 0 && r <= e && kroot[r] == r, SDPSR_E_INVALID, "kroot[e] must be the smallest member of its class");
+    if (r == e) {
+      class_of[(size_t)e] = (int64_t)classes.size();
+      classes.emplace_back();
+    }
+    classes[(size_t)class_of[(size_t)r]].push_back(e);
+    class_of[(size_t)e] = class_of[(size_t)r];
+  }
+  int64_t S = 0;
+  for (auto& k : classes) S += (int64_t)k.size();
+  cudaFree(ctx->Qhat);
+  cudaFree(ctx->Qhat_i);
+  ctx->Qhat = ctx->Qhat_i = nullptr;
+  SDPSR_CUDA(cudaMalloc(&ctx->Qhat, (size_t)ld * (size_t)S * 8));
+  SDPSR_CUDA(cudaMalloc(&ctx->Qhat_i, (size_t)ld * (size_t)S * 8));
+  SDPSR_CUDA(cudaMemsetAsync(ctx->Qhat, 0, (size_t)ld * (size_t)S * 8, ctx->stream));
+  SDPSR_CUDA(cudaMemsetAsync(ctx->Qhat_i, 0, (size_t)ld * (size_t)S * 8, ctx->stream));
+  ctx->qhat_cols = S;
+  ctx->blk_sizes.clear();
+  std::vector<int64_t> fcols, findex((size_t)ne, -1);
+  struct Pair { int64_t i, j, dst; };
+  std::vector<Pair> pairs;
+  int64_t col = 0;
+  for (auto& k : classes) {
+    ctx->blk_sizes.push_back((int64_t)k.size());
+    SDPSR_CUDA(cudaMemcpyAsync(ctx->Qhat + ld * col, ctx->Q + ld * ptrs[k[0]], (size_t)ld * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    SDPSR_CUDA(cudaMemcpyAsync(ctx->Qhat_i + ld * col, ctx->Qi + ld * ptrs[k[0]], (size_t)ld * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (k.size() > 1) {
+      for (int64_t e : k)
+        if (findex[(size_t)e] < 0) {
+          findex[(size_t)e] = (int64_t)fcols.size();
+          fcols.push_back(ptrs[e]);
+        }
+      for (size_t t = 1; t < k.size(); ++t) {
+        SDPSR_REQUIRE(ptrs[k[t] + 1] - ptrs[k[t]] == ptrs[k[0] + 1] - ptrs[k[0]], SDPSR_E_INVALID,
+                      "isomorphic eigenspaces must have equal dimension");
+        pairs.push_back(Pair{k[0], k[t], col + (int64_t)t});
+      }
+    }
+    col += (int64_t)k.size();
+  }
+  *nblk = (int64_t)classes.size();
+  for (size_t k = 0; k < classes.size(); ++k) blk_sizes[k] = ctx->blk_sizes[k];
+  SDPSR_REQUIRE(len == ctx->dim, SDPSR_E_INVALID, "length(values) != dim(P) (src/partitions.jl:69)");
+  if (!pairs.empty()) {
+    const int64_t nf = (int64_t)fcols.size(), np = (int64_t)pairs.size();
+    SDPSR_REQUIRE(np <= 65535, SDPSR_E_UNSUPPORTED, "more than 65535 isomorphic eigenspace pairs");
+    SDPSR_TRY(cfill_into(ctx, r3, len, ctx->X, ctx->Xi));                      // A3
+    int64_t* d_fcols = nullptr;
+    SDPSR_CUDA(cudaMalloc(&d_fcols, (size_t)nf * 8));
+    SDPSR_CUDA(cudaMemcpyAsync(d_fcols, fcols.data(), (size_t)nf * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const dim3 gg((unsigned)std::min<int64_t>((ld + 255) / 256, 64), (unsigned)nf);
+    gather_cols_kernel<<<gg, 256, 0, ctx->stream>>>(ctx->Q, ld, d_fcols, ctx->W);       // F (re)
+    gather_cols_kernel<<<gg, 256, 0, ctx->stream>>>(ctx->Qi, ld, d_fcols, ctx->Wi);     // F (im)
+    count_launch(ctx, 2);
+    // V = A3 F (into T) ; V' = A3^H F (into Q'-scratch X2 after forming A3^H in place of A3)
+    SDPSR_TRY(cgemm(ctx, ctx->X, ctx->Xi, ctx->W, ctx->Wi, ctx->T, ctx->Ti, nf));
+    double *Vpr = nullptr, *Vpi = nullptr, *Ahr = nullptr, *Ahi = nullptr;
+    SDPSR_CUDA(cudaMalloc(&Vpr, ctx->elems * 8));
+    SDPSR_CUDA(cudaMalloc(&Vpi, ctx->elems * 8));
+    Ahr = ctx->X2;
+    Ahi = ctx->X2i;
+    SDPSR_TRY(cadjoint(ctx, ctx->X, ctx->Xi, Ahr, Ahi));
+    SDPSR_TRY(cgemm(ctx, Ahr, Ahi, ctx->W, ctx->Wi, Vpr, Vpi, nf));
+    int64_t maxm = 1;
+    std::vector<int64_t> h((size_t)np * 6);
+    for (int64_t p = 0; p < np; ++p) {
+      const Pair& pr = pairs[(size_t)p];
+      const int64_t mlt = ptrs[pr.i + 1] - ptrs[pr.i];
+      maxm = std::max(maxm, mlt);
+      h[(size_t)p] = ptrs[pr.j];                        // Q_j for u
+      h[(size_t)(np + p)] = findex[(size_t)pr.i];       // A3^H q_i1
+      h[(size_t)(2 * np + p)] = ptrs[pr.i];             // Q_i for w
+      h[(size_t)(3 * np + p)] = findex[(size_t)pr.j];   // A3 q_j1
+      h[(size_t)(4 * np + p)] = mlt;
+      h[(size_t)(5 * np + p)] = pr.dst;
+    }
+    int64_t* d_h = nullptr;
+    double* d_uw = nullptr;
+    SDPSR_CUDA(cudaMalloc(&d_h, h.size() * 8));
+    SDPSR_CUDA(cudaMalloc(&d_uw, (size_t)np * (size_t)maxm * 4 * 8));
+    SDPSR_CUDA(cudaMemcpyAsync(d_h, h.data(), h.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    double* ur = d_uw;
+    double* ui = ur + np * maxm;
+    double* wr = ui + np * maxm;
+    double* wi = wr + np * maxm;
+    cpair_dot_kernel<<<dim3((unsigned)maxm, (unsigned)np), 256, 0, ctx->stream>>>(ctx->Q, ctx->Qi, Vpr, Vpi, n, ld, d_h,
+                                                                                   d_h + np, d_h + 4 * np, maxm, ur, ui);
+    cpair_dot_kernel<<<dim3((unsigned)maxm, (unsigned)np), 256, 0, ctx->stream>>>(
+        ctx->Q, ctx->Qi, ctx->T, ctx->Ti, n, ld, d_h + 2 * np, d_h + 3 * np, d_h + 4 * np, maxm, wr, wi);
+    cpair_combine_kernel<<<dim3((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)np), 256, 0, ctx->stream>>>(
+        ctx->Q, ctx->Qi, n, ld, d_h, d_h + 4 * np, maxm, ur, ui, wr, wi, d_h + 5 * np, ctx->Qhat, ctx->Qhat_i);
+    count_launch(ctx, 3);
+    SDPSR_CUDA(cudaGetLastError());
+    SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_h);
+    cudaFree(d_uw);
+    cudaFree(d_fcols);
+    cudaFree(Vpr);
+    cudaFree(Vpi);
+  }
+  {
+    const uint64_t total = (uint64_t)ld * (uint64_t)S;
+    const int grid = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    cclamp_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->Qhat, ctx->Qhat_i, total, atol);
+    count_launch(ctx);
+  }
+  return finish(ctx);
+}
+
+// out: interleaved complex, packed [i][k] s_k x s_k column-major; out_len counts complex numbers
+extern "C" int sdpsr_basis_image_complex(sdpsr_ctx* ctx, double atol, double* out, int64_t out_len) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(ctx->Qhat && ctx->Qhat_i && out, SDPSR_E_STATE, "no complex Qhat (call sdpsr_irreducible_complex first)");
+  const int64_t n = ctx->n, ld = ctx->ld, S = ctx->qhat_cols, d = ctx->dim;
+  int64_t Sq = 0;
+  for (int64_t s : ctx->blk_sizes) Sq += s * s;
+  SDPSR_REQUIRE(out_len == d * Sq, SDPSR_E_INVALID, "out_len must be dim * sum(s_k^2)");
+  if (d == 0) return SDPSR_OK;
+  KeyTable& t = ctx->tab[ctx->cur];
+  unsigned long long* d_cnt = nullptr;
+  SDPSR_CUDA(cudaMalloc(&d_cnt, ((size_t)d + 2) * 8));
+  SDPSR_CUDA(cudaMemsetAsync(d_cnt, 0, ((size_t)d + 2) * 8, ctx->stream));
+  const dim3 g2((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)n);
+  class_count_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->labels, t.rank, n, ld, d_cnt);
+  std::vector<unsigned long long> cnt((size_t)d + 2);
+  SDPSR_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, cnt.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<unsigned long long> start((size_t)d + 2, 0);
+  for (int64_t i = 1; i <= d; ++i) start[(size_t)i + 1] = start[(size_t)i] + cnt[(size_t)i];
+  const unsigned long long nent = start[(size_t)d + 1];
+  SDPSR_CUDA(cudaMemcpyAsync(d_cnt, start.data(), start.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  uint32_t* d_rc = nullptr;
+  SDPSR_CUDA(cudaMalloc(&d_rc, std::max<size_t>(1, (size_t)nent) * 8));
+  uint32_t* d_rows = d_rc;
+  uint32_t* d_cols = d_rc + nent;
+  class_scatter_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->labels, t.rank, n, ld, d_cnt, d_rows, d_cols);
+  count_launch(ctx, 2);
+  std::vector<unsigned long long> cbeg, cend;
+  std::vector<int64_t> cstart((size_t)d + 2, 0);
+  for (int64_t i = 1; i <= d; ++i) {
+    cstart[(size_t)i] = (int64_t)cbeg.size();
+    for (unsigned long long e = start[(size_t)i]; e < start[(size_t)i + 1]; e += BI_CHUNK) {
+      cbeg.push_back(e);
+      cend.push_back(std::min<unsigned long long>(e + BI_CHUNK, start[(size_t)i + 1]));
+    }
+  }
+  cstart[(size_t)d + 1] = (int64_t)cbeg.size();
+  const int64_t nchunks = (int64_t)cbeg.size();
+  unsigned long long* d_cb = nullptr;
+  double *d_part = nullptr, *d_qtr = nullptr, *d_qti = nullptr;
+  int* d_pairs = nullptr;
+  SDPSR_CUDA(cudaMalloc(&d_cb, std::max<size_t>(1, (size_t)nchunks) * 16));
+  SDPSR_CUDA(cudaMalloc(&d_part, std::max<size_t>(1, (size_t)nchunks) * BI_PAIRS * 16));
+  SDPSR_CUDA(cudaMalloc(&d_qtr, (size_t)n * (size_t)S * 8));
+  SDPSR_CUDA(cudaMalloc(&d_qti, (size_t)n * (size_t)S * 8));
+  SDPSR_CUDA(cudaMalloc(&d_pairs, 2 * BI_PAIRS * sizeof(int)));
+  SDPSR_CUDA(cudaMemcpyAsync(d_cb, cbeg.data(), (size_t)nchunks * 8, cudaMemcpyHostToDevice, ctx->stream));
+  SDPSR_CUDA(cudaMemcpyAsync(d_cb + nchunks, cend.data(), (size_t)nchunks * 8, cudaMemcpyHostToDevice, ctx->stream));
+  const dim3 gq((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)S);
+  qhat_rowmajor_kernel<<<gq, 256, 0, ctx->stream>>>(ctx->Qhat, n, ld, S, d_qtr);
+  qhat_rowmajor_kernel<<<gq, 256, 0, ctx->stream>>>(ctx->Qhat_i, n, ld, S, d_qti);
+  count_launch(ctx, 2);
+  std::vector<int> pa, pb;
+  std::vector<int64_t> poff;
+  {
+    int64_t colbase = 0, off = 0;
+    for (int64_t s : ctx->blk_sizes) {
+      for (int64_t b = 0; b < s; ++b)
+        for (int64_t a = 0; a < s; ++a) {
+          pa.push_back((int)(colbase + a));
+          pb.push_back((int)(colbase + b));
+          poff.push_back(off + a + s * b);
+        }
+      colbase += s;
+      off += s * s;
+    }
+  }
+  const size_t pstride = (size_t)std::max<int64_t>(1, nchunks) * BI_PAIRS;
+  std::vector<double> part(2 * pstride);
+  std::vector<double> result((size_t)(2 * d * Sq), 0.0);
+  int status = SDPSR_OK;
+  for (size_t p0 = 0; p0 < pa.size() && status == SDPSR_OK; p0 += BI_PAIRS) {
+    const int np = (int)std::min<size_t>(BI_PAIRS, pa.size() - p0);
+    int hp[2 * BI_PAIRS] = {0};
+    for (int p = 0; p < np; ++p) {
+      hp[p] = pa[p0 + p];
+      hp[BI_PAIRS + p] = pb[p0 + p];
+    }
+    cudaMemcpyAsync(d_pairs, hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream);
+    if (nchunks) {
+      cbasis_partial_kernel<<<(unsigned)nchunks, 256, 0, ctx->stream>>>(d_rows, d_cols, d_cb, d_cb + nchunks, d_qtr, d_qti,
+                                                                       S, d_pairs, d_pairs + BI_PAIRS, np, d_part,
+                                                                       d_part + pstride);
+      count_launch(ctx);
+    }
+    cudaMemcpyAsync(part.data(), d_part, 2 * pstride * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      status = ctx->fail(SDPSR_E_CUDA, "complex basis_image kernel failed");
+      break;
+    }
+    for (int64_t i = 1; i <= d; ++i)
+      for (int p = 0; p < np; ++p) {
+        double sr = 0.0, si = 0.0;
+        for (int64_t c = cstart[(size_t)i]; c < cstart[(size_t)i + 1]; ++c) {
+          sr += part[(size_t)c * BI_PAIRS + p];
+          si += part[pstride + (size_t)c * BI_PAIRS + p];
+        }
+        if (std::hypot(sr, si) < atol) sr = si = 0.0;
+        const size_t o = (size_t)((i - 1) * Sq + poff[p0 + p]);
+        result[2 * o] = sr;
+        result[2 * o + 1] = si;
+      }
+  }
+  cudaFree(d_cnt);
+  cudaFree(d_rc);
+  cudaFree(d_cb);
+  cudaFree(d_part);
+  cudaFree(d_qtr);
+  cudaFree(d_qti);
+  cudaFree(d_pairs);
+  SDPSR_TRY(status);
+  SDPSR_CUDA(cudaMemcpy(out, result.data(), result.size() * 8, cudaMemcpyDefault));
+  return finish(ctx);
+}
+
+// interleaved complex N x S (column-major)
+extern "C" int sdpsr_get_qhat_complex(sdpsr_ctx* ctx, double* qhat, int64_t len) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(ctx->Qhat && ctx->Qhat_i && qhat, SDPSR_E_STATE, "no complex Qhat");
+  SDPSR_REQUIRE(len == ctx->n * ctx->qhat_cols, SDPSR_E_INVALID, "len must be N * sum(blk_sizes) complex numbers");
+  const size_t cnt = (size_t)ctx->n * (size_t)ctx->qhat_cols;
+  std::vector<double> re(cnt), im(cnt);
+  SDPSR_CUDA(cudaMemcpy2DAsync(re.data(), (size_t)ctx->n * 8, ctx->Qhat, (size_t)ctx->ld * 8, (size_t)ctx->n * 8,
+                               (size_t)ctx->qhat_cols, cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_CUDA(cudaMemcpy2DAsync(im.data(), (size_t)ctx->n * 8, ctx->Qhat_i, (size_t)ctx->ld * 8, (size_t)ctx->n * 8,
+                               (size_t)ctx->qhat_cols, cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_TRY(finish(ctx));
+  for (size_t i = 0; i < cnt; ++i) {
+    qhat[2 * i] = re[i];
+    qhat[2 * i + 1] = im[i];
+  }
+  return SDPSR_OK;
 }

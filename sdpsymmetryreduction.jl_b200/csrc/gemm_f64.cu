@@ -86,7 +86,7 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 double* __restrict__ C, int64_t ldc, int M, int Nc, int K, int tiles_m, int tiles_n, int lower,
-                const int2* __restrict__ tile_list) {
+                const int2* __restrict__ tile_list, int accum) {
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;       // SWIZZLE_128B atoms are 1 KB
   const uint32_t bar_full = base + STAGES * STAGE_BYTES;
@@ -215,7 +215,11 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int c = 0; c < 2; ++c) {
         const int nslot = 2 * kk + c;
         const int n = n0 + wn * 32 + j * 8 + (nslot & 3) * 2 + (nslot >> 2);
-        if (m < M && n < Nc) C[(int64_t)m + ldc * (int64_t)n] = acc[i][j][c];
+        if (m < M && n < Nc) {
+          double* dst = C + (int64_t)m + ldc * (int64_t)n;
+          // accum: 0 -> C = A*B, +1 -> C += A*B, -1 -> C -= A*B (complex products from real GEMMs)
+          *dst = accum == 0 ? acc[i][j][c] : (accum > 0 ? *dst + acc[i][j][c] : *dst - acc[i][j][c]);
+        }
       }
     }
   }
@@ -283,7 +287,7 @@ static void owned_tiles(int tiles_m, int tiles_n, bool lower, int nranks, int ra
 }
 
 int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
-                   int64_t ldc, int64_t M, int64_t Nc, int64_t K, bool symmetric_out, bool shard) {
+                   int64_t ldc, int64_t M, int64_t Nc, int64_t K, bool symmetric_out, bool shard, int accum) {
   SDPSR_REQUIRE(M > 0 && Nc > 0 && K > 0, SDPSR_E_INVALID, "empty GEMM");
   SDPSR_REQUIRE(lda % 2 == 0 && ldb % 2 == 0, SDPSR_E_INVALID, "leading dimensions must be even (16-byte TMA strides)");
   SDPSR_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0), SDPSR_E_INVALID, "operands must be 16-byte aligned");
@@ -299,7 +303,7 @@ int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B
   SDPSR_TRY(make_map(ctx, &tmB, B, K, Nc, ldb, BK, BN));
   const int tiles_m = (int)((M + BM - 1) / BM);
   const int tiles_n = (int)((Nc + BN - 1) / BN);
-  const bool lower = symmetric_out && M >= Nc && tiles_m == tiles_n;
+  const bool lower = symmetric_out && accum == 0 && M >= Nc && tiles_m == tiles_n;
   int64_t ntiles = lower ? (int64_t)tiles_m * (tiles_m + 1) / 2 : (int64_t)tiles_m * tiles_n;
   const bool sharded = shard && ctx->nranks > 1;
   const int2* d_tiles = nullptr;
@@ -323,7 +327,7 @@ int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B
                                                    : 2.0 * (double)M * (double)Nc * (double)K);
     if (ntiles) {
       gemm_f64_kernel<<<(unsigned)ntiles, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, C, ldc, (int)M, (int)Nc, (int)K,
-                                                                             tiles_m, tiles_n, lower ? 1 : 0, d_tiles);
+                                                                             tiles_m, tiles_n, lower ? 1 : 0, d_tiles, accum);
       count_launch(ctx);
     }
   }

@@ -108,6 +108,13 @@ struct sdpsr_ctx {
   double* Q = nullptr;   // lazily allocated (blockDiagonalize)
   double* W = nullptr;
   double* T = nullptr;   // scratch N x N (Q', products)
+  double* Xi = nullptr;  // imaginary planes (complex path only, lazily allocated)
+  double* X2i = nullptr;
+  double* Qi = nullptr;
+  double* Wi = nullptr;
+  double* Ti = nullptr;
+  double* Qhat_i = nullptr;
+  bool q_complex = false;
   double* Qhat = nullptr;
   int64_t qhat_cols = 0;
   std::vector<int64_t> blk_sizes;
@@ -224,7 +231,7 @@ int sdpsr_upload_values(sdpsr_ctx* ctx, const double* values, int64_t len);
 // gemm_f64.cu :  C[M x Nc] = A[M x K] * B[K x Nc], all column-major with the given lds
 int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t ldb,
                    double* C, int64_t ldc, int64_t M, int64_t Nc, int64_t K, bool symmetric_out,
-                   bool shard = false);
+                   bool shard = false, int accum = 0);
 
 // project.cu
 int sdpsr_constraints_finalize(sdpsr_ctx* ctx);

@@ -422,3 +422,66 @@ def test_reduce_problem_matches_pmat(prob):
     for i in (0, P.nparts - 1):
         assert np.array_equal(cs[i], np.flatnonzero(flat == i + 1))
     P.release()
+
+
+# ---------------------------------------------------------------------------------
+# complex path (test/runtests.jl:43-57)
+# ---------------------------------------------------------------------------------
+def test_complex_path_sizes_and_characters(vec):
+    c4 = vec["circulant4"]
+    P = S.Partition(c4["nparts"], np.array(c4["matrix"], dtype=np.uint32))
+    X = S.randomize(P, Coeffs(1))
+    assert np.array_equal(X, X.T)                                   # :45
+    bd = S.blockDiagonalize(P, True, complex=True, rand=Coeffs(2))
+    assert bd.blkSizes == c4["complex_blkSizes"]                    # :47
+    P3 = S.Partition(np.array(vec["C3"]["matrix"]))
+    bd = S.blockDiagonalize(P3, False, complex=True, rand=Coeffs(4))
+    assert bd.blkSizes == vec["C3"]["complex_blkSizes"]            # :57
+    # the images of the cyclic shifts are the characters of Z_3: cube roots of unity
+    for k in range(3):
+        chars = np.array([bd.blks[i][k][0, 0] for i in range(3)])
+        assert np.allclose(np.abs(chars), 1.0, atol=1e-10)
+        assert np.allclose(chars ** 3, 1.0, atol=1e-9)
+    cols = sorted(tuple(np.round(np.angle([bd.blks[i][k][0, 0] for i in range(3)]) / (2 * np.pi / 3)).astype(int) % 3)
+                  for k in range(3))
+    assert len(set(cols)) == 3                                       # three distinct characters
+    so, _ = O.blockDiagonalize(O.partition_from_values(np.array(vec["C3"]["matrix"])), Coeffs(4), complex=True)
+    assert list(so) == bd.blkSizes
+
+
+def s3_regular_labels():
+    import itertools
+    perms = list(itertools.permutations(range(3)))
+    idx = {p: i for i, p in enumerate(perms)}
+    comp = lambda p, q: tuple(p[q[i]] for i in range(3))
+    inv = lambda p: tuple(sorted(range(3), key=lambda i: p[i]))
+    L = np.zeros((6, 6), dtype=np.int64)
+    for a in perms:
+        for b in perms:
+            L[idx[a], idx[b]] = idx[comp(inv(a), b)] + 1       # class of (a,b) = a^-1 b
+    return L
+
+
+def test_complex_path_on_noncommutative_algebra():
+    """The group algebra of S3 in its regular representation (6 classes, irreps 1 + 1 + 2x2):
+    complex block sizes [1, 1, 2].  The 1x1 blocks must be characters (multiplicative); the 2x2
+    block of the reference's construction is built from non-orthogonal eigenvectors of a non-normal
+    element and is not multiplicative in the reference either (the oracle shows the same), so only
+    its size is pinned."""
+    L = s3_regular_labels()
+    P = S.Partition(L)
+    assert P.nparts == 6
+    bd = S.blockDiagonalize(P, False, complex=True, rand=Coeffs(7))
+    so, _ = O.blockDiagonalize(O.partition_from_values(L), Coeffs(7), complex=True)
+    assert sorted(bd.blkSizes) == sorted(so) == [1, 1, 2]
+    Pm = P.matrix.astype(np.int64)
+    Bm = [(Pm == i + 1).astype(float) for i in range(6)]
+    for k, s in enumerate(bd.blkSizes):
+        if s != 1:
+            continue
+        for i in range(6):
+            for j in range(6):
+                prod = Bm[i] @ Bm[j]
+                coeff = [prod[Bm[t] > 0][0] for t in range(6)]
+                want = sum(coeff[t] * bd.blks[t][k] for t in range(6))
+                assert np.allclose(bd.blks[i][k] @ bd.blks[j][k], want, atol=1e-8)
