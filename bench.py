@@ -90,9 +90,11 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summarise the samples that arrived inside [t_begin, t_end] (the timed region).  The sampler
+        is started before the warm-up so that nvidia-smi's own start-up does not perturb it."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -100,9 +102,11 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        lines = [ln for (t, ln) in self.lines
+                 if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end)]
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -292,15 +296,16 @@ def main():
     fp64_peak = dgemm_peak(min(8192, max(1024, N)))
 
     # ---- resident arm ---------------------------------------------------------------------
+    clocks = ClockSampler(local)
+    clocks.start()
     for _ in range(args.warmup):
         dim, sizes, tr = job_resident(S, B, ctx, prob, C_dev)
     barrier()
     ctx.timing_reset()
     l0 = ctx.launch_count()
-    clocks = ClockSampler(local)
-    clocks.start()
     evs = []
     barrier()
+    t_begin = time.perf_counter()
     for _ in range(args.steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
@@ -326,7 +331,7 @@ def main():
         evs.append((a, b))
     barrier()
     ms_e2e = sum(a.elapsed_time(b) for a, b in evs)
-    clk = clocks.stop()
+    clk = clocks.stop(t_begin, time.perf_counter())
     assert dim_e == dim and sizes_e == sizes
     assert dim == prob.expected_dim and sorted(sizes) == prob.expected_blocks, (dim, sizes)
 

@@ -485,3 +485,25 @@ def test_complex_path_on_noncommutative_algebra():
                 coeff = [prod[Bm[t] > 0][0] for t in range(6)]
                 want = sum(coeff[t] * bd.blks[t][k] for t in range(6))
                 assert np.allclose(bd.blks[i][k] @ bd.blks[j][k], want, atol=1e-8)
+
+
+# ---------------------------------------------------------------------------------
+# BASELINE.json configs[2] at full size (size-independent properties)
+# ---------------------------------------------------------------------------------
+def test_config3_hamming_4_8_full_size():
+    """Theta' of H(4,8), N = 4096: dim 5, labels = distance + 1, blocks 5x[1] equal to the
+    Krawtchouk eigenmatrix, multiplicities C(4,j) 7^j (SURVEY.md 8(d) cfg 3)."""
+    prob = pr.hamming(4, 8, sparse=True)
+    tr = {}
+    P = S.admissible_subspace(*prob, rand=Coeffs(20260101), trace=tr)
+    assert P.nparts == 5 and tr["init"] == 2 and tr["iters"] == [(2, 4), (4, 5), (5, 5)]
+    assert np.array_equal(P.matrix, pr.hamming_distance_matrix(4, 8).astype(np.uint32) + 1)
+    bd = S.blockDiagonalize(P, False, rand=Coeffs(5))
+    assert bd.blkSizes == [1] * 5
+    mult = sorted(int(P._ptrs[r + 1] - P._ptrs[r]) for r in dict.fromkeys(P._kroot.tolist()))
+    assert mult == [1, 28, 294, 1372, 2401]
+    K = pr.krawtchouk(4, 8)
+    got = np.array([[bd.blks[i][k][0, 0] for k in range(5)] for i in range(5)])
+    for k in range(5):
+        assert min(np.abs(K - got[:, [k]]).max(axis=0)) < 1e-8 * np.abs(K).max()
+    P.release()
