@@ -507,3 +507,58 @@ def test_config3_hamming_4_8_full_size():
     for k in range(5):
         assert min(np.abs(K - got[:, [k]]).max(axis=0)) < 1e-8 * np.abs(K).max()
     P.release()
+
+
+# ---------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 15, 16, 17])
+def test_tiny_and_boundary_orders(n):
+    rng = np.random.default_rng(n)
+    M = rng.integers(0, 3, size=(n, n)).astype(np.float64)
+    want = O.partition_from_values(M)
+    with B.Context(n) as ctx:
+        assert ctx.refine_values(M, ATOL, True) == want.nparts
+        assert np.array_equal(ctx.get_labels(), want.matrix)
+        if want.nparts:
+            r = rng.random(want.nparts)
+            ctx.fill(r)
+            assert np.array_equal(ctx.get_matrix(B.MAT_X), O.fill(want, r))
+            ctx.square_round_refine(ATOL)
+            X = O.fill(want, r)
+            w2 = O.refine(want, O.partition_from_values(O.clamp_round(X @ X, ATOL)))
+            assert np.array_equal(ctx.get_labels(), w2.matrix)
+
+
+def test_all_zero_matrix_is_the_empty_partition():
+    with B.Context(9) as ctx:
+        assert ctx.refine_values(np.zeros((9, 9)), ATOL, True) == 0
+        assert ctx.zero_count() == 81
+        assert not ctx.get_labels().any()
+        ctx.fill(np.zeros(0))
+        assert not ctx.get_matrix(B.MAT_X).any()
+
+
+def test_argument_errors():
+    with pytest.raises(B.SdpsrError) as e:
+        B.Context(70000)
+    assert e.value.code == B.E_INVALID
+    with B.Context(4) as ctx:
+        with pytest.raises(B.SdpsrError) as e:
+            ctx.refine_values(np.ones((4, 4)), 0.5, True)          # floor(-log10(atol)) must be >= 1
+        assert e.value.code == B.E_INVALID
+        with pytest.raises(B.SdpsrError) as e:
+            ctx.set_labels(-np.ones((4, 4), dtype=np.int64))       # @assert 0 <= first(M_vals)
+        assert e.value.code == B.E_INVALID
+        with pytest.raises(B.SdpsrError) as e:
+            ctx.project_round_refine(ATOL)                         # no constraints yet
+        assert e.value.code == B.E_STATE
+        with pytest.raises(B.SdpsrError) as e:
+            ctx.square_round_refine(ATOL)                          # no X yet
+        assert e.value.code == B.E_STATE
+        A = np.zeros((2, 16))
+        A[0, :4] = 1.0
+        A[1, :4] = 2.0                                             # dependent rows: A A' singular
+        with pytest.raises(B.SdpsrError) as e:
+            ctx.set_constraints(A)
+        assert e.value.code == B.E_SINGULAR
