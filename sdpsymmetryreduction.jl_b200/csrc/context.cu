@@ -245,8 +245,7 @@ static int stage_labels(sdpsr_ctx* ctx, const void* labels, int elt_bytes) {
   SDPSR_CUDA(cudaMemcpyAsync(hb, bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
   SDPSR_REQUIRE(*hb == 0u, SDPSR_E_INVALID, "labels must be integers in 0 .. 2^32-2 (src/partitions.jl:46)");
-  // X2 was used as staging: restore its zero padding contract lazily (it is fully overwritten by
-  // the next product), and forget whatever it held.
+  // X2 served as staging; it is fully overwritten by the next product or upload.
   return SDPSR_OK;
 }
 

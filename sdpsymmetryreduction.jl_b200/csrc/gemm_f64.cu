@@ -291,7 +291,8 @@ int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B
   SDPSR_REQUIRE(M > 0 && Nc > 0 && K > 0, SDPSR_E_INVALID, "empty GEMM");
   SDPSR_REQUIRE(lda % 2 == 0 && ldb % 2 == 0, SDPSR_E_INVALID, "leading dimensions must be even (16-byte TMA strides)");
   SDPSR_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0), SDPSR_E_INVALID, "operands must be 16-byte aligned");
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {false};      // the attribute is per device
+  bool& attr_set = attr_set_dev[ctx->device & 63];
   if (!attr_set) {
     SDPSR_CUDA(cudaFuncSetAttribute(gemm_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;

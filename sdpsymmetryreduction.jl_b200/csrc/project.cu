@@ -14,7 +14,6 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
-#include <numeric>
 
 #include "sdpsr_internal.cuh"
 

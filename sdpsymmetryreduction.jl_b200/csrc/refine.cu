@@ -16,8 +16,6 @@
 // ranks of those first indices and are computed on the table only -- O(dim) work,
 // not O(N^2) -- and applied lazily (fill LUT composition, label export).
 // HBM traffic of a pass: 8 B value + 4 B old id + 4 B new id = 16 B / entry.
-#include <cooperative_groups.h>
-
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -705,7 +703,8 @@ int sdpsr_rank_table(sdpsr_ctx* ctx, KeyTable& t) {
 }
 
 int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {false};      // the attribute is per device
+  bool& attr_set = attr_set_dev[ctx->device & 63];
   const size_t smem = (size_t)SC * 16;
   if (!attr_set) {
     SDPSR_CUDA(cudaFuncSetAttribute(refine_kernel<KM_ROUND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

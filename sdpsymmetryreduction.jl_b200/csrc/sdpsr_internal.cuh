@@ -54,7 +54,6 @@ struct ConstraintSet {
   int64_t m = 0;
   int64_t nnz = 0;
   // CSR of A on the device (column index = padded linear index)
-  int64_t* d_rowptr = nullptr;   // unused on device, kept for symmetry
   uint32_t* d_col = nullptr;     // [nnz]
   double* d_val = nullptr;       // [nnz]
   uint32_t* d_chunk_row = nullptr;   // [nchunks] row of each reduction chunk
@@ -127,7 +126,6 @@ struct sdpsr_ctx {
   size_t values_alloc = 0;
   bool x_is_fill = false;       // X == fill(S, lut) and S unchanged since
   bool x_valid = false;
-  bool x_symmetric = false;     // X known symmetric (labels transpose-invariant, symmetric constraints)
 
   // ranking scratch
   uint32_t* rk_mi = nullptr;    // dense minidx list
@@ -171,7 +169,7 @@ struct sdpsr_ctx {
   }
 };
 
-// RAII-less timing helper: tic() before a kernel family, toc() after.
+// Scope timer: records a CUDA-event pair around the kernels launched in its scope (SDPSR_F_TIMING).
 struct Timed {
   sdpsr_ctx* c;
   int fam;
@@ -203,7 +201,6 @@ struct RefineSpec {
   const double* vals = nullptr;     // value source array (padded layout) or null
   double* vals_out = nullptr;       // optional: write the rounded values here
   const uint32_t* lab2 = nullptr;   // KM_PAIR: second provisional-id array
-  int lab2_bits = 0;                // (unused, informational)
   bool fillproj = false;            // value = lut[label] - tpat[pid] instead of vals[idx]
   const double* lut = nullptr;
   const double* tpat = nullptr;
