@@ -270,7 +270,7 @@ def main():
     C_dev = C_pinned_t.cuda(non_blocking=False)
     torch.cuda.synchronize()
 
-    ctx = B.Context(N, local, B.F_TIMING)
+    ctx = B.Context(N, local, B.F_TIMING | int(os.environ.get("SDPSR_BENCH_FLAGS", "0")))
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     if world > 1:

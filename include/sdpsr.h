@@ -60,6 +60,8 @@ typedef enum sdpsr_status {
 #define SDPSR_F_NO_SMEM_CACHE 4u     /* test hook: bypass the per-CTA key cache              */
 #define SDPSR_F_TIMING 8u            /* record CUDA-event timings per kernel family          */
 #define SDPSR_F_NO_SYRK 16u          /* square with the full GEMM even for symmetric X       */
+#define SDPSR_F_NCCL_EXCHANGE 32u    /* multi-GPU: exchange GEMM tiles with NCCL broadcasts instead
+                                        of peer stores from the GEMM epilogue (A/B switch)    */
 
 /* which device-resident matrix sdpsr_get_matrix / sdpsr_set_matrix address */
 #define SDPSR_MAT_X 0   /* current element X (src/partitions.jl:121)      */

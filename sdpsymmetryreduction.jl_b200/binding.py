@@ -21,7 +21,7 @@ OK = 0
 E_INVALID, E_CUDA, E_NO_DEVICE, E_ALLOC, E_LABEL_OVERFLOW, E_NOT_SYMMETRIC = -1, -2, -3, -4, -5, -6
 E_CUSOLVER, E_STATE, E_SINGULAR, E_NCCL, E_UNSUPPORTED = -7, -8, -9, -10, -11
 
-F_FORCE_BITMAP_RANK, F_TINY_TABLE, F_NO_SMEM_CACHE, F_TIMING, F_NO_SYRK = 1, 2, 4, 8, 16
+F_FORCE_BITMAP_RANK, F_TINY_TABLE, F_NO_SMEM_CACHE, F_TIMING, F_NO_SYRK, F_NCCL_EXCHANGE = 1, 2, 4, 8, 16, 32
 MAT_X, MAT_X2, MAT_Q, MAT_W = 0, 1, 2, 3
 K_REFINE, K_GEMM, K_FILL, K_PROJECT, K_RANK, K_EIG, K_BASIS, K_MISC = range(8)
 K_NAMES = ["refine", "gemm", "fill", "project", "rank", "eig", "basis", "misc"]

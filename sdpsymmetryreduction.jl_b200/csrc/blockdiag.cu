@@ -231,6 +231,12 @@ int ensure_buffer(sdpsr_ctx* ctx, double** p) {
   return SDPSR_OK;
 }
 
+}  // namespace
+
+int sdpsr_ensure_matrix(sdpsr_ctx* ctx, double** p) { return ensure_buffer(ctx, p); }
+
+namespace {
+
 struct Solver {
   cusolverDnHandle_t h = nullptr;
   cusolverDnParams_t params = nullptr;
@@ -254,13 +260,11 @@ void sdpsr_blockdiag_free(sdpsr_ctx* ctx) {
   cudaFree(ctx->Q);
   cudaFree(ctx->W);
   cudaFree(ctx->T);
-  cudaFree(ctx->Qhat);
   cudaFree(ctx->Xi);
   cudaFree(ctx->X2i);
   cudaFree(ctx->Qi);
   cudaFree(ctx->Wi);
   cudaFree(ctx->Ti);
-  cudaFree(ctx->Qhat_i);
   ctx->Xi = ctx->X2i = ctx->Qi = ctx->Wi = ctx->Ti = ctx->Qhat_i = nullptr;
   ctx->solver_work = nullptr;
   ctx->solver_info = nullptr;
@@ -386,9 +390,9 @@ extern "C" int sdpsr_block_norms(sdpsr_ctx* ctx, const double* r2, int64_t len, 
   // block maxima
   uint32_t *d_space = nullptr, *d_sdim = nullptr;
   unsigned long long* d_norms = nullptr;
-  SDPSR_CUDA(cudaMalloc(&d_space, (size_t)n * 4));
-  SDPSR_CUDA(cudaMalloc(&d_sdim, (size_t)ne * 4));
-  SDPSR_CUDA(cudaMalloc(&d_norms, (size_t)ne * ne * 8));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 0, (size_t)n, &d_space));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 1, (size_t)ne, &d_sdim));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 2, (size_t)ne * ne, &d_norms));
   SDPSR_CUDA(cudaMemcpyAsync(d_space, space.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
   SDPSR_CUDA(cudaMemcpyAsync(d_sdim, sdim.data(), (size_t)ne * 4, cudaMemcpyHostToDevice, ctx->stream));
   SDPSR_CUDA(cudaMemsetAsync(d_norms, 0, (size_t)ne * ne * 8, ctx->stream));
@@ -400,11 +404,7 @@ extern "C" int sdpsr_block_norms(sdpsr_ctx* ctx, const double* r2, int64_t len, 
   }
   SDPSR_CUDA(cudaGetLastError());
   SDPSR_CUDA(cudaMemcpyAsync(norms, d_norms, (size_t)ne * ne * 8, cudaMemcpyDefault, ctx->stream));
-  int st = finish(ctx);
-  cudaFree(d_space);
-  cudaFree(d_sdim);
-  cudaFree(d_norms);
-  SDPSR_TRY(st);
+  SDPSR_TRY(finish(ctx));
   // the kernel filled i <= j (bit patterns of non-negative doubles == the doubles); mirror
   for (int64_t j = 0; j < ne; ++j)
     for (int64_t i = 0; i < j; ++i) norms[j + ne * i] = norms[i + ne * j];
@@ -434,9 +434,7 @@ extern "C" int sdpsr_irreducible(sdpsr_ctx* ctx, const double* r3, int64_t len, 
   int64_t S = 0;
   for (auto& k : classes) S += (int64_t)k.size();
   // Qhat buffer (ld x S)
-  cudaFree(ctx->Qhat);
-  ctx->Qhat = nullptr;
-  SDPSR_CUDA(cudaMalloc(&ctx->Qhat, (size_t)ld * (size_t)S * 8));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 16, (size_t)ld * (size_t)S, &ctx->Qhat));
   SDPSR_CUDA(cudaMemsetAsync(ctx->Qhat, 0, (size_t)ld * (size_t)S * 8, ctx->stream));
   ctx->qhat_cols = S;
   ctx->blk_sizes.clear();
@@ -483,7 +481,7 @@ extern "C" int sdpsr_irreducible(sdpsr_ctx* ctx, const double* r3, int64_t len, 
     const int64_t nf = (int64_t)fcols.size();
     SDPSR_REQUIRE(nf <= n, SDPSR_E_INVALID, "internal: too many first vectors");
     int64_t* d_fcols = nullptr;
-    SDPSR_CUDA(cudaMalloc(&d_fcols, (size_t)nf * 8));
+    SDPSR_TRY(sdpsr_scratch_t(ctx, 0, (size_t)nf, &d_fcols));
     SDPSR_CUDA(cudaMemcpyAsync(d_fcols, fcols.data(), (size_t)nf * 8, cudaMemcpyHostToDevice, ctx->stream));
     // F = Q[:, fcols]  (into W), V = A3 * F (into T)
     gather_cols_kernel<<<dim3((unsigned)std::min<int64_t>((ld + 255) / 256, 64), (unsigned)nf), 256, 0, ctx->stream>>>(
@@ -507,8 +505,8 @@ extern "C" int sdpsr_irreducible(sdpsr_ctx* ctx, const double* r3, int64_t len, 
     }
     int64_t* d_h = nullptr;
     double* d_uw = nullptr;
-    SDPSR_CUDA(cudaMalloc(&d_h, h.size() * 8));
-    SDPSR_CUDA(cudaMalloc(&d_uw, (size_t)np * (size_t)maxm * 2 * 8));
+    SDPSR_TRY(sdpsr_scratch_t(ctx, 1, h.size(), &d_h));
+    SDPSR_TRY(sdpsr_scratch_t(ctx, 2, (size_t)np * (size_t)maxm * 2, &d_uw));
     SDPSR_CUDA(cudaMemcpyAsync(d_h, h.data(), h.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     double* d_u = d_uw;
     double* d_w = d_uw + np * maxm;
@@ -522,9 +520,6 @@ extern "C" int sdpsr_irreducible(sdpsr_ctx* ctx, const double* r3, int64_t len, 
     count_launch(ctx, 3);
     SDPSR_CUDA(cudaGetLastError());
     SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_h);
-    cudaFree(d_uw);
-    cudaFree(d_fcols);
   }
   // clamptol!.(Q_hat, atol)                                                  (src/diagonalize.jl:39)
   {
@@ -554,9 +549,7 @@ extern "C" int sdpsr_set_qhat(sdpsr_ctx* ctx, const double* qhat, const int64_t*
     SDPSR_REQUIRE(blk_sizes[k] >= 1, SDPSR_E_INVALID, "block sizes must be positive");
     S += blk_sizes[k];
   }
-  cudaFree(ctx->Qhat);
-  ctx->Qhat = nullptr;
-  SDPSR_CUDA(cudaMalloc(&ctx->Qhat, (size_t)ctx->ld * (size_t)S * 8));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 16, (size_t)ctx->ld * (size_t)S, &ctx->Qhat));
   SDPSR_CUDA(cudaMemsetAsync(ctx->Qhat, 0, (size_t)ctx->ld * (size_t)S * 8, ctx->stream));
   SDPSR_CUDA(cudaMemcpy2DAsync(ctx->Qhat, (size_t)ctx->ld * 8, qhat, (size_t)ctx->n * 8, (size_t)ctx->n * 8, (size_t)S,
                                cudaMemcpyDefault, ctx->stream));
@@ -576,7 +569,7 @@ extern "C" int sdpsr_basis_image(sdpsr_ctx* ctx, double atol, double* out, int64
   KeyTable& t = ctx->tab[ctx->cur];
   // ---- CSR by canonical label (_constraints, :42-50) --------------------------------------
   unsigned long long* d_cnt = nullptr;
-  SDPSR_CUDA(cudaMalloc(&d_cnt, ((size_t)d + 2) * 8));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 0, (size_t)d + 2, &d_cnt));
   SDPSR_CUDA(cudaMemsetAsync(d_cnt, 0, ((size_t)d + 2) * 8, ctx->stream));
   const dim3 g2((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)n);
   class_count_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->labels, t.rank, n, ld, d_cnt);
@@ -589,7 +582,7 @@ extern "C" int sdpsr_basis_image(sdpsr_ctx* ctx, double atol, double* out, int64
   const unsigned long long nent = start[(size_t)d + 1];
   SDPSR_CUDA(cudaMemcpyAsync(d_cnt, start.data(), start.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
   uint32_t* d_rc = nullptr;
-  SDPSR_CUDA(cudaMalloc(&d_rc, std::max<size_t>(1, (size_t)nent) * 8));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 1, std::max<size_t>(1, (size_t)nent) * 2, &d_rc));
   uint32_t* d_rows = d_rc;
   uint32_t* d_cols = d_rc + nent;
   class_scatter_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->labels, t.rank, n, ld, d_cnt, d_rows, d_cols);
@@ -610,10 +603,10 @@ extern "C" int sdpsr_basis_image(sdpsr_ctx* ctx, double atol, double* out, int64
   double* d_part = nullptr;
   double* d_qt = nullptr;
   int* d_pairs = nullptr;
-  SDPSR_CUDA(cudaMalloc(&d_cb, std::max<size_t>(1, (size_t)nchunks) * 16));
-  SDPSR_CUDA(cudaMalloc(&d_part, std::max<size_t>(1, (size_t)nchunks) * BI_PAIRS * 8));
-  SDPSR_CUDA(cudaMalloc(&d_qt, (size_t)n * (size_t)S * 8));
-  SDPSR_CUDA(cudaMalloc(&d_pairs, 2 * BI_PAIRS * sizeof(int)));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 2, std::max<size_t>(1, (size_t)nchunks) * 2, &d_cb));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 3, std::max<size_t>(1, (size_t)nchunks) * BI_PAIRS, &d_part));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 4, (size_t)n * (size_t)S, &d_qt));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 5, (size_t)2 * BI_PAIRS, &d_pairs));
   SDPSR_CUDA(cudaMemcpyAsync(d_cb, cbeg.data(), (size_t)nchunks * 8, cudaMemcpyHostToDevice, ctx->stream));
   SDPSR_CUDA(cudaMemcpyAsync(d_cb + nchunks, cend.data(), (size_t)nchunks * 8, cudaMemcpyHostToDevice, ctx->stream));
   qhat_rowmajor_kernel<<<dim3((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)S), 256, 0, ctx->stream>>>(
@@ -665,12 +658,6 @@ extern "C" int sdpsr_basis_image(sdpsr_ctx* ctx, double atol, double* out, int64
         result[(size_t)((i - 1) * Sq + poff[p0 + p])] = s;
       }
   }
-  cudaFree(d_cnt);
-  cudaFree(d_rc);
-  cudaFree(d_cb);
-  cudaFree(d_part);
-  cudaFree(d_qt);
-  cudaFree(d_pairs);
   SDPSR_TRY(status);
   SDPSR_CUDA(cudaMemcpy(out, result.data(), result.size() * 8, cudaMemcpyDefault));
   return finish(ctx);
@@ -1027,9 +1014,9 @@ extern "C" int sdpsr_block_norms_complex(sdpsr_ctx* ctx, const double* r2, int64
   SDPSR_TRY(cgemm(ctx, ctx->X2, ctx->X2i, ctx->T, ctx->Ti, ctx->W, ctx->Wi, n)); // W = Q' T
   uint32_t *d_space = nullptr, *d_sdim = nullptr;
   unsigned long long* d_norms = nullptr;
-  SDPSR_CUDA(cudaMalloc(&d_space, (size_t)n * 4));
-  SDPSR_CUDA(cudaMalloc(&d_sdim, (size_t)ne * 4));
-  SDPSR_CUDA(cudaMalloc(&d_norms, (size_t)ne * ne * 8));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 0, (size_t)n, &d_space));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 1, (size_t)ne, &d_sdim));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 2, (size_t)ne * ne, &d_norms));
   SDPSR_CUDA(cudaMemcpyAsync(d_space, space.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
   SDPSR_CUDA(cudaMemcpyAsync(d_sdim, sdim.data(), (size_t)ne * 4, cudaMemcpyHostToDevice, ctx->stream));
   SDPSR_CUDA(cudaMemsetAsync(d_norms, 0, (size_t)ne * ne * 8, ctx->stream));
@@ -1038,11 +1025,7 @@ extern "C" int sdpsr_block_norms_complex(sdpsr_ctx* ctx, const double* r2, int64
   count_launch(ctx);
   SDPSR_CUDA(cudaGetLastError());
   SDPSR_CUDA(cudaMemcpyAsync(norms, d_norms, (size_t)ne * ne * 8, cudaMemcpyDefault, ctx->stream));
-  int st = finish(ctx);
-  cudaFree(d_space);
-  cudaFree(d_sdim);
-  cudaFree(d_norms);
-  SDPSR_TRY(st);
+  SDPSR_TRY(finish(ctx));
   for (int64_t j = 0; j < ne; ++j)
     for (int64_t i = 0; i < j; ++i) norms[j + ne * i] = norms[i + ne * j];
   return SDPSR_OK;
@@ -1069,11 +1052,8 @@ extern "C" int sdpsr_irreducible_complex(sdpsr_ctx* ctx, const double* r3, int64
   }
   int64_t S = 0;
   for (auto& k : classes) S += (int64_t)k.size();
-  cudaFree(ctx->Qhat);
-  cudaFree(ctx->Qhat_i);
-  ctx->Qhat = ctx->Qhat_i = nullptr;
-  SDPSR_CUDA(cudaMalloc(&ctx->Qhat, (size_t)ld * (size_t)S * 8));
-  SDPSR_CUDA(cudaMalloc(&ctx->Qhat_i, (size_t)ld * (size_t)S * 8));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 16, (size_t)ld * (size_t)S, &ctx->Qhat));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 17, (size_t)ld * (size_t)S, &ctx->Qhat_i));
   SDPSR_CUDA(cudaMemsetAsync(ctx->Qhat, 0, (size_t)ld * (size_t)S * 8, ctx->stream));
   SDPSR_CUDA(cudaMemsetAsync(ctx->Qhat_i, 0, (size_t)ld * (size_t)S * 8, ctx->stream));
   ctx->qhat_cols = S;

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <vector>
 
 #include "sdpsr_internal.cuh"
 
@@ -95,7 +96,92 @@ int sdpsr_comm_allreduce_max_u64(sdpsr_ctx* ctx, unsigned long long* buf, size_t
   return SDPSR_OK;
 }
 
+int sdpsr_comm_barrier(sdpsr_ctx* ctx) {
+  if (ctx->nranks <= 1) return SDPSR_OK;
+  NCCL_TRY(api().AllReduce(ctx->d_barrier, ctx->d_barrier, 1, /*ncclInt32*/ 2, /*ncclSum*/ 0, (ncclComm_t)ctx->nccl,
+                           ctx->stream));
+  return SDPSR_OK;
+}
+
+// device table of the G peer copies of output buffer C, or NULL when C is not a registered buffer
+double* const* sdpsr_comm_peer_table(sdpsr_ctx* ctx, const double* C) {
+  if (!ctx->peer_ok) return nullptr;
+  const double* mine[3] = {ctx->X2, ctx->T, ctx->W};
+  for (int b = 0; b < 3; ++b)
+    if (C == mine[b]) return ctx->d_peer + b * sdpsr_ctx::MAX_RANKS;
+  return nullptr;
+}
+
+// Map every rank's X2 / T / W into this process (CUDA IPC over NVLink peer access).
+static int setup_peer_buffers(sdpsr_ctx* ctx) {
+  const int G = ctx->nranks;
+  SDPSR_REQUIRE(G <= sdpsr_ctx::MAX_RANKS, SDPSR_E_UNSUPPORTED, "at most 16 ranks");
+  SDPSR_TRY(sdpsr_ensure_matrix(ctx, &ctx->T));
+  SDPSR_TRY(sdpsr_ensure_matrix(ctx, &ctx->W));
+  SDPSR_CUDA(cudaMalloc(&ctx->d_barrier, sizeof(int)));
+  SDPSR_CUDA(cudaMemsetAsync(ctx->d_barrier, 0, sizeof(int), ctx->stream));
+  double* mine[3] = {ctx->X2, ctx->T, ctx->W};
+  cudaIpcMemHandle_t hs[3];
+  for (int b = 0; b < 3; ++b) SDPSR_CUDA(cudaIpcGetMemHandle(&hs[b], mine[b]));
+  unsigned char* d_h = nullptr;
+  const size_t hb = sizeof(cudaIpcMemHandle_t) * 3;
+  SDPSR_CUDA(cudaMalloc(&d_h, hb * G));
+  SDPSR_CUDA(cudaMemcpyAsync(d_h + hb * ctx->rank, hs, hb, cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_TRY(api().AllGather(d_h + hb * ctx->rank, d_h, hb, NCCL_UINT8, (ncclComm_t)ctx->nccl, ctx->stream));
+  std::vector<cudaIpcMemHandle_t> all((size_t)3 * G);
+  SDPSR_CUDA(cudaMemcpyAsync(all.data(), d_h, hb * G, cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_h);
+  bool ok = true;
+  for (int r = 0; r < G && ok; ++r)
+    for (int b = 0; b < 3; ++b) {
+      if (r == ctx->rank) {
+        ctx->peer_ptr[b][r] = mine[b];
+        continue;
+      }
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[(size_t)3 * r + b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = false;
+        break;
+      }
+      ctx->peer_ptr[b][r] = reinterpret_cast<double*>(p);
+    }
+  if (ok) {
+    SDPSR_CUDA(cudaMalloc(&ctx->d_peer, sizeof(double*) * 3 * sdpsr_ctx::MAX_RANKS));
+    SDPSR_CUDA(cudaMemcpyAsync(ctx->d_peer, ctx->peer_ptr, sizeof(double*) * 3 * sdpsr_ctx::MAX_RANKS,
+                               cudaMemcpyHostToDevice, ctx->stream));
+    SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  // every rank must take the same path: agree on success
+  int flag = ok ? 1 : 0, *d_f = ctx->d_barrier;
+  SDPSR_CUDA(cudaMemcpyAsync(d_f, &flag, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_TRY(api().AllReduce(d_f, d_f, 1, /*ncclInt32*/ 2, /*ncclMin*/ 3, (ncclComm_t)ctx->nccl, ctx->stream));
+  SDPSR_CUDA(cudaMemcpyAsync(&flag, d_f, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  SDPSR_CUDA(cudaMemsetAsync(ctx->d_barrier, 0, sizeof(int), ctx->stream));
+  ctx->peer_ok = flag == 1 && !(ctx->flags & SDPSR_F_NCCL_EXCHANGE);
+  return SDPSR_OK;
+}
+
 void sdpsr_comm_free(sdpsr_ctx* ctx) {
+  if (ctx->nccl && api().ok) {
+    // peers may still be storing into our buffers: rendezvous before unmapping / freeing anything
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_barrier)
+      api().AllReduce(ctx->d_barrier, ctx->d_barrier, 1, 2, 0, (ncclComm_t)ctx->nccl, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  for (int b = 0; b < 3; ++b)
+    for (int r = 0; r < sdpsr_ctx::MAX_RANKS; ++r) {
+      if (ctx->peer_ptr[b][r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->peer_ptr[b][r]);
+      ctx->peer_ptr[b][r] = nullptr;
+    }
+  cudaFree(ctx->d_peer);
+  cudaFree(ctx->d_barrier);
+  ctx->d_peer = nullptr;
+  ctx->d_barrier = nullptr;
+  ctx->peer_ok = false;
   if (ctx->nccl && api().ok) api().CommDestroy((ncclComm_t)ctx->nccl);
   cudaFree(ctx->d_tiles);
   ctx->d_tiles = nullptr;
@@ -129,6 +215,7 @@ extern "C" int sdpsr_comm_init(sdpsr_ctx* ctx, int nranks, int rank, const void*
   ctx->nccl = comm;
   ctx->nranks = nranks;
   ctx->rank = rank;
+  if (nranks > 1) SDPSR_TRY(setup_peer_buffers(ctx));
   return SDPSR_OK;
 }
 

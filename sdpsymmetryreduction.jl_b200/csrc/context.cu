@@ -54,6 +54,24 @@ Timed::~Timed() {
   }
 }
 
+int sdpsr_scratch(sdpsr_ctx* ctx, int slot, size_t bytes, void** out) {
+  if (slot < 0 || slot >= sdpsr_ctx::SCRATCH_SLOTS) return ctx->fail(SDPSR_E_INVALID, "bad scratch slot");
+  if (bytes < 256) bytes = 256;
+  if (ctx->scratch_bytes[slot] < bytes) {
+    cudaFree(ctx->scratch_ptr[slot]);
+    ctx->scratch_ptr[slot] = nullptr;
+    ctx->scratch_bytes[slot] = 0;
+    const size_t want = bytes + bytes / 4;
+    if (cudaMalloc(&ctx->scratch_ptr[slot], want) != cudaSuccess) {
+      cudaGetLastError();
+      return ctx->fail(SDPSR_E_ALLOC, "scratch allocation of " + std::to_string(want) + " bytes failed");
+    }
+    ctx->scratch_bytes[slot] = want;
+  }
+  *out = ctx->scratch_ptr[slot];
+  return SDPSR_OK;
+}
+
 // ---------------------------------------------------------------------------
 // small kernels for staging
 // ---------------------------------------------------------------------------
@@ -176,6 +194,7 @@ extern "C" int sdpsr_destroy(sdpsr_ctx* ctx) {
   sdpsr_constraints_free(ctx);
   sdpsr_table_free(ctx->tab[0]);
   sdpsr_table_free(ctx->tab[1]);
+  sdpsr_table_free(ctx->tab_scratch);
   cudaFree(ctx->labels);
   cudaFree(ctx->labels_alt);
   cudaFree(ctx->labels_tmp);
@@ -187,6 +206,7 @@ extern "C" int sdpsr_destroy(sdpsr_ctx* ctx) {
   cudaFree(ctx->bitmap);
   cudaFree(ctx->bm_block);
   cudaFree(ctx->d_scalars);
+  for (int i = 0; i < sdpsr_ctx::SCRATCH_SLOTS; ++i) cudaFree(ctx->scratch_ptr[i]);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

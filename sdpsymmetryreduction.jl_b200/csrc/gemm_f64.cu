@@ -86,7 +86,7 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 double* __restrict__ C, int64_t ldc, int M, int Nc, int K, int tiles_m, int tiles_n, int lower,
-                const int2* __restrict__ tile_list, int accum) {
+                const int2* __restrict__ tile_list, int accum, double* const* __restrict__ peers, int npeers) {
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;       // SWIZZLE_128B atoms are 1 KB
   const uint32_t bar_full = base + STAGES * STAGE_BYTES;
@@ -216,9 +216,17 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int nslot = 2 * kk + c;
         const int n = n0 + wn * 32 + j * 8 + (nslot & 3) * 2 + (nslot >> 2);
         if (m < M && n < Nc) {
-          double* dst = C + (int64_t)m + ldc * (int64_t)n;
-          // accum: 0 -> C = A*B, +1 -> C += A*B, -1 -> C -= A*B (complex products from real GEMMs)
-          *dst = accum == 0 ? acc[i][j][c] : (accum > 0 ? *dst + acc[i][j][c] : *dst - acc[i][j][c]);
+          const int64_t off = (int64_t)m + ldc * (int64_t)n;
+          if (peers) {
+            // fused exchange: the tile goes straight into every rank's copy of C (own copy included)
+            // over NVLink peer mappings, while the other CTAs are still computing
+#pragma unroll 1
+            for (int r = 0; r < npeers; ++r) peers[r][off] = acc[i][j][c];
+          } else {
+            double* dst = C + off;
+            // accum: 0 -> C = A*B, +1 -> C += A*B, -1 -> C -= A*B (complex products from real GEMMs)
+            *dst = accum == 0 ? acc[i][j][c] : (accum > 0 ? *dst + acc[i][j][c] : *dst - acc[i][j][c]);
+          }
         }
       }
     }
@@ -322,19 +330,33 @@ int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B
     SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));     // `tiles` dies at scope end
     d_tiles = reinterpret_cast<const int2*>(ctx->d_tiles);
   }
+  double* const* peers = (sharded && accum == 0) ? sdpsr_comm_peer_table(ctx, C) : nullptr;
+  if (peers) {
+    // nobody may still be reading the previous contents of C on any rank when remote stores begin
+    SDPSR_TRY(sdpsr_comm_barrier(ctx));
+  }
   {
     // work = flops issued: the lower-triangle launch covers ntiles full 128x128 tiles
     Timed tm(ctx, SDPSR_K_GEMM, (lower || sharded) ? 2.0 * (double)ntiles * BM * BN * (double)K
                                                    : 2.0 * (double)M * (double)Nc * (double)K);
     if (ntiles) {
       gemm_f64_kernel<<<(unsigned)ntiles, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, C, ldc, (int)M, (int)Nc, (int)K,
-                                                                             tiles_m, tiles_n, lower ? 1 : 0, d_tiles, accum);
+                                                                             tiles_m, tiles_n, lower ? 1 : 0, d_tiles, accum,
+                                                                             peers, ctx->nranks);
       count_launch(ctx);
     }
   }
   SDPSR_CUDA(cudaGetLastError());
-  // every rank receives the tile-columns it does not own (grouped NCCL broadcasts over NVLink)
-  if (sharded) SDPSR_TRY(sdpsr_comm_exchange_tilecols(ctx, C, ldc, Nc, BN, tiles_n));
+  if (sharded) {
+    if (peers) {
+      // the tiles were stored into every rank's C by the epilogues; all ranks' kernels must have
+      // finished before anyone reads C
+      SDPSR_TRY(sdpsr_comm_barrier(ctx));
+    } else {
+      // every rank receives the tile-columns it does not own (grouped NCCL broadcasts over NVLink)
+      SDPSR_TRY(sdpsr_comm_exchange_tilecols(ctx, C, ldc, Nc, BN, tiles_n));
+    }
+  }
   if (lower) {
     Timed tm(ctx, SDPSR_K_MISC, (double)M * (double)Nc * 8.0);
     dim3 g((unsigned)((Nc + 31) / 32), (unsigned)((Nc + 31) / 32));

@@ -257,15 +257,7 @@ int sdpsr_matrix_symmetric(sdpsr_ctx* ctx, const double* x, int* is_sym) {
 
 // ---------------------------------------------------------------------------
 void sdpsr_constraints_free(sdpsr_ctx* ctx) {
-  ConstraintSet& c = ctx->cons;
-  cudaFree(c.d_col);
-  cudaFree(c.d_val);
-  cudaFree(c.d_chunk_row);
-  cudaFree(c.d_chunk_beg);
-  cudaFree(c.d_partial);
-  cudaFree(c.d_pid);
-  cudaFree(c.d_tpat);
-  c = ConstraintSet();
+  ctx->cons = ConstraintSet();      // device arrays live in scratch slots 8-14 (freed with the context)
 }
 
 int sdpsr_symmetric_check(sdpsr_ctx* ctx, int* is_sym) {
@@ -391,12 +383,12 @@ int sdpsr_constraints_finalize(sdpsr_ctx* ctx) {
     }
   c.nchunks = (int64_t)cbeg.size();
   const size_t nz_alloc = std::max<size_t>((size_t)nnz, 1), ch_alloc = std::max<size_t>((size_t)c.nchunks, 1);
-  SDPSR_CUDA(cudaMalloc(&c.d_col, nz_alloc * sizeof(uint32_t)));
-  SDPSR_CUDA(cudaMalloc(&c.d_val, nz_alloc * sizeof(double)));
-  SDPSR_CUDA(cudaMalloc(&c.d_chunk_row, ch_alloc * sizeof(uint32_t)));
-  SDPSR_CUDA(cudaMalloc(&c.d_chunk_beg, 2 * ch_alloc * sizeof(uint32_t)));
-  SDPSR_CUDA(cudaMalloc(&c.d_partial, ch_alloc * sizeof(double)));
-  SDPSR_CUDA(cudaMalloc(&c.d_pid, ctx->elems * sizeof(uint32_t)));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 8, nz_alloc, &c.d_col));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 9, nz_alloc, &c.d_val));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 10, ch_alloc, &c.d_chunk_row));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 11, 2 * ch_alloc, &c.d_chunk_beg));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 12, ch_alloc, &c.d_partial));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 13, ctx->elems, &c.d_pid));
   if (nnz) {
     SDPSR_CUDA(cudaMemcpyAsync(c.d_col, col.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
     SDPSR_CUDA(cudaMemcpyAsync(c.d_val, c.h_val.data(), (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -414,7 +406,7 @@ int sdpsr_constraints_finalize(sdpsr_ctx* ctx) {
     SDPSR_CUDA(cudaGetLastError());
   }
   SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));   // host vectors above die below
-  KeyTable scratch;
+  KeyTable& scratch = ctx->tab_scratch;   // reused across calls, freed with the context
   RefineSpec sp;
   sp.mode = KM_RAW;
   sp.vals = ctx->X2;
@@ -426,7 +418,6 @@ int sdpsr_constraints_finalize(sdpsr_ctx* ctx) {
   int64_t npat = 0;
   int st = sdpsr_refine_pass(ctx, sp, &npat);
   if (st != SDPSR_OK) {
-    sdpsr_table_free(scratch);
     return st;
   }
   c.npat = npat;
@@ -444,7 +435,7 @@ int sdpsr_constraints_finalize(sdpsr_ctx* ctx) {
   std::vector<uint32_t> allmin((size_t)scratch.cap);
   SDPSR_CUDA(cudaMemcpyAsync(allmin.data(), scratch.minidx, allmin.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
   unsigned long long* dcnt = nullptr;
-  SDPSR_CUDA(cudaMalloc(&dcnt, ((size_t)npat + 1) * 8));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 0, (size_t)npat + 1, &dcnt));
   SDPSR_CUDA(cudaMemsetAsync(dcnt, 0, ((size_t)npat + 1) * 8, ctx->stream));
   pattern_count_kernel<<<dim3((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)n), 256, 0, ctx->stream>>>(
       c.d_pid, n, ld, dcnt);
@@ -452,8 +443,6 @@ int sdpsr_constraints_finalize(sdpsr_ctx* ctx) {
   std::vector<unsigned long long> cnt((size_t)npat + 1);
   SDPSR_CUDA(cudaMemcpyAsync(cnt.data(), dcnt, cnt.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
   SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaFree(dcnt);
-  sdpsr_table_free(scratch);
   std::vector<int64_t> rep((size_t)npat + 1, -1);
   for (int64_t i = 0; i < npat; ++i) {
     const uint32_t slot = occ[(size_t)i];
@@ -495,7 +484,7 @@ int sdpsr_constraints_finalize(sdpsr_ctx* ctx) {
         c.gram_lu[(size_t)c.pat_row[e1] * m + c.pat_row[e2]] += (double)cnt[(size_t)p] * c.pat_val[e1] * c.pat_val[e2];
   SDPSR_REQUIRE(lu_factor(c.gram_lu, c.gram_piv, (int)m), SDPSR_E_SINGULAR,
                 "constraint rows are linearly dependent (A A' is singular)");
-  SDPSR_CUDA(cudaMalloc(&c.d_tpat, ((size_t)npat + 1) * sizeof(double)));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 14, (size_t)npat + 1, &c.d_tpat));
   SDPSR_CUDA(cudaMemsetAsync(c.d_tpat, 0, ((size_t)npat + 1) * sizeof(double), ctx->stream));
   c.ready = true;
   return SDPSR_OK;
@@ -630,7 +619,7 @@ extern "C" int sdpsr_project_round_refine(sdpsr_ctx* ctx, double atol, int64_t* 
   } else {
     // wide rounding grid: materialise X first, then the generic two-step refine
     SDPSR_TRY(sdpsr_ensure_tmp_labels(ctx));
-    KeyTable scratch;
+    KeyTable& scratch = ctx->tab_scratch;   // reused across calls, freed with the context
     sp.mode = KM_RAW;
     sp.out_override = ctx->labels_tmp;
     sp.table_override = &scratch;
@@ -642,7 +631,6 @@ extern "C" int sdpsr_project_round_refine(sdpsr_ctx* ctx, double atol, int64_t* 
       pr.do_round = false;
       st = sdpsr_refine_pass(ctx, pr, dim);
     }
-    sdpsr_table_free(scratch);
     SDPSR_TRY(st);
   }
   ctx->x_valid = true;
@@ -721,7 +709,7 @@ extern "C" int sdpsr_reduce_problem(sdpsr_ctx* ctx, const double* C, double* new
   double* dC = nullptr;
   int st = SDPSR_OK;
   if (newA) {
-    SDPSR_CUDA(cudaMalloc(&dA, (size_t)m * d * sizeof(double)));
+    SDPSR_TRY(sdpsr_scratch_t(ctx, 0, (size_t)m * d, &dA));
     SDPSR_CUDA(cudaMemsetAsync(dA, 0, (size_t)m * d * sizeof(double), ctx->stream));
     if (c.nchunks) {
       reduce_rows_kernel<<<(unsigned)c.nchunks, 256, smem, ctx->stream>>>(c.d_col, c.d_val, c.d_chunk_row, c.d_chunk_beg,
@@ -737,7 +725,7 @@ extern "C" int sdpsr_reduce_problem(sdpsr_ctx* ctx, const double* C, double* new
     if (ctx->ld != ctx->n) cudaMemsetAsync(ctx->X2, 0, ctx->elems * 8, ctx->stream);
     cudaMemcpy2DAsync(ctx->X2, (size_t)ctx->ld * 8, C, (size_t)ctx->n * 8, (size_t)ctx->n * 8, (size_t)ctx->n,
                       cudaMemcpyDefault, ctx->stream);
-    cudaMalloc(&dC, (size_t)d * sizeof(double));
+    SDPSR_TRY(sdpsr_scratch_t(ctx, 1, (size_t)d, &dC));
     cudaMemsetAsync(dC, 0, (size_t)d * sizeof(double), ctx->stream);
     const int grid = (int)std::min<uint64_t>((ctx->elems + 255) / 256, (uint64_t)ctx->sm_count * 4);
     reduce_objective_kernel<<<grid, 256, smem, ctx->stream>>>(ctx->X2, ctx->labels, t.rank, ctx->elems, d, dC);
@@ -746,7 +734,5 @@ extern "C" int sdpsr_reduce_problem(sdpsr_ctx* ctx, const double* C, double* new
       st = ctx->fail(SDPSR_E_CUDA, "copy of newC failed");
   }
   const int fin = finish(ctx);
-  cudaFree(dA);
-  cudaFree(dC);
   return st != SDPSR_OK ? st : fin;
 }

@@ -846,7 +846,7 @@ int sdpsr_generic_refine_values(sdpsr_ctx* ctx, const double* dvals, double atol
     return sdpsr_refine_pass(ctx, sp, dim);
   }
   SDPSR_TRY(sdpsr_ensure_tmp_labels(ctx));
-  KeyTable scratch;
+  KeyTable& scratch = ctx->tab_scratch;   // reused across calls, freed with the context
   sp.mode = KM_RAW;
   sp.ignore_labels = true;
   sp.out_override = ctx->labels_tmp;
@@ -860,7 +860,6 @@ int sdpsr_generic_refine_values(sdpsr_ctx* ctx, const double* dvals, double atol
     pr.do_round = false;
     st = sdpsr_refine_pass(ctx, pr, dim);
   }
-  sdpsr_table_free(scratch);
   return st;
 }
 

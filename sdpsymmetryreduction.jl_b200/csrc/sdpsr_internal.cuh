@@ -99,6 +99,7 @@ struct sdpsr_ctx {
   uint32_t* labels_alt = nullptr;
   uint32_t* labels_tmp = nullptr;   // lazily allocated third buffer (generic two-step refine, IO)
   KeyTable tab[2];
+  KeyTable tab_scratch;             // reusable third table (two-step refine, pattern ids)
   int cur = 0;
   int64_t dim = 0;
 
@@ -152,6 +153,14 @@ struct sdpsr_ctx {
   int nranks = 1, rank = 0;
   void* d_tiles = nullptr;      // this rank's (tm, tn) tile list for sharded GEMMs
   size_t tile_alloc = 0;
+  // peer-mapped output buffers (CUDA IPC): peer_ptr[b][r] = rank r's copy of shardable buffer b
+  // (0: X2, 1: T, 2: W); d_peer is the same table on the device.  The sharded GEMM stores its tiles
+  // into every rank's buffer from its epilogue, so the exchange overlaps the math.
+  static constexpr int MAX_RANKS = 16;
+  double* peer_ptr[3][MAX_RANKS] = {};
+  double** d_peer = nullptr;
+  bool peer_ok = false;
+  int* d_barrier = nullptr;
 
   // timing
   std::vector<EventPair> ev_pending;
@@ -160,6 +169,12 @@ struct sdpsr_ctx {
   int64_t t_launch[SDPSR_K_COUNT] = {0};
   double t_work[SDPSR_K_COUNT] = {0};
   int64_t launches = 0;
+
+  // grow-only scratch buffers (slot -> device allocation): no cudaMalloc/cudaFree on the steady-state
+  // path (allocation calls serialise across processes and jitter by up to seconds with IPC mappings)
+  static constexpr int SCRATCH_SLOTS = 32;
+  void* scratch_ptr[SCRATCH_SLOTS] = {};
+  size_t scratch_bytes[SCRATCH_SLOTS] = {};
 
   std::string err;
 
@@ -248,6 +263,16 @@ void sdpsr_comm_free(sdpsr_ctx* ctx);
 int sdpsr_comm_exchange_tilecols(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t ncols, int tile_cols, int ntilecols);
 int sdpsr_comm_bcast(sdpsr_ctx* ctx, void* buf, size_t bytes, int root);
 int sdpsr_comm_allreduce_max_u64(sdpsr_ctx* ctx, unsigned long long* buf, size_t count);
+int sdpsr_comm_barrier(sdpsr_ctx* ctx);
+double* const* sdpsr_comm_peer_table(sdpsr_ctx* ctx, const double* C);
+int sdpsr_ensure_matrix(sdpsr_ctx* ctx, double** p);
+
+// context.cu: grow-only scratch (slots 0-7 transient per call, 8-15 constraint set, 16+ persistent)
+int sdpsr_scratch(sdpsr_ctx* ctx, int slot, size_t bytes, void** out);
+template <typename T>
+static inline int sdpsr_scratch_t(sdpsr_ctx* ctx, int slot, size_t count, T** out) {
+  return sdpsr_scratch(ctx, slot, count * sizeof(T), reinterpret_cast<void**>(out));
+}
 
 // launch bookkeeping
 static inline void count_launch(sdpsr_ctx* ctx, int k = 1) { ctx->launches += k; }

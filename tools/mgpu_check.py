@@ -32,8 +32,9 @@ def main():
     probs = [pr.lovasz_er(7), pr.qap_esc16j(os.path.join("tests", "golden", "esc16j.npz")), pr.kneser(10, 4),
              pr.hamming(3, 8), pr.synthetic_product_scheme(3, 3, 16), pr.hamming(5, 4)]
     ok_all = True
+    flags = int(os.environ.get("SDPSR_MGPU_FLAGS", "0"))      # 32 = exchange with NCCL broadcasts instead of peer stores
     for prob in probs:
-        ctx = B.Context(prob.n, local, 0)
+        ctx = B.Context(prob.n, local, flags)
         box = [B.Context.comm_unique_id() if rank == 0 else None]     # one NCCL id per communicator
         dist.broadcast_object_list(box, src=0)
         ctx.comm_init(world, rank, box[0])
@@ -61,7 +62,7 @@ def main():
                         "sizes": same_sizes, "blk_err": err, "all_ranks_ok": bool(flag.item())})
         ctx.close()
     if rank == 0:
-        print(json.dumps({"world": world, "ok": ok_all, "results": results}), flush=True)
+        print(json.dumps({"world": world, "flags": flags, "ok": ok_all, "results": results}), flush=True)
     dist.destroy_process_group()
     return 0 if ok_all else 1
 
