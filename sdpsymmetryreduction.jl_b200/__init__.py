@@ -16,6 +16,7 @@ from .api import (  # noqa: F401
     admissible_subspace,
     basis_image,
     blockDiagonalize,
+    clear_context_pool,
     desymmetrize,
     diagonalize,
     dim,

@@ -49,6 +49,45 @@ class DimensionMismatch(Exception):
     """thrown by check_block_sizes, src/diagonalize.jl:1-23"""
 
 
+# ----------------------------------------------------------------------------
+# context pool: device buffers (and the cuSOLVER workspace) are reused across calls of the same
+# shape instead of being cudaMalloc'ed / cudaFree'd per call (like a caching allocator)
+# ----------------------------------------------------------------------------
+_CTX_POOL: dict = {}
+_POOL_PER_KEY = 1
+
+
+def _acquire_context(n: int, device: int = 0, flags: int = 0) -> B.Context:
+    lst = _CTX_POOL.get((int(n), int(device), int(flags)))
+    while lst:
+        ctx = lst.pop()
+        if getattr(ctx, "_h", None):
+            ctx.reset()
+            ctx._constraints_set = False
+            return ctx
+    return B.Context(n, device, flags)
+
+
+def _release_context(ctx: Optional[B.Context]):
+    if ctx is None or not getattr(ctx, "_h", None):
+        return
+    if ctx.comm_info()[0] > 1:           # contexts that carry a communicator belong to their creator
+        return
+    lst = _CTX_POOL.setdefault((ctx.n, ctx.device, ctx.flags), [])
+    if len(lst) < _POOL_PER_KEY:
+        lst.append(ctx)
+    else:
+        ctx.close()
+
+
+def clear_context_pool():
+    """Free the device memory held by pooled contexts."""
+    for lst in _CTX_POOL.values():
+        for ctx in lst:
+            ctx.close()
+    _CTX_POOL.clear()
+
+
 def _default_rand():
     rng = np.random.default_rng()
     return lambda n: rng.random(int(n))
@@ -101,16 +140,16 @@ class Partition:
         if ctx is not None and getattr(ctx, "_h", None):
             return ctx
         n = self.matrix.shape[0]
-        ctx = B.Context(n, self.device, flags)
+        ctx = _acquire_context(n, self.device, flags)
         d = ctx.set_labels(self.matrix)
         assert d == self.nparts, (d, self.nparts)
         self._ctx = ctx
         return ctx
 
     def release(self):
-        """Free the device state kept alive for follow-up calls."""
+        """Give the device state kept alive for follow-up calls back to the context pool."""
         if self._ctx is not None:
-            self._ctx.close()
+            _release_context(self._ctx)
             self._ctx = None
 
 
@@ -163,7 +202,7 @@ def admissible_subspace(C, A, b, *, verbose: bool = False, atol: float = RTOL_DE
         raise AssertionError("n^2 == length(C)")                    # :118
     own = ctx is None
     if own:
-        ctx = B.Context(n, device, flags)
+        ctx = _acquire_context(n, device, flags)
     t0 = time.perf_counter()
     if init_elements is None:
         ctx.set_constraints(A)
@@ -210,7 +249,7 @@ def admissible_subspace(C, A, b, *, verbose: bool = False, atol: float = RTOL_DE
         raise
     P = Partition(ctx.dim(), labels, device=device, _ctx=ctx if keep_context else None)
     if own and not keep_context:
-        ctx.close()
+        _release_context(ctx)
     return P
 
 
@@ -222,7 +261,7 @@ def desymmetrize(P: Partition, *, verbose: bool = False, atol: float = RTOL_DEFA
     """WL-style closure under products X*Y (src/partitions.jl:197-223)."""
     rand = rand or _default_rand()
     n = P.matrix.shape[0]
-    ctx = B.Context(n, P.device)                 # deepcopy(P): never touch P's own context
+    ctx = _acquire_context(n, P.device)          # deepcopy(P): never touch P's own context
     cur = ctx.set_labels(P.matrix)
     it = 0
     while True:

@@ -144,6 +144,7 @@ class Context:
         self.lib = load_library()
         self.n = int(n)
         self.device = device
+        self.flags = int(flags)
         self._h = _p()
         st = self.lib.sdpsr_create(C.byref(self._h), self.n, device, flags)
         if st != OK:

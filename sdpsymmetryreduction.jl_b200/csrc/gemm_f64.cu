@@ -83,6 +83,7 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
 
 // lower==1: only tiles with tile_m >= tile_n are launched (C symmetric); the strictly lower
 // tiles are mirrored into the upper triangle by mirror_kernel afterwards.
+template <bool PEERS>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 double* __restrict__ C, int64_t ldc, int M, int Nc, int K, int tiles_m, int tiles_n, int lower,
@@ -217,7 +218,7 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int n = n0 + wn * 32 + j * 8 + (nslot & 3) * 2 + (nslot >> 2);
         if (m < M && n < Nc) {
           const int64_t off = (int64_t)m + ldc * (int64_t)n;
-          if (peers) {
+          if (PEERS) {
             // fused exchange: the tile goes straight into every rank's copy of C (own copy included)
             // over NVLink peer mappings, while the other CTAs are still computing
 #pragma unroll 1
@@ -302,7 +303,8 @@ int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B
   static bool attr_set_dev[64] = {false};      // the attribute is per device
   bool& attr_set = attr_set_dev[ctx->device & 63];
   if (!attr_set) {
-    SDPSR_CUDA(cudaFuncSetAttribute(gemm_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SDPSR_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SDPSR_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
   CUtensorMap tmA, tmB;
@@ -340,9 +342,12 @@ int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B
     Timed tm(ctx, SDPSR_K_GEMM, (lower || sharded) ? 2.0 * (double)ntiles * BM * BN * (double)K
                                                    : 2.0 * (double)M * (double)Nc * (double)K);
     if (ntiles) {
-      gemm_f64_kernel<<<(unsigned)ntiles, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, C, ldc, (int)M, (int)Nc, (int)K,
-                                                                             tiles_m, tiles_n, lower ? 1 : 0, d_tiles, accum,
-                                                                             peers, ctx->nranks);
+      if (peers)
+        gemm_f64_kernel<true><<<(unsigned)ntiles, THREADS, SMEM_BYTES, ctx->stream>>>(
+            tmA, tmB, C, ldc, (int)M, (int)Nc, (int)K, tiles_m, tiles_n, lower ? 1 : 0, d_tiles, accum, peers, ctx->nranks);
+      else
+        gemm_f64_kernel<false><<<(unsigned)ntiles, THREADS, SMEM_BYTES, ctx->stream>>>(
+            tmA, tmB, C, ldc, (int)M, (int)Nc, (int)K, tiles_m, tiles_n, lower ? 1 : 0, d_tiles, accum, nullptr, 1);
       count_launch(ctx);
     }
   }
