@@ -77,3 +77,16 @@ def test_problem_generators():
     assert p.n == 64 and p.A.shape == (8, 4096) and p.expected_dim == 27
     ps = S.problems.hamming(2, 8, sparse=True)
     assert np.array_equal(ps.A.toarray(), S.problems.hamming(2, 8, sparse=False).A)
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """bench.py --impl reference is CPU-only (oracle port) and must keep working without a GPU."""
+    import subprocess
+    import sys
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload",
+                        "theta-H(3,4)-N64", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "s" and line["higher_is_better"] is False
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
