@@ -339,6 +339,8 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_res, ms_e2e = (float(x) for x in t.tolist())
+    if world > 1:
+        ctx.close()          # collective: every rank unmaps its peers' buffers before anyone frees
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -358,7 +360,7 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
-    g, rf = tim["gemm"], tim["refine"]
+    g, rf = tim["gemm"], tim["refine"]     # read before the context was closed
     gemm_tf = g["work"] / g["ms"] / 1e9 if g["ms"] else None
     ref_gbs = rf["work"] / rf["ms"] / 1e6 if rf["ms"] else None
     h2d = N * N * 8 + int(prob.A.data.nbytes + prob.A.indices.astype(np.int64).nbytes + prob.A.indptr.nbytes)

@@ -165,18 +165,20 @@ static int setup_peer_buffers(sdpsr_ctx* ctx) {
 }
 
 void sdpsr_comm_free(sdpsr_ctx* ctx) {
-  if (ctx->nccl && api().ok) {
-    // peers may still be storing into our buffers: rendezvous before unmapping / freeing anything
-    cudaStreamSynchronize(ctx->stream);
-    if (ctx->d_barrier)
-      api().AllReduce(ctx->d_barrier, ctx->d_barrier, 1, 2, 0, (ncclComm_t)ctx->nccl, ctx->stream);
-    cudaStreamSynchronize(ctx->stream);
-  }
+  // Remote stores only happen inside sharded GEMMs, which end with a cross-rank barrier, so none is in
+  // flight here.  Order: unmap the peers' buffers, rendezvous, and only then let the caller free ours
+  // (freeing exported memory that is still mapped elsewhere is undefined).  Every rank must destroy its
+  // context (collective, like the communicator itself).
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (int b = 0; b < 3; ++b)
     for (int r = 0; r < sdpsr_ctx::MAX_RANKS; ++r) {
       if (ctx->peer_ptr[b][r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->peer_ptr[b][r]);
       ctx->peer_ptr[b][r] = nullptr;
     }
+  if (ctx->nccl && api().ok && ctx->d_barrier) {
+    api().AllReduce(ctx->d_barrier, ctx->d_barrier, 1, 2, 0, (ncclComm_t)ctx->nccl, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+  }
   cudaFree(ctx->d_peer);
   cudaFree(ctx->d_barrier);
   ctx->d_peer = nullptr;
