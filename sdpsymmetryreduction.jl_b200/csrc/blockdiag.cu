@@ -140,42 +140,98 @@ __global__ void qhat_rowmajor_kernel(const double* __restrict__ Qhat, int64_t n,
 }
 
 // --- CSR-by-label (the reference's _constraints, src/diagonalize.jl:42-50) ----------------
+// Persistent CTAs walk whole columns.  Class counters live in shared memory (SM_BINS classes); lanes
+// holding the same class are aggregated with __match_any_sync, so the global atomics drop from one per
+// warp-group per 32 entries to one per class per column (scatter) or per CTA (count).
+constexpr int SM_BINS = 8192;      // class_count: 32 KB of counters
+constexpr int SCAT_BINS = 2048;    // class_scatter: counters + 8-byte bases
+
 __global__ void __launch_bounds__(256) class_count_kernel(const uint32_t* __restrict__ lab,
                                                           const uint32_t* __restrict__ rank, int64_t n, int64_t ld,
-                                                          unsigned long long* __restrict__ cnt) {
-  const int64_t j = blockIdx.y;
-  const int64_t step = (int64_t)gridDim.x * blockDim.x;
-  const int64_t nround = (n + step - 1) / step * step;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += step) {
-    const bool valid = i < n;
-    const uint32_t c = valid ? rank[lab[i + ld * j]] : 0xffffffffu;
-    const unsigned mask = __match_any_sync(0xffffffffu, c);
-    if (valid && c != 0u && (int)(__ffs(mask) - 1) == (int)(threadIdx.x & 31))
-      atomicAdd(cnt + c, (unsigned long long)__popc(mask));
+                                                          unsigned long long* __restrict__ cnt, int64_t nbins) {
+  __shared__ uint32_t bins[SM_BINS];
+  const bool smem = nbins <= SM_BINS;
+  if (smem) {
+    for (int i = threadIdx.x; i < nbins; i += blockDim.x) bins[i] = 0u;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int64_t nround = (n + blockDim.x - 1) / blockDim.x * blockDim.x;      // warp-uniform trip count
+  for (int64_t j = blockIdx.x; j < n; j += gridDim.x) {
+    for (int64_t i = threadIdx.x; i < nround; i += blockDim.x) {
+      const bool valid = i < n;
+      uint32_t c = valid ? lab[i + ld * j] : 0xffffffffu;
+      if (valid && rank) c = rank[c];
+      const unsigned mask = __match_any_sync(0xffffffffu, c);
+      if (valid && c < (uint32_t)nbins && (int)(__ffs(mask) - 1) == lane) {
+        if (smem) {
+          // a column has < 2^32 entries, but a CTA's share of the matrix may not: flush on the way
+          const uint32_t old = atomicAdd(&bins[c], (uint32_t)__popc(mask));
+          if (old > 0xf0000000u) {
+            atomicAdd(cnt + c, (unsigned long long)atomicExch(&bins[c], 0u));
+          }
+        } else {
+          atomicAdd(cnt + c, (unsigned long long)__popc(mask));
+        }
+      }
+    }
+  }
+  if (smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nbins; i += blockDim.x)
+      if (bins[i]) atomicAdd(cnt + i, (unsigned long long)bins[i]);
   }
 }
 
+// rows/cols of every entry, grouped by class: cursor[c] is the next free position of class c
 __global__ void __launch_bounds__(256) class_scatter_kernel(const uint32_t* __restrict__ lab,
                                                             const uint32_t* __restrict__ rank, int64_t n, int64_t ld,
                                                             unsigned long long* __restrict__ cursor,
-                                                            uint32_t* __restrict__ rows, uint32_t* __restrict__ cols) {
-  const int64_t j = blockIdx.y;
-  const int64_t step = (int64_t)gridDim.x * blockDim.x;
-  const int64_t nround = (n + step - 1) / step * step;
+                                                            uint32_t* __restrict__ rows, uint32_t* __restrict__ cols,
+                                                            int64_t nbins) {
+  __shared__ uint32_t s_cnt[SCAT_BINS];
+  __shared__ unsigned long long s_base[SCAT_BINS];
+  const bool smem = nbins <= SCAT_BINS;
   const int lane = threadIdx.x & 31;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += step) {
-    const bool valid = i < n;
-    const uint32_t c = valid ? rank[lab[i + ld * j]] : 0xffffffffu;
-    const unsigned mask = __match_any_sync(0xffffffffu, c);
-    const int leader = __ffs(mask) - 1;
-    unsigned long long basepos = 0ull;
-    if (valid && c != 0u && lane == leader) basepos = atomicAdd(cursor + c, (unsigned long long)__popc(mask));
-    basepos = __shfl_sync(0xffffffffu, basepos, leader);
-    if (valid && c != 0u) {
-      const unsigned long long pos = basepos + __popc(mask & ((1u << lane) - 1u));
-      rows[pos] = (uint32_t)i;
-      cols[pos] = (uint32_t)j;
+  const int64_t nround = (n + blockDim.x - 1) / blockDim.x * blockDim.x;
+  for (int64_t j = blockIdx.x; j < n; j += gridDim.x) {
+    if (smem) {
+      for (int i = threadIdx.x; i < nbins; i += blockDim.x) s_cnt[i] = 0u;
+      __syncthreads();
+      // phase 1: class sizes inside this column
+      for (int64_t i = threadIdx.x; i < nround; i += blockDim.x) {
+        const bool valid = i < n;
+        const uint32_t c = valid ? rank[lab[i + ld * j]] : 0xffffffffu;
+        const unsigned mask = __match_any_sync(0xffffffffu, c);
+        if (valid && c != 0u && (int)(__ffs(mask) - 1) == lane) atomicAdd(&s_cnt[c], (uint32_t)__popc(mask));
+      }
+      __syncthreads();
+      // phase 2: one global reservation per class present in the column
+      for (int i = threadIdx.x; i < nbins; i += blockDim.x) {
+        const uint32_t k = s_cnt[i];
+        if (k) s_base[i] = atomicAdd(cursor + i, (unsigned long long)k);
+        s_cnt[i] = 0u;                                   // becomes the running offset of phase 3
+      }
+      __syncthreads();
     }
+    // phase 3: place the entries
+    for (int64_t i = threadIdx.x; i < nround; i += blockDim.x) {
+      const bool valid = i < n;
+      const uint32_t c = valid ? rank[lab[i + ld * j]] : 0xffffffffu;
+      const unsigned mask = __match_any_sync(0xffffffffu, c);
+      const int leader = __ffs(mask) - 1;
+      unsigned long long basepos = 0ull;
+      if (valid && c != 0u && lane == leader)
+        basepos = smem ? s_base[c] + atomicAdd(&s_cnt[c], (uint32_t)__popc(mask))
+                       : atomicAdd(cursor + c, (unsigned long long)__popc(mask));
+      basepos = __shfl_sync(0xffffffffu, basepos, leader);
+      if (valid && c != 0u) {
+        const unsigned long long pos = basepos + __popc(mask & ((1u << lane) - 1u));
+        rows[pos] = (uint32_t)i;
+        cols[pos] = (uint32_t)j;
+      }
+    }
+    if (smem) __syncthreads();
   }
 }
 
@@ -571,8 +627,8 @@ extern "C" int sdpsr_basis_image(sdpsr_ctx* ctx, double atol, double* out, int64
   unsigned long long* d_cnt = nullptr;
   SDPSR_TRY(sdpsr_scratch_t(ctx, 0, (size_t)d + 2, &d_cnt));
   SDPSR_CUDA(cudaMemsetAsync(d_cnt, 0, ((size_t)d + 2) * 8, ctx->stream));
-  const dim3 g2((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)n);
-  class_count_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->labels, t.rank, n, ld, d_cnt);
+  const unsigned g2 = (unsigned)std::min<int64_t>(n, (int64_t)ctx->sm_count * 8);
+  class_count_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->labels, t.rank, n, ld, d_cnt, d + 1);
   count_launch(ctx);
   std::vector<unsigned long long> cnt((size_t)d + 2);
   SDPSR_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, cnt.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -585,7 +641,7 @@ extern "C" int sdpsr_basis_image(sdpsr_ctx* ctx, double atol, double* out, int64
   SDPSR_TRY(sdpsr_scratch_t(ctx, 1, std::max<size_t>(1, (size_t)nent) * 2, &d_rc));
   uint32_t* d_rows = d_rc;
   uint32_t* d_cols = d_rc + nent;
-  class_scatter_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->labels, t.rank, n, ld, d_cnt, d_rows, d_cols);
+  class_scatter_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->labels, t.rank, n, ld, d_cnt, d_rows, d_cols, d + 1);
   count_launch(ctx);
   // chunks: class i owns chunks [cstart[i], cstart[i+1])
   std::vector<unsigned long long> cbeg, cend;
@@ -1162,8 +1218,8 @@ extern "C" int sdpsr_basis_image_complex(sdpsr_ctx* ctx, double atol, double* ou
   unsigned long long* d_cnt = nullptr;
   SDPSR_CUDA(cudaMalloc(&d_cnt, ((size_t)d + 2) * 8));
   SDPSR_CUDA(cudaMemsetAsync(d_cnt, 0, ((size_t)d + 2) * 8, ctx->stream));
-  const dim3 g2((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)n);
-  class_count_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->labels, t.rank, n, ld, d_cnt);
+  const unsigned g2 = (unsigned)std::min<int64_t>(n, (int64_t)ctx->sm_count * 8);
+  class_count_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->labels, t.rank, n, ld, d_cnt, d + 1);
   std::vector<unsigned long long> cnt((size_t)d + 2);
   SDPSR_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, cnt.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
   SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1175,7 +1231,7 @@ extern "C" int sdpsr_basis_image_complex(sdpsr_ctx* ctx, double atol, double* ou
   SDPSR_CUDA(cudaMalloc(&d_rc, std::max<size_t>(1, (size_t)nent) * 8));
   uint32_t* d_rows = d_rc;
   uint32_t* d_cols = d_rc + nent;
-  class_scatter_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->labels, t.rank, n, ld, d_cnt, d_rows, d_cols);
+  class_scatter_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->labels, t.rank, n, ld, d_cnt, d_rows, d_cols, d + 1);
   count_launch(ctx, 2);
   std::vector<unsigned long long> cbeg, cend;
   std::vector<int64_t> cstart((size_t)d + 2, 0);

@@ -50,18 +50,37 @@ __global__ void relabel_kernel(uint32_t* __restrict__ ids, const uint32_t* __res
     ids[i] = rank[ids[i]];
 }
 
+// cnt[p] = number of matrix entries with pattern id p (padding rows excluded); persistent CTAs over
+// columns with shared-memory bins, lanes of equal id aggregated first
+constexpr int PC_BINS = 8192;
 __global__ void __launch_bounds__(256) pattern_count_kernel(const uint32_t* __restrict__ pid, int64_t n, int64_t ld,
-                                                            unsigned long long* __restrict__ cnt) {
-  // padding rows (i >= n) are excluded: they are not entries of the matrix
-  const int64_t j = blockIdx.y;
-  const int64_t step = (int64_t)gridDim.x * blockDim.x;
-  const int64_t nround = (n + step - 1) / step * step;     // warp-uniform trip count
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += step) {
-    const bool valid = i < n;
-    const uint32_t p = valid ? pid[i + ld * j] : 0xffffffffu;
-    const unsigned mask = __match_any_sync(0xffffffffu, p);
-    if (valid && (int)(__ffs(mask) - 1) == (int)(threadIdx.x & 31))
-      atomicAdd(cnt + p, (unsigned long long)__popc(mask));
+                                                            unsigned long long* __restrict__ cnt, int64_t nbins) {
+  __shared__ uint32_t bins[PC_BINS];
+  const bool smem = nbins <= PC_BINS;
+  if (smem) {
+    for (int i = threadIdx.x; i < nbins; i += blockDim.x) bins[i] = 0u;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int64_t nround = (n + blockDim.x - 1) / blockDim.x * blockDim.x;     // warp-uniform trip count
+  for (int64_t j = blockIdx.x; j < n; j += gridDim.x)
+    for (int64_t i = threadIdx.x; i < nround; i += blockDim.x) {
+      const bool valid = i < n;
+      const uint32_t p = valid ? pid[i + ld * j] : 0xffffffffu;
+      const unsigned mask = __match_any_sync(0xffffffffu, p);
+      if (valid && (int)(__ffs(mask) - 1) == lane) {
+        if (smem) {
+          const uint32_t old = atomicAdd(&bins[p], (uint32_t)__popc(mask));
+          if (old > 0xf0000000u) atomicAdd(cnt + p, (unsigned long long)atomicExch(&bins[p], 0u));
+        } else {
+          atomicAdd(cnt + p, (unsigned long long)__popc(mask));
+        }
+      }
+    }
+  if (smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nbins; i += blockDim.x)
+      if (bins[i]) atomicAdd(cnt + i, (unsigned long long)bins[i]);
   }
 }
 
@@ -437,8 +456,8 @@ int sdpsr_constraints_finalize(sdpsr_ctx* ctx) {
   unsigned long long* dcnt = nullptr;
   SDPSR_TRY(sdpsr_scratch_t(ctx, 0, (size_t)npat + 1, &dcnt));
   SDPSR_CUDA(cudaMemsetAsync(dcnt, 0, ((size_t)npat + 1) * 8, ctx->stream));
-  pattern_count_kernel<<<dim3((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)n), 256, 0, ctx->stream>>>(
-      c.d_pid, n, ld, dcnt);
+  pattern_count_kernel<<<(unsigned)std::min<int64_t>(n, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(
+      c.d_pid, n, ld, dcnt, npat + 1);
   count_launch(ctx);
   std::vector<unsigned long long> cnt((size_t)npat + 1);
   SDPSR_CUDA(cudaMemcpyAsync(cnt.data(), dcnt, cnt.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
