@@ -1,0 +1,110 @@
+"""The reference's own test-suite, transliterated assertion by assertion and run through the
+GPU path (public API -> C ABI -> CUDA).  File/line comments point at the Julia originals.
+SDP objective values (JuMP + CSDP) are replaced by the solver-free spectrum invariant."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import sdpsr_b200 as S
+from sdpsr_b200 import problems as pr
+from sdpsr_b200.api import _constraints, check_block_sizes, eigen_decomposition
+
+from conftest import GOLDEN, Coeffs
+
+pytestmark = pytest.mark.gpu
+SR = S
+dim = S.dim
+part = S.Partition                                   # src/compat.jl:11
+coarsestPart = S.refine                              # src/compat.jl:12
+rndPart = lambda P: S.randomize(P, Coeffs(0))        # src/compat.jl:13
+
+
+def spectrum_invariant(P, blkSizes, blks, mult):
+    x = np.random.default_rng(0).random(P.nparts)
+    big = np.linalg.eigvalsh(np.concatenate([[0.0], x])[P.matrix])
+    small = []
+    for k, s in enumerate(blkSizes):
+        Mk = sum(x[i] * blks[i][k] for i in range(P.nparts))
+        small += list(np.linalg.eigvalsh(Mk)) * mult[k]
+    return np.allclose(sorted(small), big, atol=1e-9)
+
+
+# ------------------------------------------------------------------ test/runtests.jl
+def test_runtests_jl():
+    assert S.api.RTOL_DEFAULT > 1e-10                                     # roundToZero(1e-10) == 0   (:11)
+    rng = np.random.default_rng(0)
+    M = rng.integers(1, 11, size=(10, 10))
+    M[0, 0] = 0
+    assert dim(part(M)) == len(np.unique(M)) - 1                          # :15
+    assert dim(part(M.astype(float))) == len(np.unique(M)) - 1            # :16
+    M = rng.integers(1, 11, size=(10, 10))
+    assert dim(part(M)) == len(np.unique(M))                              # :19
+    assert dim(part(M.astype(float))) == len(np.unique(M))                # :20
+    P1 = S.Partition(np.array([[1, 2, 2], [2, 3, 3], [2, 3, 3]]))          # :22
+    P2 = S.Partition(np.array([[1, 1, 2], [1, 1, 2], [1, 1, 3]]))          # :23
+    P3 = S.Partition(np.array([[1, 2, 4], [2, 3, 5], [2, 3, 6]]))          # :24
+    assert coarsestPart(P1, P2) == P3                                     # :25
+    assert part(rndPart(P1)) == P1                                        # :27
+    # unsymmetrization and complex                                        # :39-58
+    assert S.unSymmetrize(P1, rand=Coeffs(1)) == S.Partition(4, np.array([[1, 3, 3], [2, 4, 4], [2, 4, 4]]))   # :40
+    P = S.Partition(3, np.array([[1, 2, 3, 2], [2, 1, 2, 3], [3, 2, 1, 2], [2, 3, 2, 1]], dtype=np.uint32))     # :43
+    X = S.randomize(P, Coeffs(2))
+    assert np.array_equal(X, X.T)                                         # issymmetric        :45
+    assert S.blockDiagonalize(P, True, complex=True, rand=Coeffs(3)).blkSizes == [1, 1, 1]    # :47
+    P3c = S.Partition(np.array([[1, 3, 2], [2, 1, 3], [3, 2, 1]]))         # :50-55
+    with pytest.raises(S.InvalidDecompositionField):
+        S.blockDiagonalize(P3c, rand=Coeffs(4))                           # :56
+    assert S.blockDiagonalize(P3c, complex=True, rand=Coeffs(5)).blkSizes == [1, 1, 1]        # :57
+
+
+# ------------------------------------------------------------------ test/lovasz.jl
+@pytest.mark.parametrize("q,expect_dim,expect_blocks", [(3, 12, [2, 2, 3]), (5, 15, [2, 2, 2, 3]),
+                                                         (7, 18, [2, 2, 2, 2, 3])])
+def test_lovasz_jl(q, expect_dim, expect_blocks):
+    CAb = pr.lovasz_er(q)                                                 # Lovászϑ′_ER_graph(q)  :4
+    P = SR.admissible_subspace(*CAb, rand=Coeffs(q))                      # :5
+    assert SR.dim(P) == expect_dim                                        # :6
+    Q_hat = SR.diagonalize(P, rand=Coeffs(q + 1))                         # :7
+    assert sorted(qk.shape[1] for qk in Q_hat) == expect_blocks           # :8
+    # opt_model(P, Q_hat, CAb) + CSDP (:10-16) -> reduced data + spectrum invariant
+    newA, newB, newC = SR.reduce_problem(P, CAb.C, CAb.A, CAb.b)
+    assert newA.shape == (2, expect_dim) and newC.sum() == CAb.n ** 2
+    blks = SR.basis_image(Q_hat, P)
+    mult = [int(P._ptrs[r + 1] - P._ptrs[r]) for r in dict.fromkeys(P._kroot.tolist())]
+    assert spectrum_invariant(P, [qk.shape[1] for qk in Q_hat], blks, mult)
+    P.release()
+
+
+# ------------------------------------------------------------------ test/qap.jl
+def test_qap_jl():
+    CAb = pr.qap_esc16j(os.path.join(GOLDEN, "esc16j.npz"))               # read_qapdata + QuadraticAssignment :16-18
+    P = SR.admissible_subspace(*CAb, verbose=True, rand=Coeffs(1))        # :19
+    assert SR.dim(P) == 150                                               # :20
+    Q_hat = SR.diagonalize(P, verbose=True, rand=Coeffs(2))               # :22
+    assert sorted(qk.shape[1] for qk in Q_hat) == [1] * 10 + [7] * 5      # :23
+    check_block_sizes([qk.shape[1] for qk in Q_hat], P)
+    cs = _constraints(P)                                                  # used by opt_model   test/sd_problems.jl:113
+    assert len(cs) == 150 and sum(len(c) for c in cs) == 256 * 256
+    blks = SR.basis_image(Q_hat, P)
+    mult = [int(P._ptrs[r + 1] - P._ptrs[r]) for r in dict.fromkeys(P._kroot.tolist())]
+    assert spectrum_invariant(P, [qk.shape[1] for qk in Q_hat], blks, mult)
+    P.release()
+
+
+# ------------------------------------------------------------------ test/numerical_issues.jl
+def test_numerical_issues_jl():
+    Pm = np.load(os.path.join(GOLDEN, "numerical_issues_P.npy"))
+    prt = SR.Partition(Pm)                                                # :70
+    c = Coeffs(7)
+    N, eps = 200, 1e-7                                                    # 10_000 in the reference (:91)
+    res = (N, None)
+    for it in range(1, N + 1):                                            # try_fail_eigen_decomposition :72-89
+        try:
+            eigen_decomposition(prt, atol=eps, rand=c)
+        except Exception as err:                                          # noqa: BLE001
+            res = (it, err)
+            break
+    assert res == (N, None)                                               # :94
+    prt.release()
