@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sdpsr", choices=["sdpsr", "reference"])
     ap.add_argument("--workload", default=os.environ.get("SDPSR_BENCH_WORKLOAD", "theta-H(7,4)-N16384"))
+    ap.add_argument("--eig", default="auto", choices=["auto", "syevd", "krylov"],
+                    help="blockDiagonalize path: auto (default API behaviour), syevd (the reference's algorithm "
+                         "step by step through cuSOLVER), krylov (matrix-free variant only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     return ap.parse_args()
@@ -129,21 +132,23 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------
 # the job
 # ----------------------------------------------------------------------------------
-def job_resident(S, B, ctx, prob, C_dev, seed=20260101):
+def job_resident(S, B, ctx, prob, C_dev, seed=20260101, eig="auto"):
     """Whole job with C already in HBM and the partition left on the device."""
     rand = Coeffs(seed)
     tr = {}
     P = S.admissible_subspace(C_dev, prob.A, prob.b, rand=rand, ctx=ctx, fetch_labels=False, trace=tr)
-    bd = S.blockDiagonalize(P, False, rand=rand)
+    bd = S.blockDiagonalize(P, False, rand=rand, eig=eig)
+    tr["eig_mode"] = P._eig_mode
+    tr["blk00"] = [float(bd.blks[i][0][0, 0]) for i in range(P.nparts)]
     return P.nparts, list(bd.blkSizes), tr
 
 
-def job_e2e(S, B, prob, C_pinned, labels_pinned, seed=20260101, ctx=None):
+def job_e2e(S, B, prob, C_pinned, labels_pinned, seed=20260101, ctx=None, eig="auto"):
     """The public API with host buffers: the call a user makes.  With several GPUs the caller
     owns a context that carries the NCCL communicator and passes it in."""
     rand = Coeffs(seed)
     P = S.admissible_subspace(C_pinned, prob.A, prob.b, rand=rand, labels_out=labels_pinned, ctx=ctx)
-    bd = S.blockDiagonalize(P, False, rand=rand)
+    bd = S.blockDiagonalize(P, False, rand=rand, eig=eig)
     launches = P._ctx.launch_count()
     if ctx is None:
         P.release()
@@ -299,7 +304,7 @@ def main():
     clocks = ClockSampler(local)
     clocks.start()
     for _ in range(args.warmup):
-        dim, sizes, tr = job_resident(S, B, ctx, prob, C_dev)
+        dim, sizes, tr = job_resident(S, B, ctx, prob, C_dev, eig=args.eig)
     barrier()
     ctx.timing_reset()
     l0 = ctx.launch_count()
@@ -309,7 +314,7 @@ def main():
     for _ in range(args.steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
-        dim, sizes, tr = job_resident(S, B, ctx, prob, C_dev)
+        dim, sizes, tr = job_resident(S, B, ctx, prob, C_dev, eig=args.eig)
         b.record(stream)
         evs.append((a, b))
     barrier()
@@ -317,16 +322,38 @@ def main():
     launches = ctx.launch_count() - l0
     tim = ctx.timing()
 
+    # ---- the same job with the other blockDiagonalize path, for comparison (resident) -----
+    # "syevd" = the reference's algorithm step by step (dense eigen through cuSOLVER).  Both paths
+    # must produce the same blocks from the same coefficient vectors.
+    other = None
+    if tr.get("eig_mode") == "krylov" and args.eig == "auto":
+        ko = min(args.steps, 2)
+        job_resident(S, B, ctx, prob, C_dev, eig="syevd")
+        barrier()
+        evo = []
+        for _ in range(ko):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            dim_o, sizes_o, tr_o = job_resident(S, B, ctx, prob, C_dev, eig="syevd")
+            b.record(stream)
+            evo.append((a, b))
+        barrier()
+        assert dim_o == dim and sizes_o == sizes and tr_o["eig_mode"] == "syevd"
+        diff = float(np.max(np.abs(np.array(tr_o["blk00"]) - np.array(tr["blk00"]))))
+        scale = float(np.max(np.abs(np.array(tr_o["blk00"]))))
+        assert diff <= 1e-8 * max(1.0, scale), ("krylov and syevd blocks differ", diff)
+        other = {"ms": sum(a.elapsed_time(b) for a, b in evo), "steps": ko, "max_block_diff": diff}
+
     # ---- e2e arm: public API, host buffers ------------------------------------------------
     e2e_ctx = ctx if world > 1 else None
     for _ in range(min(args.warmup, 1)):
-        job_e2e(S, B, prob, C_pinned, labels_pinned, ctx=e2e_ctx)
+        job_e2e(S, B, prob, C_pinned, labels_pinned, ctx=e2e_ctx, eig=args.eig)
     barrier()
     evs = []
     for _ in range(args.steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
-        dim_e, sizes_e, l_e2e = job_e2e(S, B, prob, C_pinned, labels_pinned, ctx=e2e_ctx)
+        dim_e, sizes_e, l_e2e = job_e2e(S, B, prob, C_pinned, labels_pinned, ctx=e2e_ctx, eig=args.eig)
         b.record(stream)
         evs.append((a, b))
     barrier()
@@ -335,10 +362,10 @@ def main():
     assert dim_e == dim and sizes_e == sizes
     assert dim == prob.expected_dim and sorted(sizes) == prob.expected_blocks, (dim, sizes)
 
-    t = torch.tensor([ms_res, ms_e2e], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms_res, ms_e2e, other["ms"] if other else 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_res, ms_e2e = (float(x) for x in t.tolist())
+    ms_res, ms_e2e, ms_other = (float(x) for x in t.tolist())
     if world > 1:
         ctx.close()          # collective: every rank unmaps its peers' buffers before anyone frees
     if rank != 0:
@@ -370,10 +397,11 @@ def main():
         "ms_per_step": ms_res / K, "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "N": N, "m": 2, "dim": dim, "blocks": sizes,
-                   "iterations": tr.get("iterations"), "atol": ATOL,
+                   "iterations": tr.get("iterations"), "atol": ATOL, "eig": tr.get("eig_mode"),
                    "l2": "inputs larger than L2 (X is %.1f GB)" % (N * N * 8 / 1e9),
-                   "parallelism": ("GEMM tile-columns sharded over %d ranks (NCCL broadcast exchange), streaming "
-                                   "passes replicated, syevd on rank 0" % world) if world > 1 else "single GPU"},
+                   "parallelism": ("GEMM tile-columns sharded over %d ranks (tiles exchanged from the GEMM epilogue "
+                                   "over NVLink peer memory), streaming passes and the eigen step replicated / on "
+                                   "rank 0" % world) if world > 1 else "single GPU"},
         "e2e": {"value": sec_e2e, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "clocks": clk,
@@ -391,6 +419,11 @@ def main():
         "fp64_tflops": gemm_tf,
         "kernel_ms_per_step": {k: v["ms"] / K for k, v in tim.items() if v["launches"]},
     }
+    if other:
+        line["syevd_path"] = {"value": ms_other / other["steps"] / 1e3, "unit": "s", "steps": other["steps"],
+                              "max_block_diff_vs_default_path": other["max_block_diff"],
+                              "note": "same job, same coefficient vectors, blockDiagonalize forced onto the dense "
+                                      "eigendecomposition (cuSOLVER Xsyevd): the reference's algorithm step by step"}
     if not args.no_cpu_baseline and world == 1:
         try:
             cb = cpu_reference_estimate(args.workload, budget_s=args.cpu_budget_s, iters=tr.get("iterations"))

@@ -50,7 +50,9 @@ typedef enum sdpsr_status {
   SDPSR_E_STATE = -8,          /* call sequence error (e.g. square before fill)         */
   SDPSR_E_SINGULAR = -9,       /* constraint rows linearly dependent (Gram singular)    */
   SDPSR_E_NCCL = -10,          /* NCCL failure / NCCL library not loadable              */
-  SDPSR_E_UNSUPPORTED = -11    /* valid request outside this build's limits             */
+  SDPSR_E_UNSUPPORTED = -11,   /* valid request outside this build's limits             */
+  SDPSR_E_KRYLOV = -12         /* the Krylov block-diagonalisation path is not applicable
+                                  (no clean Lanczos breakdown): run the dense path      */
 } sdpsr_status;
 
 /* flags for sdpsr_create */
@@ -78,7 +80,8 @@ typedef enum sdpsr_status {
 #define SDPSR_K_EIG 5      /* cuSOLVER syevd (library)                            */
 #define SDPSR_K_BASIS 6    /* basis_image reduction                               */
 #define SDPSR_K_MISC 7     /* everything else (transpose, norms, ...)             */
-#define SDPSR_K_COUNT 8
+#define SDPSR_K_KRYLOV 8   /* label-matrix x vector products of the Krylov path   */
+#define SDPSR_K_COUNT 9
 
 /* ------------------------------------------------------------------ lifetime */
 int sdpsr_version(void);
@@ -181,6 +184,28 @@ int sdpsr_set_qhat(sdpsr_ctx* ctx, const double* qhat, const int64_t* blk_sizes,
  *   for i in 0..dim-1, for k in 0..nblk-1: Qhat_k' * 1[S==i+1] * Qhat_k  (s_k x s_k, col-major)
  * with |entries| < atol clamped to 0.  out_len must be dim * sum(s_k^2).              */
 int sdpsr_basis_image(sdpsr_ctx* ctx, double atol, double* out, int64_t out_len);
+
+/* ------------------------------------------ blockDiagonalize, Krylov variant
+ * Same results as sdpsr_eig / sdpsr_block_norms / sdpsr_irreducible (i.e. as
+ * src/eigen_decomposition.jl:236-348) for partitions whose generic element has FEW distinct
+ * eigenvalues, at the cost of O(ne) label-matrix x vector products instead of an O(N^3) `eigen`:
+ * Lanczos on A1 = fill(S, r1) breaks down after ne = #eigenspaces steps and its Ritz vectors are one
+ * unit eigenvector per eigenspace -- all the reference ever uses (first column of the root
+ * eigenspace, :311-314, and projections of A3 times it, :327-336).  Self-validating: every entry
+ * point returns SDPSR_E_KRYLOV when a clean breakdown / integer multiplicities / matching Ritz
+ * values are not observed; the caller then runs the dense entry points with the same r1, r2, r3.
+ *
+ * sdpsr_eig_krylov: vals[0..ne) = distinct eigenvalues of A1 ascending, mult[i] = dim E_i
+ *   (sum = N); vals and mult need room for max_steps entries; tol = relative breakdown
+ *   threshold (beta <= tol * ||A1||), 1e-10 recommended.  max_steps is capped at 48.
+ * sdpsr_block_norms_krylov: norms (ne x ne, column-major) = ||P_j A2 y_i|| for eigenspaces of
+ *   equal dimension, else 0 -- the stand-in for block_norms(Q'A2Q, Inf) (:177-204).
+ * sdpsr_irreducible_krylov: as sdpsr_irreducible, with the eigenspaces of sdpsr_eig_krylov.      */
+int sdpsr_eig_krylov(sdpsr_ctx* ctx, const double* r1, int64_t len, int64_t max_steps, double tol,
+                     double* vals, int64_t* mult, int64_t* ne);
+int sdpsr_block_norms_krylov(sdpsr_ctx* ctx, const double* r2, int64_t len, double* norms);
+int sdpsr_irreducible_krylov(sdpsr_ctx* ctx, const double* r3, int64_t len, const int64_t* kroot,
+                             double atol, int64_t* blk_sizes, int64_t* nblk);
 
 /* ---------------------------------------------------------------- complex path
  * diagonalize(ComplexF64, P) (src/diagonalize.jl:25-40, src/compat.jl:46-68) for partitions that are

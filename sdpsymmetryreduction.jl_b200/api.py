@@ -369,6 +369,37 @@ def _isomorphism_classes(norms: np.ndarray, atol: float) -> np.ndarray:
 # ----------------------------------------------------------------------------
 # diagonalize / basis_image / blockDiagonalize
 # ----------------------------------------------------------------------------
+# Largest dim(P) for which ``eig="auto"`` tries the Krylov variant first (ne <= dim(P); a clean Lanczos
+# breakdown is only observed for about a dozen eigenspaces, and a failed attempt costs <= 48 label-matrix
+# x vector products -- a few ms at N = 16384 against seconds for syevd).
+KRYLOV_AUTO_MAX_DIM = 64
+EIG_MODES = ("auto", "syevd", "krylov")
+
+
+class _Draws:
+    """Records the coefficient vectors drawn from ``rand`` so that a second attempt (the dense path
+    after an inapplicable Krylov attempt) consumes the SAME vectors and the caller's generator
+    advances exactly as in the reference (three draws per ``diagonalize``)."""
+
+    def __init__(self, rand):
+        self.rand = rand
+        self.vals = []
+        self.pos = 0
+
+    def __call__(self, n):
+        if self.pos < len(self.vals):
+            v = self.vals[self.pos]
+            assert v.size == int(n)
+        else:
+            v = np.asarray(self.rand(n), dtype=np.float64)
+            self.vals.append(v)
+        self.pos += 1
+        return v
+
+    def rewind(self):
+        self.pos = 0
+
+
 def eigen_decomposition(P: Partition, *, atol: float, rand: Callable, ctx: Optional[B.Context] = None):
     """src/eigen_decomposition.jl:236-273. Returns (values, ptrs, kroot); Q stays on the device."""
     ctx = ctx or P._context()
@@ -386,25 +417,84 @@ def eigen_decomposition(P: Partition, *, atol: float, rand: Callable, ctx: Optio
     return vals, ptrs, kroot
 
 
+class _KrylovNotApplicable(Exception):
+    pass
+
+
+def _diagonalize_krylov(P: Partition, ctx: B.Context, atol: float, rand: Callable):
+    """The same three steps on one vector per eigenspace (csrc/krylov.cu).  Raises
+    ``_KrylovNotApplicable`` when the device reports no clean Lanczos breakdown."""
+    try:
+        vals, mult = ctx.eig_krylov(rand(P.nparts))                  # :242-254
+        if vals.size > 1 and np.min(np.diff(vals)) <= atol:          # the reference would merge these (:19-40)
+            raise _KrylovNotApplicable("distinct eigenvalues closer than atol")
+        ptrs = np.concatenate([[0], np.cumsum(mult)]).astype(np.int64)
+        norms = ctx.block_norms_krylov(rand(P.nparts), vals.size)    # :259, :203-204
+        kroot = _isomorphism_classes(norms, atol)
+        sizes = ctx.irreducible_krylov(rand(P.nparts), kroot, atol)  # :306, clamptol! :39
+    except B.SdpsrError as e:
+        if e.code == B.E_NOT_SYMMETRIC:
+            raise InvalidDecompositionField(
+                "Decomposition over Float64 was requested but eigenvalues of type ComplexF64 were found. "
+                "Consider calling `diagonalize` with ComplexF64 as its first argument.") from e
+        if e.code == B.E_KRYLOV:
+            raise _KrylovNotApplicable(e.msg) from e
+        raise
+    return ptrs, kroot, sizes
+
+
 def diagonalize(P: Partition, *, verbose: bool = False, atol: Optional[float] = None,
                 rand: Optional[Callable] = None, complex: bool = False,
-                fetch: bool = True, ctx: Optional[B.Context] = None):
-    """``diagonalize(Float64, P)`` (src/diagonalize.jl:25-40): list of N x s_k matrices Q_hat."""
+                fetch: bool = True, ctx: Optional[B.Context] = None, eig: str = "auto"):
+    """``diagonalize(Float64, P)`` (src/diagonalize.jl:25-40): list of N x s_k matrices Q_hat.
+
+    ``eig``: ``"syevd"`` = the reference's algorithm step by step (dense ``eigen`` through cuSOLVER);
+    ``"krylov"`` = the matrix-free variant for partitions with few eigenspaces (same blocks, no dense
+    eigendecomposition; raises if it is not applicable); ``"auto"`` (default) tries the Krylov variant
+    when dim(P) <= KRYLOV_AUTO_MAX_DIM and falls back to ``syevd`` with the same coefficient vectors.
+    ``P._eig_mode`` records the path taken."""
     rand = rand or _default_rand()
+    if eig not in EIG_MODES:
+        raise ValueError(f"eig must be one of {EIG_MODES}")
     if complex:
         return _diagonalize_complex(P, verbose=verbose, atol=atol, rand=rand, fetch=fetch)
     ctx = ctx or P._context()
     n = ctx.n
     if atol is None:
         atol = 1e-12 * n
-    t = time.perf_counter()
-    vals, ptrs, kroot = eigen_decomposition(P, atol=atol, rand=rand, ctx=ctx)
-    if verbose:
-        log.info("Determining eigen-decomposition over Float64... %.3fs", time.perf_counter() - t)
-    t = time.perf_counter()
-    sizes = ctx.irreducible(rand(P.nparts), ptrs, kroot, atol)       # :306, clamptol! :39
-    if verbose:
-        log.info("Determining the algebra-isomorphism... %.3fs", time.perf_counter() - t)
+    draws = _Draws(rand)
+    sizes = None
+    if eig == "krylov" or (eig == "auto" and P.nparts <= KRYLOV_AUTO_MAX_DIM):
+        t = time.perf_counter()
+        try:
+            try:
+                ptrs, kroot, sizes = _diagonalize_krylov(P, ctx, atol, draws)
+            except NumericalInconsistency as e:              # its norms are not the reference's: let the
+                if eig == "krylov":                           # reference's own statistic decide
+                    raise
+                raise _KrylovNotApplicable(str(e)) from e
+            if eig == "auto" and sum(int(x) * (int(x) + 1) // 2 for x in sizes) != P.nparts:
+                raise _KrylovNotApplicable("block sizes do not add up to dim(P)")
+            P._eig_mode = "krylov"
+            if verbose:
+                log.info("Eigenspaces and algebra-isomorphism by Lanczos (%d eigenspaces)... %.3fs",
+                         ptrs.size - 1, time.perf_counter() - t)
+        except _KrylovNotApplicable as e:
+            if eig == "krylov":
+                raise NumericalInconsistency(f"Krylov block-diagonalisation not applicable: {e}") from e
+            log.debug("Krylov path not applicable (%s); using syevd", e)
+            draws.rewind()
+            sizes = None
+    if sizes is None:
+        t = time.perf_counter()
+        vals, ptrs, kroot = eigen_decomposition(P, atol=atol, rand=draws, ctx=ctx)
+        if verbose:
+            log.info("Determining eigen-decomposition over Float64... %.3fs", time.perf_counter() - t)
+        t = time.perf_counter()
+        sizes = ctx.irreducible(draws(P.nparts), ptrs, kroot, atol)      # :306, clamptol! :39
+        if verbose:
+            log.info("Determining the algebra-isomorphism... %.3fs", time.perf_counter() - t)
+        P._eig_mode = "syevd"
     P._blk_sizes = sizes
     P._ptrs, P._kroot = ptrs, kroot
     if not fetch:
@@ -434,7 +524,7 @@ def basis_image(Qhat: List[np.ndarray], P: Partition, *, atol: Optional[float] =
 
 
 def blockDiagonalize(P: Partition, verbose: bool = True, *, epsilon: float = RTOL_DEFAULT,
-                     complex: bool = False, rand: Optional[Callable] = None):
+                     complex: bool = False, rand: Optional[Callable] = None, eig: str = "auto"):
     """src/compat.jl:26-68.  Returns ``(blkSizes, blks)``; ``blks[i][k]`` is the image of
     the basis element ``P.matrix == i+1`` in block k."""
     rand = rand or _default_rand()
@@ -442,7 +532,7 @@ def blockDiagonalize(P: Partition, verbose: bool = True, *, epsilon: float = RTO
         return _block_diagonalize_complex(P, verbose, epsilon, rand)
     ctx = P._context()
     n = ctx.n
-    sizes = diagonalize(P, verbose=verbose, atol=epsilon, rand=rand, fetch=False, ctx=ctx)
+    sizes = diagonalize(P, verbose=verbose, atol=epsilon, rand=rand, fetch=False, ctx=ctx, eig=eig)
     check_block_sizes(sizes, P, False)
     t = time.perf_counter()
     blks = ctx.basis_image(sizes, 1e-12 * n, dim=P.nparts)      # atol default, not epsilon (Appendix C)

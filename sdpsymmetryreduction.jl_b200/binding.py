@@ -19,12 +19,12 @@ _LIB = None
 # status codes (include/sdpsr.h)
 OK = 0
 E_INVALID, E_CUDA, E_NO_DEVICE, E_ALLOC, E_LABEL_OVERFLOW, E_NOT_SYMMETRIC = -1, -2, -3, -4, -5, -6
-E_CUSOLVER, E_STATE, E_SINGULAR, E_NCCL, E_UNSUPPORTED = -7, -8, -9, -10, -11
+E_CUSOLVER, E_STATE, E_SINGULAR, E_NCCL, E_UNSUPPORTED, E_KRYLOV = -7, -8, -9, -10, -11, -12
 
 F_FORCE_BITMAP_RANK, F_TINY_TABLE, F_NO_SMEM_CACHE, F_TIMING, F_NO_SYRK, F_NCCL_EXCHANGE = 1, 2, 4, 8, 16, 32
 MAT_X, MAT_X2, MAT_Q, MAT_W = 0, 1, 2, 3
-K_REFINE, K_GEMM, K_FILL, K_PROJECT, K_RANK, K_EIG, K_BASIS, K_MISC = range(8)
-K_NAMES = ["refine", "gemm", "fill", "project", "rank", "eig", "basis", "misc"]
+K_REFINE, K_GEMM, K_FILL, K_PROJECT, K_RANK, K_EIG, K_BASIS, K_MISC, K_KRYLOV = range(9)
+K_NAMES = ["refine", "gemm", "fill", "project", "rank", "eig", "basis", "misc", "krylov"]
 
 
 class LibraryNotBuilt(RuntimeError):
@@ -70,6 +70,9 @@ _SIGNATURES = {
     "sdpsr_eig": ([_p, _p, _i64, _p], C.c_int),
     "sdpsr_block_norms": ([_p, _p, _i64, _p, _i64, _p], C.c_int),
     "sdpsr_irreducible": ([_p, _p, _i64, _p, _i64, _p, C.c_double, _p, C.POINTER(_i64)], C.c_int),
+    "sdpsr_eig_krylov": ([_p, _p, _i64, _i64, C.c_double, _p, _p, C.POINTER(_i64)], C.c_int),
+    "sdpsr_block_norms_krylov": ([_p, _p, _i64, _p], C.c_int),
+    "sdpsr_irreducible_krylov": ([_p, _p, _i64, _p, C.c_double, _p, C.POINTER(_i64)], C.c_int),
     "sdpsr_get_qhat": ([_p, _p, _i64], C.c_int),
     "sdpsr_set_qhat": ([_p, _p, _p, _i64], C.c_int),
     "sdpsr_basis_image": ([_p, C.c_double, _p, _i64], C.c_int),
@@ -325,6 +328,33 @@ class Context:
         nblk = _i64(0)
         self._check(self.lib.sdpsr_irreducible(self._h, r3.ctypes.data, r3.size, ptrs.ctypes.data, ptrs.size,
                                                kroot.ctypes.data, float(atol), sizes.ctypes.data, C.byref(nblk)))
+        return sizes[:nblk.value].copy()
+
+    # -- Krylov variant (few distinct eigenvalues): raises SdpsrError(E_KRYLOV) when not applicable
+    def eig_krylov(self, r1, max_steps: int = 48, tol: float = 1e-10):
+        """Distinct eigenvalues (ascending) of fill(S, r1) and the dimensions of their eigenspaces."""
+        r1 = _f64(r1)
+        max_steps = int(max(1, min(max_steps, 48)))
+        vals = np.zeros(max_steps, dtype=np.float64)
+        mult = np.zeros(max_steps, dtype=np.int64)
+        ne = _i64(0)
+        self._check(self.lib.sdpsr_eig_krylov(self._h, r1.ctypes.data, r1.size, max_steps, float(tol),
+                                              vals.ctypes.data, mult.ctypes.data, C.byref(ne)))
+        return vals[:ne.value].copy(), mult[:ne.value].copy()
+
+    def block_norms_krylov(self, r2, ne: int) -> np.ndarray:
+        r2 = _f64(r2)
+        norms = np.zeros((ne, ne), dtype=np.float64, order="F")
+        self._check(self.lib.sdpsr_block_norms_krylov(self._h, r2.ctypes.data, r2.size, norms.ctypes.data))
+        return norms
+
+    def irreducible_krylov(self, r3, kroot, atol: float):
+        r3 = _f64(r3)
+        kroot = np.ascontiguousarray(kroot, dtype=np.int64)
+        sizes = np.zeros(kroot.size, dtype=np.int64)
+        nblk = _i64(0)
+        self._check(self.lib.sdpsr_irreducible_krylov(self._h, r3.ctypes.data, r3.size, kroot.ctypes.data,
+                                                      float(atol), sizes.ctypes.data, C.byref(nblk)))
         return sizes[:nblk.value].copy()
 
     def get_qhat(self, sizes) -> list:

@@ -191,6 +191,7 @@ extern "C" int sdpsr_destroy(sdpsr_ctx* ctx) {
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   sdpsr_comm_free(ctx);
   sdpsr_blockdiag_free(ctx);
+  sdpsr_krylov_free(ctx);
   sdpsr_constraints_free(ctx);
   sdpsr_table_free(ctx->tab[0]);
   sdpsr_table_free(ctx->tab[1]);

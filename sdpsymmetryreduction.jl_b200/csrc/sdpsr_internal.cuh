@@ -148,6 +148,9 @@ struct sdpsr_ctx {
   void* solver_hwork = nullptr;
   size_t solver_hwork_bytes = 0;
 
+  // Krylov block-diagonalisation state (opaque here, krylov.cu)
+  void* krylov = nullptr;
+
   // comm (multi-GPU)
   void* nccl = nullptr;
   int nranks = 1, rank = 0;
@@ -257,6 +260,9 @@ int sdpsr_matrix_symmetric(sdpsr_ctx* ctx, const double* x, int* is_sym);
 // blockdiag.cu
 void sdpsr_blockdiag_free(sdpsr_ctx* ctx);
 void sdpsr_blockdiag_rebind(sdpsr_ctx* ctx);
+
+// krylov.cu
+void sdpsr_krylov_free(sdpsr_ctx* ctx);
 
 // comm.cu
 void sdpsr_comm_free(sdpsr_ctx* ctx);

@@ -265,12 +265,18 @@ def test_medium_hamming_closed_form():
 # ---------------------------------------------------------------------------------
 # blockDiagonalize
 # ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("eig", ["syevd", "auto"])
 @pytest.mark.parametrize("prob", small_problems(), ids=lambda p: p.name)
-def test_block_diagonalize_matches_oracle(prob):
+def test_block_diagonalize_matches_oracle(prob, eig):
+    """Same coefficient vectors -> same blocks as the oracle's dense restatement, on the reference's own
+    algorithm (``syevd``) and on the default path (``auto``: Krylov variant where it applies)."""
     Po = O.admissible_subspace(*prob, Coeffs(21))
     Pg = S.Partition(Po.nparts, Po.matrix.astype(np.uint32))
     so, bo = O.blockDiagonalize(Po, Coeffs(22))
-    bd = S.blockDiagonalize(Pg, False, rand=Coeffs(22))
+    cg = Coeffs(22)
+    bd = S.blockDiagonalize(Pg, False, rand=cg, eig=eig)
+    assert cg.draws == [Po.nparts] * 3                  # three draws of dim(P), whatever the path (A.5)
+    assert Pg._eig_mode == "syevd" if eig == "syevd" else Pg._eig_mode in ("krylov", "syevd")
     assert list(bd.blkSizes) == list(so)
     assert sorted(bd.blkSizes) == prob.expected_blocks
     for i in range(Po.nparts):
@@ -279,6 +285,66 @@ def test_block_diagonalize_matches_oracle(prob):
             tol = 1e-8 * max(1.0, np.abs(ref).max())
             assert np.abs(bd.blks[i][k] - ref).max() < tol, (i, k)
     Pg.release()
+
+
+KRYLOV_PROBLEMS = [pr.petersen(), pr.lovasz_er(3), pr.lovasz_er(5), pr.lovasz_er(7), pr.kneser(8, 3),
+                   pr.kneser(10, 4), pr.hamming(3, 8), pr.hamming(5, 4)]
+
+
+@pytest.mark.parametrize("prob", KRYLOV_PROBLEMS, ids=lambda p: p.name)
+def test_krylov_block_diagonalize_matches_oracle_and_dense(prob):
+    """The matrix-free variant (csrc/krylov.cu) must be applicable on these few-eigenspace problems and
+    reproduce the oracle's blocks, block order, multiplicities and the dense path's results."""
+    Po = O.admissible_subspace(*prob, Coeffs(31))
+    so, bo = O.blockDiagonalize(Po, Coeffs(32))
+    Pk = S.Partition(Po.nparts, Po.matrix.astype(np.uint32))
+    Pd = S.Partition(Po.nparts, Po.matrix.astype(np.uint32))
+    bk = S.blockDiagonalize(Pk, False, rand=Coeffs(32), eig="krylov")
+    bdn = S.blockDiagonalize(Pd, False, rand=Coeffs(32), eig="syevd")
+    assert Pk._eig_mode == "krylov" and Pd._eig_mode == "syevd"
+    assert list(bk.blkSizes) == list(bdn.blkSizes) == list(so)
+    assert np.array_equal(Pk._ptrs, Pd._ptrs) and np.array_equal(Pk._kroot, Pd._kroot)
+    for i in range(Po.nparts):
+        for k in range(len(so)):
+            tol = 1e-8 * max(1.0, np.abs(bo[i][k]).max())
+            assert np.abs(bk.blks[i][k] - bo[i][k]).max() < tol, (i, k)
+            assert np.abs(bk.blks[i][k] - bdn.blks[i][k]).max() < tol, (i, k)
+    Qk = S.diagonalize(Pk, rand=Coeffs(33), eig="krylov", atol=1e-9)
+    for q in Qk:                                        # orthonormal columns
+        assert np.allclose(q.T @ q, np.eye(q.shape[1]), atol=1e-9)
+    Pk.release()
+    Pd.release()
+
+
+def test_krylov_not_applicable_falls_back_to_dense():
+    """esc16j has 45 eigenspaces: no clean Lanczos breakdown.  ``eig="krylov"`` reports it, ``auto``
+    (forced to try) lands on the dense path with the same coefficient vectors and the same blocks."""
+    prob = pr.qap_esc16j(os.path.join(GOLDEN, "esc16j.npz"))
+    Po = O.admissible_subspace(*prob, Coeffs(41))
+    so, bo = O.blockDiagonalize(Po, Coeffs(42))
+    P = S.Partition(Po.nparts, Po.matrix.astype(np.uint32))
+    with pytest.raises(S.NumericalInconsistency):
+        S.blockDiagonalize(P, False, rand=Coeffs(42), eig="krylov")
+    import sdpsr_b200.api as api
+    old = api.KRYLOV_AUTO_MAX_DIM
+    api.KRYLOV_AUTO_MAX_DIM = 1 << 20
+    try:
+        cg = Coeffs(42)
+        bd = S.blockDiagonalize(P, False, rand=cg, eig="auto")
+    finally:
+        api.KRYLOV_AUTO_MAX_DIM = old
+    assert P._eig_mode == "syevd" and cg.draws == [150] * 3
+    assert list(bd.blkSizes) == list(so)
+    for i in range(0, Po.nparts, 7):
+        for k in range(len(so)):
+            assert np.abs(bd.blks[i][k] - bo[i][k]).max() < 1e-8 * max(1.0, np.abs(bo[i][k]).max())
+    P.release()
+
+
+def test_krylov_rejects_nonsymmetric(vec):
+    P3 = S.Partition(np.array(vec["C3"]["matrix"]))
+    with pytest.raises(S.InvalidDecompositionField):
+        S.blockDiagonalize(P3, False, rand=Coeffs(1), eig="krylov")
 
 
 def test_diagonalize_default_atol_and_qhat(vec):
@@ -498,14 +564,16 @@ def test_config3_hamming_4_8_full_size():
     P = S.admissible_subspace(*prob, rand=Coeffs(20260101), trace=tr)
     assert P.nparts == 5 and tr["init"] == 2 and tr["iters"] == [(2, 4), (4, 5), (5, 5)]
     assert np.array_equal(P.matrix, pr.hamming_distance_matrix(4, 8).astype(np.uint32) + 1)
-    bd = S.blockDiagonalize(P, False, rand=Coeffs(5))
-    assert bd.blkSizes == [1] * 5
-    mult = sorted(int(P._ptrs[r + 1] - P._ptrs[r]) for r in dict.fromkeys(P._kroot.tolist()))
-    assert mult == [1, 28, 294, 1372, 2401]
     K = pr.krawtchouk(4, 8)
-    got = np.array([[bd.blks[i][k][0, 0] for k in range(5)] for i in range(5)])
-    for k in range(5):
-        assert min(np.abs(K - got[:, [k]]).max(axis=0)) < 1e-8 * np.abs(K).max()
+    for eig in ("krylov", "syevd"):
+        bd = S.blockDiagonalize(P, False, rand=Coeffs(5), eig=eig)
+        assert P._eig_mode == eig
+        assert bd.blkSizes == [1] * 5
+        mult = sorted(int(P._ptrs[r + 1] - P._ptrs[r]) for r in dict.fromkeys(P._kroot.tolist()))
+        assert mult == [1, 28, 294, 1372, 2401]
+        got = np.array([[bd.blks[i][k][0, 0] for k in range(5)] for i in range(5)])
+        for k in range(5):
+            assert min(np.abs(K - got[:, [k]]).max(axis=0)) < 1e-8 * np.abs(K).max()
     P.release()
 
 
