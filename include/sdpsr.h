@@ -64,6 +64,9 @@ typedef enum sdpsr_status {
 #define SDPSR_F_NO_SYRK 16u          /* square with the full GEMM even for symmetric X       */
 #define SDPSR_F_NCCL_EXCHANGE 32u    /* multi-GPU: exchange GEMM tiles with NCCL broadcasts instead
                                         of peer stores from the GEMM epilogue (A/B switch)    */
+#define SDPSR_F_NO_I8 64u            /* never square on the INT8 tensor path (always DMMA)    */
+#define SDPSR_F_FORCE_I8 128u        /* square every symmetric X on the INT8 tensor path, whatever
+                                        N (default: only where it is faster, N >= 2048)       */
 
 /* which device-resident matrix sdpsr_get_matrix / sdpsr_set_matrix address */
 #define SDPSR_MAT_X 0   /* current element X (src/partitions.jl:121)      */
@@ -81,7 +84,8 @@ typedef enum sdpsr_status {
 #define SDPSR_K_BASIS 6    /* basis_image reduction                               */
 #define SDPSR_K_MISC 7     /* everything else (transpose, norms, ...)             */
 #define SDPSR_K_KRYLOV 8   /* label-matrix x vector products of the Krylov path   */
-#define SDPSR_K_COUNT 9
+#define SDPSR_K_GEMM_I8 9 /* symmetric square on the tcgen05 INT8 tensor path      */
+#define SDPSR_K_COUNT 10
 
 /* ------------------------------------------------------------------ lifetime */
 int sdpsr_version(void);
@@ -234,8 +238,16 @@ int sdpsr_set_matrix(sdpsr_ctx* ctx, int which, const double* in);  /* N x N dou
 /* C = A * B on the device with the engine's FP64 DMMA GEMM (test / bench hook);
  * a, b, c are SDPSR_MAT_* ids, c != a, c != b. */
 int sdpsr_gemm(sdpsr_ctx* ctx, int a, int b, int c);
+/* X2 = X * X on the device matrices, the product of `mul!(X2, X, X)` (src/partitions.jl:172) alone
+ * (test / bench hook).  method 0: FP64 DMMA GEMM (half GEMM when X is symmetric); method 1: INT8
+ * tensor path with `slices` 7-bit digits per entry (2..8; 0 = the context's setting), which
+ * requires a bit-for-bit symmetric X (SDPSR_E_INVALID otherwise).                              */
+int sdpsr_square(sdpsr_ctx* ctx, int method, int slices);
+/* Number of int8 digits per entry used by the INT8 square inside sdpsr_square_round_refine
+ * (2..8, default 8 = 55 magnitude bits, the accuracy of an FP64 GEMM).                          */
+int sdpsr_set_square_slices(sdpsr_ctx* ctx, int slices);
 /* Accumulated CUDA-event time, launch count and algorithmic work (bytes for HBM-bound
- * families, flops for SDPSR_K_GEMM) per kernel family since the last reset.           */
+ * families, flops for SDPSR_K_GEMM, int8 operations for SDPSR_K_GEMM_I8) per kernel family since the last reset.           */
 int sdpsr_timing_reset(sdpsr_ctx* ctx);
 int sdpsr_timing_get(sdpsr_ctx* ctx, int family, double* total_ms, int64_t* launches,
                      double* work);

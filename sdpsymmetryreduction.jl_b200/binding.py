@@ -22,9 +22,10 @@ E_INVALID, E_CUDA, E_NO_DEVICE, E_ALLOC, E_LABEL_OVERFLOW, E_NOT_SYMMETRIC = -1,
 E_CUSOLVER, E_STATE, E_SINGULAR, E_NCCL, E_UNSUPPORTED, E_KRYLOV = -7, -8, -9, -10, -11, -12
 
 F_FORCE_BITMAP_RANK, F_TINY_TABLE, F_NO_SMEM_CACHE, F_TIMING, F_NO_SYRK, F_NCCL_EXCHANGE = 1, 2, 4, 8, 16, 32
+F_NO_I8, F_FORCE_I8 = 64, 128
 MAT_X, MAT_X2, MAT_Q, MAT_W = 0, 1, 2, 3
-K_REFINE, K_GEMM, K_FILL, K_PROJECT, K_RANK, K_EIG, K_BASIS, K_MISC, K_KRYLOV = range(9)
-K_NAMES = ["refine", "gemm", "fill", "project", "rank", "eig", "basis", "misc", "krylov"]
+K_REFINE, K_GEMM, K_FILL, K_PROJECT, K_RANK, K_EIG, K_BASIS, K_MISC, K_KRYLOV, K_GEMM_I8 = range(10)
+K_NAMES = ["refine", "gemm", "fill", "project", "rank", "eig", "basis", "misc", "krylov", "gemm_i8"]
 
 
 class LibraryNotBuilt(RuntimeError):
@@ -85,6 +86,8 @@ _SIGNATURES = {
     "sdpsr_get_matrix": ([_p, C.c_int, _p], C.c_int),
     "sdpsr_set_matrix": ([_p, C.c_int, _p], C.c_int),
     "sdpsr_gemm": ([_p, C.c_int, C.c_int, C.c_int], C.c_int),
+    "sdpsr_square": ([_p, C.c_int, C.c_int], C.c_int),
+    "sdpsr_set_square_slices": ([_p, C.c_int], C.c_int),
     "sdpsr_timing_reset": ([_p], C.c_int),
     "sdpsr_timing_get": ([_p, C.c_int, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(C.c_double)], C.c_int),
     "sdpsr_launch_count": ([_p, C.POINTER(_i64)], C.c_int),
@@ -464,6 +467,13 @@ class Context:
 
     def gemm(self, a: int, b: int, c: int):
         self._check(self.lib.sdpsr_gemm(self._h, a, b, c))
+
+    def square(self, method: int = 0, slices: int = 0):
+        """X2 = X * X alone: method 0 = FP64 DMMA GEMM, 1 = INT8 tensor path (symmetric X only)."""
+        self._check(self.lib.sdpsr_square(self._h, method, slices))
+
+    def set_square_slices(self, slices: int):
+        self._check(self.lib.sdpsr_set_square_slices(self._h, slices))
 
     def timing_reset(self):
         self._check(self.lib.sdpsr_timing_reset(self._h))

@@ -441,6 +441,32 @@ extern "C" int sdpsr_fill(sdpsr_ctx* ctx, const double* values, int64_t len) {
   return finish(ctx);
 }
 
+// X2 = X * X.  method -1: automatic (INT8 tensor path for symmetric X where it is the faster one,
+// else DMMA), 0: DMMA, 1: INT8 (error if X is not symmetric).
+static int square_x(sdpsr_ctx* ctx, int method, int slices) {
+  // X symmetric (bit for bit) => X*X symmetric: compute the lower tiles only and mirror them,
+  // which also makes X2 exactly symmetric (SYRK-style, half the flops)
+  int sym = 0;
+  if (!(ctx->flags & SDPSR_F_NO_SYRK) || method == 1) SDPSR_TRY(sdpsr_matrix_symmetric(ctx, ctx->X, &sym));
+  bool use_i8 = false;
+  if (method == 1) {
+    SDPSR_REQUIRE(sym != 0, SDPSR_E_INVALID, "the INT8 square needs a bit-for-bit symmetric X");
+    use_i8 = true;
+  } else if (method < 0 && sym && !(ctx->flags & (SDPSR_F_NO_I8 | SDPSR_F_NO_SYRK)) && ctx->nranks == 1 &&
+             ctx->n <= 32768) {
+    use_i8 = (ctx->flags & SDPSR_F_FORCE_I8) || ctx->n >= 2048;
+  }
+  if (use_i8) {
+    int done = 0;
+    SDPSR_TRY(sdpsr_square_i8(ctx, ctx->X, ctx->X2, slices, &done));
+    if (done) return SDPSR_OK;
+    SDPSR_REQUIRE(method != 1, SDPSR_E_UNSUPPORTED, "the INT8 square does not handle Inf/NaN or extreme exponents");
+  }
+  SDPSR_TRY(sdpsr_gemm_f64(ctx, ctx->X, ctx->ld, ctx->X, ctx->ld, ctx->X2, ctx->ld, ctx->ld, ctx->n, ctx->n,
+                           sym != 0 && !(ctx->flags & SDPSR_F_NO_SYRK), /*shard=*/true));
+  return SDPSR_OK;
+}
+
 extern "C" int sdpsr_square_round_refine(sdpsr_ctx* ctx, double atol, int64_t* dim) {
   CTX_ENTER();
   SDPSR_REQUIRE(ctx->x_valid, SDPSR_E_STATE, "X is not defined yet (call sdpsr_fill first)");
@@ -448,14 +474,25 @@ extern "C" int sdpsr_square_round_refine(sdpsr_ctx* ctx, double atol, int64_t* d
     SDPSR_TRY(sdpsr_materialize_fill(ctx, ctx->X));
     // S is unchanged, so X stays a valid fill; keep the flag for a later projection
   }
-  // X symmetric (bit for bit) => X*X symmetric: compute the lower tiles only and mirror them,
-  // which also makes X2 exactly symmetric (SYRK-style, half the flops)
-  int sym = 0;
-  if (!(ctx->flags & SDPSR_F_NO_SYRK)) SDPSR_TRY(sdpsr_matrix_symmetric(ctx, ctx->X, &sym));
-  SDPSR_TRY(sdpsr_gemm_f64(ctx, ctx->X, ctx->ld, ctx->X, ctx->ld, ctx->X2, ctx->ld, ctx->ld, ctx->n, ctx->n,
-                           sym != 0, /*shard=*/true));
+  SDPSR_TRY(square_x(ctx, /*method=*/-1, ctx->i8_slices));
   SDPSR_TRY(sdpsr_generic_refine_values(ctx, ctx->X2, atol, true, nullptr, dim));
   return finish(ctx);
+}
+
+extern "C" int sdpsr_square(sdpsr_ctx* ctx, int method, int slices) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(ctx->x_valid, SDPSR_E_STATE, "X is not defined yet (call sdpsr_fill or sdpsr_set_matrix first)");
+  SDPSR_REQUIRE(method == 0 || method == 1, SDPSR_E_INVALID, "method must be 0 (DMMA) or 1 (INT8)");
+  if (ctx->x_is_fill) SDPSR_TRY(sdpsr_materialize_fill(ctx, ctx->X));
+  SDPSR_TRY(square_x(ctx, method, slices > 0 ? slices : ctx->i8_slices));
+  return finish(ctx);
+}
+
+extern "C" int sdpsr_set_square_slices(sdpsr_ctx* ctx, int slices) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(slices >= 2 && slices <= 8, SDPSR_E_INVALID, "slices must be in [2, 8]");
+  ctx->i8_slices = slices;
+  return SDPSR_OK;
 }
 
 extern "C" int sdpsr_product_round_refine(sdpsr_ctx* ctx, const double* rx, const double* ry, int64_t len,

@@ -362,12 +362,16 @@ int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B
       SDPSR_TRY(sdpsr_comm_exchange_tilecols(ctx, C, ldc, Nc, BN, tiles_n));
     }
   }
-  if (lower) {
-    Timed tm(ctx, SDPSR_K_MISC, (double)M * (double)Nc * 8.0);
-    dim3 g((unsigned)((Nc + 31) / 32), (unsigned)((Nc + 31) / 32));
-    mirror_lower_kernel<<<g, 256, 0, ctx->stream>>>(C, ldc, (int)Nc);
-    count_launch(ctx);
-  }
+  if (lower) SDPSR_TRY(sdpsr_mirror_lower(ctx, C, ldc, Nc));
+  return SDPSR_OK;
+}
+
+// C[j, i] = C[i, j] for i > j
+int sdpsr_mirror_lower(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t n) {
+  Timed tm(ctx, SDPSR_K_MISC, (double)n * (double)n * 8.0);
+  dim3 g((unsigned)((n + 31) / 32), (unsigned)((n + 31) / 32));
+  mirror_lower_kernel<<<g, 256, 0, ctx->stream>>>(C, ldc, (int)n);
+  count_launch(ctx);
   SDPSR_CUDA(cudaGetLastError());
   return SDPSR_OK;
 }

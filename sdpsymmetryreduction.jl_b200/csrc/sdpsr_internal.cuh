@@ -103,6 +103,8 @@ struct sdpsr_ctx {
   int cur = 0;
   int64_t dim = 0;
 
+  int i8_slices = 8;    // int8 digits per entry of the INT8 square (gemm_i8.cu)
+
   double* X = nullptr;   // [elems]
   double* X2 = nullptr;  // [elems]
   double* Q = nullptr;   // lazily allocated (blockDiagonalize)
@@ -247,6 +249,10 @@ int sdpsr_upload_values(sdpsr_ctx* ctx, const double* values, int64_t len);
 int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t ldb,
                    double* C, int64_t ldc, int64_t M, int64_t Nc, int64_t K, bool symmetric_out,
                    bool shard = false, int accum = 0);
+int sdpsr_mirror_lower(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t n);
+
+// gemm_i8.cu : C = X * X for bit-for-bit symmetric X on the tcgen05 INT8 tensor path
+int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int slices, int* done);
 
 // project.cu
 int sdpsr_constraints_finalize(sdpsr_ctx* ctx);
