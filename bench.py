@@ -300,6 +300,25 @@ def main():
         return 2.0 * n ** 3 / best / 1e9          # TFLOP/s
     fp64_peak = dgemm_peak(min(8192, max(1024, N)))
 
+    # ---- INT8 tensor peak, measured live (cuBLASLt through torch._int_mm) -----------------
+    def int8_peak(n=8192, reps=5):
+        A = torch.randint(-64, 64, (n, n), dtype=torch.int8, device="cuda")
+        Bm = torch.randint(-64, 64, (n, n), dtype=torch.int8, device="cuda").t()
+        torch._int_mm(A, Bm)
+        best = 1e30
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            torch._int_mm(A, Bm)
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return 2.0 * n ** 3 / best / 1e9          # tera-operations / s
+    try:
+        i8_peak, i8_peak_src = int8_peak(), "cuBLASLt int8 GEMM 8192^3 (torch._int_mm) measured live in this run"
+    except Exception as e:                        # noqa: BLE001 -- a reported denominator, never required
+        i8_peak, i8_peak_src = None, "torch._int_mm unavailable (%s)" % type(e).__name__
+
     # ---- resident arm ---------------------------------------------------------------------
     clocks = ClockSampler(local)
     clocks.start()
@@ -387,8 +406,16 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
-    g, rf = tim["gemm"], tim["refine"]     # read before the context was closed
+    g, rf, gi = tim["gemm"], tim["refine"], tim["gemm_i8"]     # read before the context was closed
     gemm_tf = g["work"] / g["ms"] / 1e9 if g["ms"] else None
+    i8_tops = gi["work"] / gi["ms"] / 1e9 if gi["ms"] else None
+    if i8_peak is None:
+        i8_peak = 2.0 * peaks.get("bf16_tflops", 1590.0)
+        i8_peak_src += "; 2 x MEASURED_PEAKS.json bf16_tflops used instead (int8 is twice the bf16 rate)"
+    # FP64-equivalent rate of the squares: the flops a DGEMM of the same (half) product would issue
+    sq_launches = gi["launches"] if gi["launches"] else 0
+    tiles_half = (N // 128) * (N // 128 + 1) // 2 if N % 128 == 0 else None
+    fp64_equiv = (2.0 * tiles_half * 128 * 128 * N * sq_launches / gi["ms"] / 1e9) if (gi["ms"] and tiles_half) else None
     ref_gbs = rf["work"] / rf["ms"] / 1e6 if rf["ms"] else None
     h2d = N * N * 8 + int(prob.A.data.nbytes + prob.A.indices.astype(np.int64).nbytes + prob.A.indptr.nbytes)
     d2h = N * N * 4 + N * 8 + dim * len(sizes) * 8
@@ -405,7 +432,8 @@ def main():
         "e2e": {"value": sec_e2e, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"bound": "tensor", "kernel": "gemm_f64_kernel (DMMA.8x8x4)", "achieved": gemm_tf,
+        "roofline": None,
+        "roofline_dmma": {"bound": "tensor", "kernel": "gemm_f64_kernel (DMMA.8x8x4)", "achieved": gemm_tf,
                      "peak": fp64_peak, "unit": "TFLOP/s", "frac": (gemm_tf / fp64_peak) if gemm_tf else None,
                      "traffic": traffic.get("gemm_f64_kernel"),
                      "peak_source": "cuBLAS DGEMM measured live in this run (MEASURED_PEAKS.json has no FP64 "
@@ -416,9 +444,26 @@ def main():
                          "traffic": traffic.get("refine_kernel"), "peak_source": hbm_src,
                          "launches": rf["launches"], "ms_per_launch": rf["ms"] / max(1, rf["launches"])},
         "refine_passes_per_s": (1e3 * rf["launches"] / rf["ms"]) if rf["ms"] else None,
-        "fp64_tflops": gemm_tf,
+        "fp64_tflops": fp64_equiv if fp64_equiv else gemm_tf,
         "kernel_ms_per_step": {k: v["ms"] / K for k, v in tim.items() if v["launches"]},
     }
+    if i8_tops:
+        line["roofline"] = {"bound": "tensor", "kernel": "square_i8_kernel (tcgen05.mma kind::i8, UTCIMMA)",
+                            "achieved": i8_tops, "peak": i8_peak, "unit": "TFLOP/s",
+                            "frac": i8_tops / i8_peak, "traffic": traffic.get("square_i8_kernel"),
+                            "unit_note": "int8 tera-operations per second (multiply-add = 2 operations); nominal dense "
+                                         "int8 4500",
+                            "peak_source": i8_peak_src, "launches": gi["launches"],
+                            "ms_per_launch": gi["ms"] / max(1, gi["launches"]),
+                            "slices": int(os.environ.get("SDPSR_I8_SLICES", "8")),
+                            "fp64_equivalent_tflops": fp64_equiv,
+                            "note": "X*X of the closure loop through 8 base-128 digit slices: 36 exact int8 products "
+                                    "per square instead of one FP64 product; fp64_equivalent_tflops = flops of the "
+                                    "same half product / kernel time (the DMMA kernel issues them at 36 TFLOP/s)"}
+        if not g["launches"]:
+            del line["roofline_dmma"]
+    else:
+        line["roofline"] = line.pop("roofline_dmma")
     if other:
         line["syevd_path"] = {"value": ms_other / other["steps"] / 1e3, "unit": "s", "steps": other["steps"],
                               "max_block_diff_vs_default_path": other["max_block_diff"],

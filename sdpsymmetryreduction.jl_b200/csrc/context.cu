@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "sdpsr_internal.cuh"
 
 static thread_local std::string g_create_error;
@@ -173,6 +175,10 @@ extern "C" int sdpsr_create(sdpsr_ctx** out, int64_t n, int device, uint32_t fla
   ctx->ld = round_up(n, 16);
   ctx->elems = (size_t)ctx->ld * (size_t)n;
   ctx->flags = flags;
+  if (const char* sl = getenv("SDPSR_I8_SLICES")) {   // default digit count of the INT8 square (2..8)
+    const int v = atoi(sl);
+    if (v >= 2 && v <= 8) ctx->i8_slices = v;
+  }
   const int st = create_impl(ctx);
   if (st != SDPSR_OK) {
     g_create_error = ctx->err;

@@ -127,6 +127,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xFFFFFFFF;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ double pow2(int e) { return __longlong_as_double((long long)(e + 1023) << 52); }
 
 // --------------------------------------------------------------------------------------------
@@ -254,39 +265,42 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      uint32_t t = 0, drained = 0;
-      for (int w = blockIdx.x; w < ntiles; w += gridDim.x) {
-        for (int c0 = S - 2; c0 >= -1; c0 -= 2) {
-          const int nprod = 2 * c0 + 3;
-          mbar_wait(bar_tempty, (drained & 1u) ^ 1u);      // the epilogue has read the previous pair
-          tc_fence_after();
-          for (int kb = 0; kb < KB; ++kb) {
-            for (int j = 0; j < nprod; ++j) {
-              const uint32_t ta = t + j, tb = t + j + 1;    // consecutive tiles of the path
-              if (j == 0) mbar_wait(bar_full + 8 * (ta % NSLOT), (ta / NSLOT) & 1u);
-              mbar_wait(bar_full + 8 * (tb % NSLOT), (tb / NSLOT) & 1u);
-              tc_fence_after();
-              // even j: (B = ta, A = tb) -> accumulator c0+1 ; odd j: (A = ta, B = tb) -> accumulator c0
-              const uint32_t a_tile = (j & 1) ? ta : tb, b_tile = (j & 1) ? tb : ta;
-              const uint64_t adesc = smem_desc(slot_addr(a_tile % NSLOT));
-              const uint64_t bdesc = smem_desc(slot_addr(b_tile % NSLOT));
-              const uint32_t d = tmem + ((j & 1) ? 0u : (uint32_t)TN);
-              const uint32_t fresh = (kb == 0 && j < 2) ? 1u : 0u;
+    // The whole warp walks the loop (warp-uniform control flow keeps the descriptors in uniform
+    // registers); one elected lane issues the tcgen05 instructions.
+    uint32_t t = 0, drained = 0;
+    for (int w = blockIdx.x; w < ntiles; w += gridDim.x) {
+      for (int c0 = S - 2; c0 >= -1; c0 -= 2) {
+        const int nprod = 2 * c0 + 3;
+        mbar_wait(bar_tempty, (drained & 1u) ^ 1u);      // the epilogue has read the previous pair
+        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb) {
+          for (int j = 0; j < nprod; ++j) {
+            const uint32_t ta = t + j, tb = t + j + 1;    // consecutive tiles of the path
+            if (j == 0) mbar_wait(bar_full + 8 * (ta % NSLOT), (ta / NSLOT) & 1u);
+            mbar_wait(bar_full + 8 * (tb % NSLOT), (tb / NSLOT) & 1u);
+            tc_fence_after();
+            // even j: (B = ta, A = tb) -> accumulator c0+1 ; odd j: (A = ta, B = tb) -> accumulator c0
+            const uint32_t a_tile = (j & 1) ? ta : tb, b_tile = (j & 1) ? tb : ta;
+            const uint64_t adesc = smem_desc(slot_addr(a_tile % NSLOT));
+            const uint64_t bdesc = smem_desc(slot_addr(b_tile % NSLOT));
+            const uint32_t d = tmem + ((j & 1) ? 0u : (uint32_t)TN);
+            const uint32_t fresh = (kb == 0 && j < 2) ? 1u : 0u;
+            if (elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < TK / UK; ++ks)
                 mma_i8(d, adesc + (uint64_t)(ks * (UK >> 4)), bdesc + (uint64_t)(ks * (UK >> 4)), (fresh && ks == 0) ? 0u : 1u);
               tc_commit(bar_empty + 8 * (ta % NSLOT));      // tile ta is not used again
               if (j == nprod - 1) tc_commit(bar_empty + 8 * (tb % NSLOT));
             }
-            t += (uint32_t)nprod + 1u;
+            __syncwarp();
           }
-          tc_commit(bar_tfull);
-          ++drained;
+          t += (uint32_t)nprod + 1u;
         }
+        if (elect_one()) tc_commit(bar_tfull);
+        __syncwarp();
+        ++drained;
       }
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
@@ -307,20 +321,22 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t a0[32], a1[32];
           tmem_ld32(trow + (uint32_t)(ch * 32), a0);
           tmem_ld32(trow + (uint32_t)(TN + ch * 32), a1);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (row < n) {
+          // all 32 running sums of this chunk are fetched before any is stored (the stores could
+          // alias the loads as far as the compiler knows, which would serialise 32 round trips)
+          double v[32];
+          double* const p0 = C + (int64_t)row + ldc * (int64_t)(n0 + ch * 32);
+          const int ncol = row < n ? min(32, n - (n0 + ch * 32)) : 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = n0 + ch * 32 + j;
-              if (col < n) {
-                double* p = C + (int64_t)row + ldc * (int64_t)col;
-                double v = first ? 0.0 : *p;
-                v = fma(w_lo, (double)(int)a1[j], v);
-                if (c0 >= 0) v = fma(w_hi, (double)(int)a0[j], v);
-                *p = v;
-              }
-            }
+          for (int j = 0; j < 32; ++j) v[j] = (!first && j < ncol) ? __ldcg(p0 + ldc * j) : 0.0;
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = fma(w_lo, (double)(int)a1[j], v[j]);
+            if (c0 >= 0) v[j] = fma(w_hi, (double)(int)a0[j], v[j]);
           }
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncol) __stcg(p0 + ldc * j, v[j]);
         }
         tc_fence_before();
         mbar_arrive(bar_tempty);
