@@ -458,13 +458,12 @@ static int square_x(sdpsr_ctx* ctx, int method, int slices) {
   if (method == 1) {
     SDPSR_REQUIRE(sym != 0, SDPSR_E_INVALID, "the INT8 square needs a bit-for-bit symmetric X");
     use_i8 = true;
-  } else if (method < 0 && sym && !(ctx->flags & (SDPSR_F_NO_I8 | SDPSR_F_NO_SYRK)) && ctx->nranks == 1 &&
-             ctx->n <= 32768) {
+  } else if (method < 0 && sym && !(ctx->flags & (SDPSR_F_NO_I8 | SDPSR_F_NO_SYRK)) && ctx->n <= 32768) {
     use_i8 = (ctx->flags & SDPSR_F_FORCE_I8) || ctx->n >= 2048;
   }
   if (use_i8) {
     int done = 0;
-    SDPSR_TRY(sdpsr_square_i8(ctx, ctx->X, ctx->X2, slices, &done));
+    SDPSR_TRY(sdpsr_square_i8(ctx, ctx->X, ctx->X2, slices, /*shard=*/true, &done));
     if (done) return SDPSR_OK;
     SDPSR_REQUIRE(method != 1, SDPSR_E_UNSUPPORTED, "the INT8 square does not handle Inf/NaN or extreme exponents");
   }

@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(256) slice_kernel(const double* __restrict__ x
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS, 1)
 square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, double* __restrict__ C,
-                 int64_t ldc, int n, int S, const int2* __restrict__ tiles, int ntiles, int wexp) {
+                 int64_t ldc, int n, int S, const int2* __restrict__ tiles, int ntiles, int wexp,
+                 double* const* __restrict__ peers, int npeers) {
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const uint32_t bar_full = base + NPAIR * PAIR_BYTES;
@@ -315,6 +316,7 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const double w_hi = pow2(wexp - 7 * c0);          // accumulator c0   (TMEM columns 0..255)
         const double w_lo = pow2(wexp - 7 * (c0 + 1));    // accumulator c0+1 (TMEM columns 256..511)
         const bool first = (c0 == S - 2);
+        const bool last = (c0 <= 0);
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
         for (int ch = 0; ch < TN / 32; ++ch) {
@@ -324,7 +326,8 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // all 32 running sums of this chunk are fetched before any is stored (the stores could
           // alias the loads as far as the compiler knows, which would serialise 32 round trips)
           double v[32];
-          double* const p0 = C + (int64_t)row + ldc * (int64_t)(n0 + ch * 32);
+          const int64_t off0 = (int64_t)row + ldc * (int64_t)(n0 + ch * 32);
+          double* const p0 = C + off0;
           const int ncol = row < n ? min(32, n - (n0 + ch * 32)) : 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = (!first && j < ncol) ? __ldcg(p0 + ldc * j) : 0.0;
@@ -334,9 +337,21 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             v[j] = fma(w_lo, (double)(int)a1[j], v[j]);
             if (c0 >= 0) v[j] = fma(w_hi, (double)(int)a0[j], v[j]);
           }
+          if (last && peers) {
+            // multi-GPU: the finished tile goes straight into every rank's copy of X2 (own copy
+            // included) over NVLink peer mappings while the other CTAs are still computing
+#pragma unroll 1
+            for (int r = 0; r < npeers; ++r) {
+              double* const pr = peers[r] + off0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncol) __stcg(p0 + ldc * j, v[j]);
+              for (int j = 0; j < 32; ++j)
+                if (j < ncol) pr[ldc * j] = v[j];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncol) __stcg(p0 + ldc * j, v[j]);
+          }
         }
         tc_fence_before();
         mbar_arrive(bar_tempty);
@@ -386,13 +401,13 @@ int make_slice_map(sdpsr_ctx* ctx, CUtensorMap* map, const int8_t* ptr, int64_t 
 
 // Lower-triangle tiles (tile rows of 128, tile columns of 256), ordered so that the ~148 tiles in
 // flight form a compact block of the matrix (operand tiles are shared through L2).
-void build_tiles(int n, std::vector<int2>& out) {
+void build_tiles(int n, int nranks, int rank, std::vector<int2>& out) {
   const int tiles_m = (n + TM - 1) / TM, tiles_n = (n + TN - 1) / TN;
   constexpr int GROUP = 12;
   out.clear();
   for (int g0 = 0; g0 < tiles_m; g0 += GROUP) {
     const int g1 = std::min(tiles_m, g0 + GROUP);
-    for (int tn = 0; tn < tiles_n; ++tn) {
+    for (int tn = rank; tn < tiles_n; tn += nranks) {    // tile-columns are dealt round-robin to the ranks
       // the tile holds entries on or below the diagonal iff its last row >= its first column
       for (int tm = g0; tm < g1; ++tm)
         if ((tm + 1) * TM - 1 >= tn * TN) out.push_back(make_int2(tm, tn));
@@ -412,7 +427,7 @@ bool sdpsr_square_i8_supported(const sdpsr_ctx* ctx) { return ctx->n <= 32768; }
 
 // X2 = X * X for bit-for-bit symmetric X (checked by the caller).  *done = 0 when the values are out of
 // the range the slicing handles (Inf/NaN, extreme exponents): the caller then uses the DMMA path.
-int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int* done) {
+int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, bool shard, int* done) {
   *done = 0;
   SDPSR_REQUIRE(S >= 2 && S <= 8, SDPSR_E_INVALID, "number of int8 slices must be in [2, 8]");
   SDPSR_REQUIRE(ctx->n <= 32768, SDPSR_E_INVALID, "int8 square: int32 accumulators need N <= 32768");
@@ -439,7 +454,7 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int* done
   double vmax;
   std::memcpy(&vmax, h_max, sizeof(double));
   if (!(vmax < INFINITY)) return SDPSR_OK;                 // Inf / NaN: not handled here
-  if (vmax == 0.0) {
+  if (vmax == 0.0) {     // (X is replicated bit for bit, so every rank takes the same branch)
     SDPSR_CUDA(cudaMemsetAsync(C, 0, elems * sizeof(double), ctx->stream));
     *done = 1;
     return SDPSR_OK;
@@ -466,7 +481,8 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int* done
   SDPSR_CUDA(cudaGetLastError());
   // ---- tiles ----
   std::vector<int2> tiles;
-  build_tiles((int)n, tiles);
+  const bool sharded = shard && ctx->nranks > 1;
+  build_tiles((int)n, sharded ? ctx->nranks : 1, sharded ? ctx->rank : 0, tiles);
   int2* d_tiles = nullptr;
   SDPSR_TRY(sdpsr_scratch_t(ctx, 27, std::max<size_t>(tiles.size(), 1024), &d_tiles));
   SDPSR_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
@@ -475,15 +491,26 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int* done
   SDPSR_TRY(make_slice_map(ctx, &tmA, slices, n, ld, S, TM));
   SDPSR_TRY(make_slice_map(ctx, &tmB, slices, n, ld, S, TN));
   const int ntiles = (int)tiles.size();
-  const int grid = std::min(ctx->sm_count, ntiles);
+  const int grid = std::max(1, std::min(ctx->sm_count, ntiles));
+  double* const* peers = sharded ? sdpsr_comm_peer_table(ctx, C) : nullptr;
+  // nobody may still be reading the previous contents of C on any rank when remote stores begin
+  if (peers) SDPSR_TRY(sdpsr_comm_barrier(ctx));
   {
     // work = int8 operations issued: S(S+1)/2 products of 128 x 256 x K per tile
     const double kpad = (double)((n + TK - 1) / TK * TK);
     Timed tm(ctx, SDPSR_K_GEMM_I8, 2.0 * (double)ntiles * TM * TN * kpad * (double)(S * (S + 1) / 2));
-    square_i8_kernel<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, C, ld, (int)n, S, d_tiles, ntiles, 2 * e - 12);
+    square_i8_kernel<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, C, ld, (int)n, S, d_tiles, ntiles, 2 * e - 12,
+                                                                 peers, ctx->nranks);
     count_launch(ctx);
   }
   SDPSR_CUDA(cudaGetLastError());
+  if (sharded) {
+    if (peers) {
+      SDPSR_TRY(sdpsr_comm_barrier(ctx));      // every rank's tiles have landed in every copy of C
+    } else {
+      SDPSR_TRY(sdpsr_comm_exchange_tilecols(ctx, C, ld, n, TN, (int)((n + TN - 1) / TN)));
+    }
+  }
   SDPSR_TRY(sdpsr_mirror_lower(ctx, C, ld, n));
   *done = 1;
   return SDPSR_OK;

@@ -1,0 +1,40 @@
+"""Host model of the INT8 tensor-path square (csrc/gemm_i8.cu), bit for bit.
+
+The device kernel is integer-exact, so the host can reproduce its result exactly: slice X
+into balanced base-128 digits, form P_c = sum_{s+t=c} D_s D_t with dgemm on integer-valued
+doubles (exact below 2^53), and fold sum_c 2^(2e-12-7c) P_c from the smallest weight up in
+the kernel's order.  Test infrastructure only (used by tests/ and tools/i8_check.py).
+"""
+import numpy as np
+
+
+def slices_of(X: np.ndarray, S: int):
+    vmax = float(np.max(np.abs(X)))
+    e = int(np.frexp(vmax)[1])          # vmax = m * 2^e, m in [0.5, 1)  (== ilogb(vmax) + 1)
+    q = np.rint(X * 2.0 ** (7 * S - 1 - e)).astype(np.int64)
+    D = [None] * S
+    for s in range(S - 1, 0, -1):
+        d = ((q + 64) & 127) - 64
+        q = (q - d) >> 7
+        D[s] = d.astype(np.float64)
+    assert np.max(np.abs(q)) <= 64
+    D[0] = q.astype(np.float64)
+    return D, e
+
+
+def exact_square(X: np.ndarray, S: int) -> np.ndarray:
+    D, e = slices_of(X, S)
+    P = []
+    for c in range(S):
+        acc = np.zeros_like(X)
+        for s in range(c + 1):
+            acc += D[s] @ D[c - s]
+        P.append(acc)
+    out = np.zeros_like(X)
+    c0 = S - 2
+    while c0 >= -1:
+        out = out + 2.0 ** (2 * e - 12 - 7 * (c0 + 1)) * P[c0 + 1]
+        if c0 >= 0:
+            out = out + 2.0 ** (2 * e - 12 - 7 * c0) * P[c0]
+        c0 -= 2
+    return out

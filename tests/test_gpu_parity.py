@@ -202,7 +202,7 @@ def small_problems():
 
 
 @pytest.mark.parametrize("prob", small_problems(), ids=lambda p: p.name)
-@pytest.mark.parametrize("flags", [0, B.F_TINY_TABLE | B.F_FORCE_BITMAP_RANK])
+@pytest.mark.parametrize("flags", [0, B.F_TINY_TABLE | B.F_FORCE_BITMAP_RANK, B.F_FORCE_I8])
 def test_admissible_subspace_labels_identical(prob, flags):
     """Final partition identical (bit-exact canonical labels) and identical dim
     trajectory, given the same random coefficients."""
@@ -423,18 +423,74 @@ def test_symmetric_square_uses_half_gemm_and_matches(n):
     X = O.fill(P, r)
     ref = X @ X
     outs = []
-    for flags in (0, B.F_NO_SYRK):
-        with B.Context(n, 0, flags) as ctx:
+    for flags in (0, B.F_NO_SYRK, B.F_FORCE_I8):
+        with B.Context(n, 0, flags | B.F_TIMING) as ctx:
             ctx.set_labels(L)
             ctx.fill(r)
             d = ctx.square_round_refine(ATOL)
             X2 = ctx.get_matrix(B.MAT_X2)
             outs.append((d, ctx.get_labels(), X2))
+            assert (ctx.timing()["gemm_i8"]["launches"] == 1) == (flags == B.F_FORCE_I8)
     assert np.max(np.abs(outs[0][2] - ref)) < 1e-12 * np.abs(ref).max()
+    assert np.max(np.abs(outs[2][2] - ref)) < 1e-12 * np.abs(ref).max()     # INT8 path: FP64-grade
     assert np.array_equal(outs[0][2], outs[0][2].T)                  # mirrored: exactly symmetric
+    assert np.array_equal(outs[2][2], outs[2][2].T)
     want = O.refine(P, O.partition_from_values(O.clamp_round(ref, ATOL)))
     for d, lab, _ in outs:
         assert d == want.nparts and np.array_equal(lab, want.matrix)
+
+
+def _sym_matrix(n, rng, kind):
+    if kind == "lut":          # what the closure loop squares: few distinct uniform values, symmetric pattern
+        lab = rng.integers(0, 8, size=(n, n))
+        lab = np.triu(lab) + np.triu(lab, 1).T
+        return np.asfortranarray(np.concatenate([[0.0], rng.random(7)])[lab])
+    A = rng.standard_normal((n, n)) * np.exp(rng.uniform(-6, 2, size=(n, n)))      # both signs, wide range
+    return np.asfortranarray(np.triu(A) + np.triu(A, 1).T)
+
+
+@pytest.mark.parametrize("kind", ["lut", "wide"])
+@pytest.mark.parametrize("n", [1, 15, 130, 257, 384])
+def test_int8_square_bit_exact_against_host_model(n, kind):
+    """csrc/gemm_i8.cu is integer-exact: the device result equals the host model (tests/i8_model.py)
+    bit for bit, is exactly symmetric, and at 8 digits agrees with the FP64 product to dgemm accuracy."""
+    from i8_model import exact_square
+    rng = np.random.default_rng(1000 + n)
+    X = _sym_matrix(n, rng, kind)
+    ref = X @ X
+    with B.Context(n) as ctx:
+        ctx.set_matrix(B.MAT_X, X)
+        for S_ in (8, 7, 4, 2):
+            ctx.square(1, S_)
+            got = ctx.get_matrix(B.MAT_X2)
+            assert np.array_equal(got, exact_square(X, S_)), (n, kind, S_)
+            assert np.array_equal(got, got.T)
+            if S_ == 8:
+                assert np.max(np.abs(got - ref)) <= 1e-13 * np.abs(ref).max()
+        ctx.square(0)                                            # DMMA on the same X
+        assert np.max(np.abs(ctx.get_matrix(B.MAT_X2) - ref)) <= 1e-13 * max(np.abs(ref).max(), 1e-300)
+
+
+def test_int8_square_degenerate_inputs():
+    n = 40
+    with B.Context(n) as ctx:
+        ctx.set_matrix(B.MAT_X, np.zeros((n, n)))
+        ctx.square(1, 8)
+        assert not ctx.get_matrix(B.MAT_X2).any()
+        X = np.arange(n * n, dtype=np.float64).reshape(n, n)                  # not symmetric
+        ctx.set_matrix(B.MAT_X, X)
+        with pytest.raises(B.SdpsrError) as ei:
+            ctx.square(1, 8)
+        assert ei.value.code == B.E_INVALID
+        Xs = X + X.T
+        Xs[3, 5] = Xs[5, 3] = np.inf                                           # Inf: outside the slicing range
+        ctx.set_matrix(B.MAT_X, Xs)
+        with pytest.raises(B.SdpsrError) as ei:
+            ctx.square(1, 8)
+        assert ei.value.code == B.E_UNSUPPORTED
+        with pytest.raises(B.SdpsrError):
+            ctx.set_square_slices(9)
+        ctx.set_square_slices(6)
 
 
 def test_nonsymmetric_square_falls_back_to_full_gemm():

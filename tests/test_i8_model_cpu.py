@@ -1,0 +1,34 @@
+"""CPU checks of the host model of the INT8 square (tests/i8_model.py): the model the GPU tests
+hold csrc/gemm_i8.cu to must itself be an FP64-grade X*X."""
+import numpy as np
+import pytest
+
+from i8_model import exact_square, slices_of
+
+
+@pytest.mark.parametrize("n", [1, 7, 64, 200])
+def test_model_is_fp64_grade_and_symmetric(n):
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n)) * np.exp(rng.uniform(-4, 2, size=(n, n)))
+    X = np.triu(A) + np.triu(A, 1).T
+    ref = X @ X
+    prev = None
+    for S in (8, 7, 6, 5, 4, 3, 2):
+        got = exact_square(X, S)
+        assert np.array_equal(got, got.T)
+        err = np.abs(got - ref).max() / np.abs(ref).max()
+        if S == 8:
+            assert err < 2e-14
+        if prev is not None:
+            assert err >= prev * 0.5          # fewer digits never help
+        prev = err
+
+
+def test_digits_reconstruct_the_quantised_entries():
+    rng = np.random.default_rng(3)
+    X = rng.random((50, 50)) - 0.3
+    for S in (2, 5, 8):
+        D, e = slices_of(X, S)
+        q = sum(D[s] * 128.0 ** (S - 1 - s) for s in range(S))
+        assert all(np.abs(d).max() <= 64 for d in D)
+        assert np.abs(q * 2.0 ** (e - (7 * S - 1)) - X).max() <= 2.0 ** (e - 7 * S)   # half a unit of the last digit
