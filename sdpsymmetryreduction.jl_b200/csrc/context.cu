@@ -463,7 +463,7 @@ static int square_x(sdpsr_ctx* ctx, int method, int slices) {
   }
   if (use_i8) {
     int done = 0;
-    SDPSR_TRY(sdpsr_square_i8(ctx, ctx->X, ctx->X2, slices, /*shard=*/true, &done));
+    SDPSR_TRY(sdpsr_square_i8(ctx, ctx->X, ctx->X2, slices, /*shard=*/true, /*force_range=*/method == 1, &done));
     if (done) return SDPSR_OK;
     SDPSR_REQUIRE(method != 1, SDPSR_E_UNSUPPORTED, "the INT8 square does not handle Inf/NaN or extreme exponents");
   }

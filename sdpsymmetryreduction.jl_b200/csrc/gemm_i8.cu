@@ -141,19 +141,29 @@ __device__ __forceinline__ uint32_t elect_one() {
 __device__ __forceinline__ double pow2(int e) { return __longlong_as_double((long long)(e + 1023) << 52); }
 
 // --------------------------------------------------------------------------------------------
-// max |x| over the padded matrix (positive doubles order like their bit patterns)
+// out[0] = max |x| over the matrix, out[1] = the smallest non-zero column maximum (positive doubles
+// order like their bit patterns).  One warp per column.  The slices share ONE scale, so a row / column
+// whose entries are all far below the global maximum would lose relative accuracy: the host compares
+// the two numbers and leaves such matrices to the FP64 DMMA path.
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) maxabs_kernel(const double2* __restrict__ x, size_t n2, unsigned long long* out) {
-  unsigned long long m = 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
-    const double2 v = x[i];
-    const unsigned long long a = (unsigned long long)__double_as_longlong(v.x) & 0x7FFFFFFFFFFFFFFFull;
-    const unsigned long long b = (unsigned long long)__double_as_longlong(v.y) & 0x7FFFFFFFFFFFFFFFull;
-    m = max(m, max(a, b));
-  }
+__global__ void __launch_bounds__(256) colmax_kernel(const double* __restrict__ x, int n, int64_t ld, unsigned long long* out) {
+  const int lane = threadIdx.x & 31;
+  for (int col = blockIdx.x * 8 + (threadIdx.x >> 5); col < n; col += gridDim.x * 8) {
+    const double2* src = reinterpret_cast<const double2*>(x + ld * (int64_t)col);
+    unsigned long long m = 0;
+    for (int i = lane; i < (int)(ld / 2); i += 32) {
+      const double2 v = src[i];
+      const unsigned long long a = (unsigned long long)__double_as_longlong(v.x) & 0x7FFFFFFFFFFFFFFFull;
+      const unsigned long long b = (unsigned long long)__double_as_longlong(v.y) & 0x7FFFFFFFFFFFFFFFull;
+      m = max(m, max(a, b));
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
-  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if (lane == 0 && m) {
+      atomicMax(out, m);
+      atomicMin(out + 1, m);
+    }
+  }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -426,8 +436,9 @@ void launch_slices(const double* X, size_t elems, int8_t* slices, double scale, 
 bool sdpsr_square_i8_supported(const sdpsr_ctx* ctx) { return ctx->n <= 32768; }
 
 // X2 = X * X for bit-for-bit symmetric X (checked by the caller).  *done = 0 when the values are out of
-// the range the slicing handles (Inf/NaN, extreme exponents): the caller then uses the DMMA path.
-int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, bool shard, int* done) {
+// the range the slicing handles (Inf/NaN, extreme exponents, or -- unless force_range -- rows whose
+// largest entry is more than 2^8 below the global maximum): the caller then uses the DMMA path.
+int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, bool shard, bool force_range, int* done) {
   *done = 0;
   SDPSR_REQUIRE(S >= 2 && S <= 8, SDPSR_E_INVALID, "number of int8 slices must be in [2, 8]");
   SDPSR_REQUIRE(ctx->n <= 32768, SDPSR_E_INVALID, "int8 square: int32 accumulators need N <= 32768");
@@ -442,16 +453,18 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, bool shar
   // ---- scale: sigma = 2^e > max|X| ----
   unsigned long long* d_max = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 40);
   unsigned long long* h_max = reinterpret_cast<unsigned long long*>(ctx->h_pinned) + 40;
-  SDPSR_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), ctx->stream));
+  h_max[0] = 0ull;
+  h_max[1] = ~0ull;
+  SDPSR_CUDA(cudaMemcpyAsync(d_max, h_max, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
   {
     Timed tm(ctx, SDPSR_K_MISC, (double)elems * 8.0);
-    maxabs_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(reinterpret_cast<const double2*>(X), elems / 2, d_max);
+    colmax_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(X, (int)n, ld, d_max);
     count_launch(ctx);
   }
   SDPSR_CUDA(cudaGetLastError());
-  SDPSR_CUDA(cudaMemcpyAsync(h_max, d_max, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_CUDA(cudaMemcpyAsync(h_max, d_max, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
   SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
-  double vmax;
+  double vmax, cmin;
   std::memcpy(&vmax, h_max, sizeof(double));
   if (!(vmax < INFINITY)) return SDPSR_OK;                 // Inf / NaN: not handled here
   if (vmax == 0.0) {     // (X is replicated bit for bit, so every rank takes the same branch)
@@ -459,6 +472,10 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, bool shar
     *done = 1;
     return SDPSR_OK;
   }
+  std::memcpy(&cmin, h_max + 1, sizeof(double));
+  // one scale for the whole matrix: every non-zero row must reach within 2^-8 of the maximum, or its
+  // entries would keep fewer than 47 of their 53 bits (S = 8); the closure loop's X always does
+  if (!force_range && cmin < std::ldexp(vmax, -8)) return SDPSR_OK;
   const int e = std::ilogb(vmax) + 1;
   if (e < -400 || e > 400) return SDPSR_OK;
   // ---- slices ----

@@ -252,7 +252,7 @@ int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B
 int sdpsr_mirror_lower(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t n);
 
 // gemm_i8.cu : C = X * X for bit-for-bit symmetric X on the tcgen05 INT8 tensor path
-int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int slices, bool shard, int* done);
+int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int slices, bool shard, bool force_range, int* done);
 
 // project.cu
 int sdpsr_constraints_finalize(sdpsr_ctx* ctx);

@@ -493,6 +493,32 @@ def test_int8_square_degenerate_inputs():
         ctx.set_square_slices(6)
 
 
+def test_int8_square_leaves_badly_scaled_rows_to_dmma():
+    """One scale serves the whole matrix, so a row far below the maximum goes to the FP64 path."""
+    n = 96
+    rng = np.random.default_rng(5)
+    L = rng.integers(1, 5, size=(n, n))
+    L = np.minimum(L, L.T)
+    L[7, :] = L[:, 7] = 5
+    P = O.partition_from_values(L)
+    r = rng.random(P.nparts)
+    r[int(P.matrix[7, 0]) - 1] = 1e-9
+    X = O.fill(P, r)
+    want = O.refine(P, O.partition_from_values(O.clamp_round(X @ X, ATOL)))
+    for tiny_row, launches in ((True, (0, 1)), (False, (1, 0))):
+        with B.Context(n, 0, B.F_FORCE_I8 | B.F_TIMING) as ctx:
+            ctx.set_labels(L)
+            rr = r.copy()
+            if not tiny_row:
+                rr[int(P.matrix[7, 0]) - 1] = 0.3
+            ctx.fill(rr)
+            d = ctx.square_round_refine(ATOL)
+            t = ctx.timing()
+            assert (t["gemm_i8"]["launches"], t["gemm"]["launches"]) == launches
+            if tiny_row:
+                assert d == want.nparts and np.array_equal(ctx.get_labels(), want.matrix)
+
+
 def test_nonsymmetric_square_falls_back_to_full_gemm():
     n = 150
     rng = np.random.default_rng(1)
