@@ -480,8 +480,10 @@ extern "C" int sdpsr_eig_krylov(sdpsr_ctx* ctx, const double* r1, int64_t len, i
     kr_unit_kernel<<<vec_grid(ctx), 256, 0, ctx->stream>>>(startv, ld, reps[c].second);
     count_launch(ctx);
     LanczosOut l2;
-    SDPSR_TRY(lanczos(ctx, *kr, kr->lut1, startv, ne, tol, kr->anorm, l2));
-    if (!l2.breakdown) return ctx->fail(SDPSR_E_KRYLOV, "multiplicity run: no clean breakdown");
+    // The Krylov space of e_r has at most ne dimensions, so ne steps give the exact quadrature whether or
+    // not the last beta drops below the threshold; the run validates itself below (every weighted Ritz
+    // value must match an eigenvalue, the dimensions must be integers and add up to N).
+    SDPSR_TRY(lanczos(ctx, *kr, kr->lut1, startv, ne, kr->soft_tol, kr->anorm, l2));
     std::vector<double> t2, Z2;
     tridiag_eig(l2.alpha, l2.beta, l2.steps, t2, Z2);
     for (int k = 0; k < l2.steps; ++k) {
