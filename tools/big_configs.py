@@ -1,7 +1,7 @@
 """Run BASELINE.json configs 3-5 at full size on one GPU and check them against known answers
 (size-independent properties; the CPU oracle cannot finish these in seconds).
     python tools/big_configs.py h48 k205 h74 syn32768
-Writes one JSON line per config (also to gpurun_out/configs_r1.jsonl)."""
+Writes one JSON line per config (also to gpurun_out/configs_r1s3.jsonl)."""
 import json
 import os
 import sys
@@ -54,6 +54,9 @@ def run(name, prob, truth, value_check=None, fetch=True):
     g, r = tim["gemm"], tim["refine"]
     rec["gemm_tflops"] = g["work"] / g["ms"] / 1e9 if g["ms"] else None
     rec["refine_gbs"] = r["work"] / r["ms"] / 1e6 if r["ms"] else None
+    gi = tim.get("gemm_i8", {"ms": 0, "work": 0, "launches": 0})
+    rec["i8_square_tops"] = gi["work"] / gi["ms"] / 1e9 if gi["ms"] else None
+    rec["i8_square_ms_per_launch"] = gi["ms"] / gi["launches"] if gi["launches"] else None
     P._ctx.timing_reset()
     t0 = time.perf_counter()
     bd = S.blockDiagonalize(P, False, rand=rand)
@@ -84,7 +87,7 @@ def run(name, prob, truth, value_check=None, fetch=True):
                      and rec.get("trace2_identity_err", 0) < 1e-8 and rec.get("closed_form_err", 0) < 1e-8)
     P.release()
     print(json.dumps(rec), flush=True)
-    with open(os.path.join("gpurun_out", "configs_r1.jsonl"), "a") as fh:
+    with open(os.path.join("gpurun_out", "configs_r1s3.jsonl"), "a") as fh:
         fh.write(json.dumps(rec) + "\n")
     return rec
 
