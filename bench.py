@@ -147,7 +147,9 @@ def job_e2e(S, B, prob, C_pinned, labels_pinned, seed=20260101, ctx=None, eig="a
     """The public API with host buffers: the call a user makes.  With several GPUs the caller
     owns a context that carries the NCCL communicator and passes it in."""
     rand = Coeffs(seed)
-    P = S.admissible_subspace(C_pinned, prob.A, prob.b, rand=rand, labels_out=labels_pinned, ctx=ctx)
+    # UInt16 labels: what the reference's admissible_subspace(C, A, b) returns (src/partitions.jl:84)
+    P = S.admissible_subspace(C_pinned, prob.A, prob.b, rand=rand, labels_out=labels_pinned, ctx=ctx,
+                              label_dtype=labels_pinned.dtype)
     bd = S.blockDiagonalize(P, False, rand=rand, eig=eig)
     launches = P._ctx.launch_count()
     if ctx is None:
@@ -270,8 +272,8 @@ def main():
     prob = pr.hamming(d, q, sparse=True)
     C_pinned_t = torch.ones(N * N, dtype=torch.float64).pin_memory()
     C_pinned = C_pinned_t.numpy()
-    labels_pinned_t = torch.empty(N * N, dtype=torch.int32).pin_memory()
-    labels_pinned = labels_pinned_t.numpy().view(np.uint32).reshape(N, N, order="F")
+    labels_pinned_t = torch.empty(N * N, dtype=torch.int16).pin_memory()
+    labels_pinned = labels_pinned_t.numpy().view(np.uint16).reshape(N, N, order="F")
     C_dev = C_pinned_t.cuda(non_blocking=False)
     torch.cuda.synchronize()
 
@@ -369,7 +371,7 @@ def main():
     sweep = None
     if world == 1 and tim["gemm_i8"]["launches"]:
         sweep = {}
-        for sl in (7, 6, 4):
+        for sl in (6, 5, 4):
             ctx.set_square_slices(sl)
             job_resident(S, B, ctx, prob, C_dev, eig=args.eig)
             barrier()
@@ -380,7 +382,7 @@ def main():
             barrier()
             assert dim_s == dim and sizes_s == sizes
             sweep[str(sl)] = a.elapsed_time(b) / 1e3
-        ctx.set_square_slices(int(os.environ.get("SDPSR_I8_SLICES", "8")))
+        ctx.set_square_slices(int(os.environ.get("SDPSR_I8_SLICES", "0")))
 
     # ---- e2e arm: public API, host buffers ------------------------------------------------
     e2e_ctx = ctx if world > 1 else None
@@ -438,7 +440,7 @@ def main():
     fp64_equiv = (2.0 * tiles_half * 128 * 128 * N * sq_launches / world / gi["ms"] / 1e9) if (gi["ms"] and tiles_half) else None
     ref_gbs = rf["work"] / rf["ms"] / 1e6 if rf["ms"] else None
     h2d = N * N * 8 + int(prob.A.data.nbytes + prob.A.indices.astype(np.int64).nbytes + prob.A.indptr.nbytes)
-    d2h = N * N * 4 + N * 8 + dim * len(sizes) * 8
+    d2h = N * N * labels_pinned.dtype.itemsize + N * 8 + dim * len(sizes) * 8
     line = {
         "metric": METRIC, "value": sec_res, "unit": "s", "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": ms_res / K, "higher_is_better": False,
@@ -449,7 +451,8 @@ def main():
                    "parallelism": ("GEMM tile-columns sharded over %d ranks (tiles exchanged from the GEMM epilogue "
                                    "over NVLink peer memory), streaming passes and the eigen step replicated / on "
                                    "rank 0" % world) if world > 1 else "single GPU"},
-        "e2e": {"value": sec_e2e, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": sec_e2e, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "labels": "UInt16 (the reference's default label type, src/partitions.jl:84)"},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": None,
@@ -467,6 +470,11 @@ def main():
         "fp64_tflops": fp64_equiv if fp64_equiv else gemm_tf,
         "kernel_ms_per_step": {k: v["ms"] / K for k, v in tim.items() if v["launches"]},
     }
+    env_sl = int(os.environ.get("SDPSR_I8_SLICES", "0"))
+    wide = N <= 16384 and env_sl != 8
+    n_sl = env_sl if env_sl else (7 if wide else 8)
+    i8_cfg = {"digits": n_sl, "digit_bits": 8 if wide else 7, "products_per_square": n_sl * (n_sl + 1) // 2,
+              "magnitude_bits": (8 if wide else 7) * (n_sl - 1) + 6}
     if i8_tops:
         line["roofline"] = {"bound": "tensor", "kernel": "square_i8_kernel (tcgen05.mma kind::i8, UTCIMMA)",
                             "achieved": i8_tops, "peak": i8_peak, "unit": "TFLOP/s",
@@ -475,18 +483,20 @@ def main():
                                          "int8 4500",
                             "peak_source": i8_peak_src, "launches": gi["launches"],
                             "ms_per_launch": gi["ms"] / max(1, gi["launches"]),
-                            "slices": int(os.environ.get("SDPSR_I8_SLICES", "8")),
+                            "slices": i8_cfg,
                             "fp64_equivalent_tflops": fp64_equiv,
-                            "note": "X*X of the closure loop through 8 base-128 digit slices: 36 exact int8 products "
-                                    "per square instead of one FP64 product; fp64_equivalent_tflops = flops of the "
-                                    "same half product / kernel time (the DMMA kernel issues them at 36 TFLOP/s)"}
+                            "note": "X*X of the closure loop through int8 digit slices (exact int32 products of every "
+                                    "pair of slices whose weights reach the FP64 level) instead of one FP64 "
+                                    "product; fp64_equivalent_tflops = flops of the same half product / kernel time "
+                                    "(the DMMA kernel issues them at 36 TFLOP/s)"}
         if not g["launches"]:
             del line["roofline_dmma"]
     else:
         line["roofline"] = line.pop("roofline_dmma")
     if sweep:
-        line["i8_slices_sweep_s"] = {"note": "whole job (resident) with fewer int8 digits per entry in X*X; same "
-                                             "partition and blocks; 8 is the headline", **sweep}
+        line["i8_slices_sweep_s"] = {"note": "whole job (resident) with fewer int8 digits per entry in X*X (8-bit "
+                                             "digits: 6 -> 46, 5 -> 38, 4 -> 30 magnitude bits); same partition and "
+                                             "blocks; the headline uses the default above", **sweep}
     if other:
         line["syevd_path"] = {"value": ms_other / other["steps"] / 1e3, "unit": "s", "steps": other["steps"],
                               "max_block_diff_vs_default_path": other["max_block_diff"],

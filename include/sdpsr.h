@@ -240,11 +240,14 @@ int sdpsr_set_matrix(sdpsr_ctx* ctx, int which, const double* in);  /* N x N dou
 int sdpsr_gemm(sdpsr_ctx* ctx, int a, int b, int c);
 /* X2 = X * X on the device matrices, the product of `mul!(X2, X, X)` (src/partitions.jl:172) alone
  * (test / bench hook).  method 0: FP64 DMMA GEMM (half GEMM when X is symmetric); method 1: INT8
- * tensor path with `slices` 7-bit digits per entry (2..8; 0 = the context's setting), which
- * requires a bit-for-bit symmetric X (SDPSR_E_INVALID otherwise).                              */
+ * tensor path with `slices` int8 digits per entry (0 = the context's setting), which requires a
+ * bit-for-bit symmetric X (SDPSR_E_INVALID otherwise); the digits are 8 bits wide for N <= 16384
+ * (up to 7 slices) and 7 bits wide above (up to 8 slices).  method 2 / 3: INT8 with 7-bit / 8-bit
+ * digits forced.                                                                                 */
 int sdpsr_square(sdpsr_ctx* ctx, int method, int slices);
-/* Number of int8 digits per entry used by the INT8 square inside sdpsr_square_round_refine
- * (2..8, default 8 = 55 magnitude bits, the accuracy of an FP64 GEMM).                          */
+/* Number of int8 digits per entry used by the INT8 square inside sdpsr_square_round_refine:
+ * 0 (default) = 7 digits of 8 bits for N <= 16384, 8 digits of 7 bits above (54 / 55 magnitude bits,
+ * the accuracy of an FP64 GEMM); 2..7 = fewer digits; 8 = eight 7-bit digits.                    */
 int sdpsr_set_square_slices(sdpsr_ctx* ctx, int slices);
 /* Accumulated CUDA-event time, launch count and algorithmic work (bytes for HBM-bound
  * families, flops for SDPSR_K_GEMM, int8 operations for SDPSR_K_GEMM_I8) per kernel family since the last reset.           */

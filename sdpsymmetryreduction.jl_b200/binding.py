@@ -469,7 +469,8 @@ class Context:
         self._check(self.lib.sdpsr_gemm(self._h, a, b, c))
 
     def square(self, method: int = 0, slices: int = 0):
-        """X2 = X * X alone: method 0 = FP64 DMMA GEMM, 1 = INT8 tensor path (symmetric X only)."""
+        """X2 = X * X alone: method 0 = FP64 DMMA GEMM, 1 = INT8 tensor path (symmetric X only; digit
+        width chosen by N), 2 / 3 = INT8 with 7-bit / 8-bit digits; slices 0 = default."""
         self._check(self.lib.sdpsr_square(self._h, method, slices))
 
     def set_square_slices(self, slices: int):

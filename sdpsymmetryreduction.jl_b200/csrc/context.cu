@@ -449,7 +449,7 @@ extern "C" int sdpsr_fill(sdpsr_ctx* ctx, const double* values, int64_t len) {
 
 // X2 = X * X.  method -1: automatic (INT8 tensor path for symmetric X where it is the faster one,
 // else DMMA), 0: DMMA, 1: INT8 (error if X is not symmetric).
-static int square_x(sdpsr_ctx* ctx, int method, int slices) {
+static int square_x(sdpsr_ctx* ctx, int method, int slices, int bits = 0) {
   // X symmetric (bit for bit) => X*X symmetric: compute the lower tiles only and mirror them,
   // which also makes X2 exactly symmetric (SYRK-style, half the flops)
   int sym = 0;
@@ -463,7 +463,7 @@ static int square_x(sdpsr_ctx* ctx, int method, int slices) {
   }
   if (use_i8) {
     int done = 0;
-    SDPSR_TRY(sdpsr_square_i8(ctx, ctx->X, ctx->X2, slices, /*shard=*/true, /*force_range=*/method == 1, &done));
+    SDPSR_TRY(sdpsr_square_i8(ctx, ctx->X, ctx->X2, slices, bits, /*shard=*/true, /*force_range=*/method == 1, &done));
     if (done) return SDPSR_OK;
     SDPSR_REQUIRE(method != 1, SDPSR_E_UNSUPPORTED, "the INT8 square does not handle Inf/NaN or extreme exponents");
   }
@@ -487,15 +487,16 @@ extern "C" int sdpsr_square_round_refine(sdpsr_ctx* ctx, double atol, int64_t* d
 extern "C" int sdpsr_square(sdpsr_ctx* ctx, int method, int slices) {
   CTX_ENTER();
   SDPSR_REQUIRE(ctx->x_valid, SDPSR_E_STATE, "X is not defined yet (call sdpsr_fill or sdpsr_set_matrix first)");
-  SDPSR_REQUIRE(method == 0 || method == 1, SDPSR_E_INVALID, "method must be 0 (DMMA) or 1 (INT8)");
+  SDPSR_REQUIRE(method >= 0 && method <= 3, SDPSR_E_INVALID,
+                "method must be 0 (DMMA), 1 (INT8), 2 (INT8, 7-bit digits) or 3 (INT8, 8-bit digits)");
   if (ctx->x_is_fill) SDPSR_TRY(sdpsr_materialize_fill(ctx, ctx->X));
-  SDPSR_TRY(square_x(ctx, method, slices > 0 ? slices : ctx->i8_slices));
+  SDPSR_TRY(square_x(ctx, method ? 1 : 0, slices > 0 ? slices : ctx->i8_slices, method == 2 ? 7 : method == 3 ? 8 : 0));
   return finish(ctx);
 }
 
 extern "C" int sdpsr_set_square_slices(sdpsr_ctx* ctx, int slices) {
   CTX_ENTER();
-  SDPSR_REQUIRE(slices >= 2 && slices <= 8, SDPSR_E_INVALID, "slices must be in [2, 8]");
+  SDPSR_REQUIRE(slices == 0 || (slices >= 2 && slices <= 8), SDPSR_E_INVALID, "slices must be 0 (default) or in [2, 8]");
   ctx->i8_slices = slices;
   return SDPSR_OK;
 }

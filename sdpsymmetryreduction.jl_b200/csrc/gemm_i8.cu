@@ -5,14 +5,16 @@
 // runs at the FP64 tensor-pipe limit (36 TFLOP/s); the only faster FP64-grade product on a B200 goes
 // through the integer tensor path (Ozaki-style splitting):
 //
-//   1. slice:  X = sigma * 2^-(7S-1) * sum_s D_s * 128^(S-1-s),  D_s int8 "digits" in [-64, 64],
-//              sigma = 2^e the power of two above max|X|  (S = 8 digits: 55 magnitude bits, i.e. every
-//              entry within 1/8 of the maximum is represented exactly, the rest to 2^-55 sigma);
+//   1. slice:  X = sigma * 2^-(b(S-1)+6) * sum_s D_s * 2^(b(S-1-s)),  balanced int8 digits of b bits
+//              (|D_0| <= 64, the others in [-2^(b-1), 2^(b-1))), sigma = 2^e the power of two above max|X|.
+//              b = 8, S = 7 (N <= 16384): 54 magnitude bits, every entry within 1/4 of the maximum is
+//              represented exactly, the rest to 2^-55 sigma;  b = 7, S = 8 (N <= 32768): 55 bits;
 //   2. square: for c = 0..S-1   P_c = sum_{s+t=c} D_s * D_t   in EXACT int32 arithmetic
-//              (tcgen05.mma kind::i8, accumulators in TMEM; |P_c| <= 8 * 64^2 * K < 2^31 for K <= 32768);
-//   3. fold:   X2 = sum_c 2^(2e-12-7c) * P_c, added from the smallest weight up in FP64.
+//              (tcgen05.mma kind::i8, accumulators in TMEM; b = 8: |P_c| <= (2*64*128 + 5*128^2) K < 2^31
+//              for K <= 16384;  b = 7: |P_c| <= 8 * 64^2 * K < 2^31 for K <= 32768);
+//   3. fold:   X2 = sum_c 2^(2e-12-bc) * P_c, added from the smallest weight up in FP64.
 //
-// The truncated terms (s+t >= S) are below 2^-7S relative, the level of dgemm's own rounding error, and
+// The truncated terms (s+t >= S) are below 2^-bS relative, the level of dgemm's own rounding error, and
 // because the integer sums are exact the result does not depend on the summation order: two entries
 // whose products are the same multiset (= entries of one class of the coherent closure) get
 // bit-identical values, which a floating-point GEMM cannot guarantee.
@@ -169,9 +171,9 @@ __global__ void __launch_bounds__(256) colmax_kernel(const double* __restrict__ 
 // --------------------------------------------------------------------------------------------
 // digit slices: D_s[idx] for the padded linear index idx (same layout as X, one byte per entry)
 // --------------------------------------------------------------------------------------------
-template <int S>
+template <int S, int BITS>
 __global__ void __launch_bounds__(256) slice_kernel(const double* __restrict__ x, size_t elems, int8_t* __restrict__ slices,
-                                                    double scale /* 2^(7S-1-e) */) {
+                                                    double scale /* 2^(BITS(S-1)+6-e) */) {
   const size_t chunk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // 16 consecutive entries
   if (chunk * 16 >= elems) return;
   const double2* src = reinterpret_cast<const double2*>(x + chunk * 16);
@@ -187,8 +189,9 @@ __global__ void __launch_bounds__(256) slice_kernel(const double* __restrict__ x
       const int pos = 2 * h + u;
 #pragma unroll
       for (int s = S - 1; s >= 1; --s) {
-        const long long d = ((q + 64) & 127) - 64;       // balanced digit in [-64, 63]
-        q = (q - d) >> 7;
+        constexpr long long HALF = 1ll << (BITS - 1);
+        const long long d = ((q + HALF) & (2 * HALF - 1)) - HALF;       // balanced digit in [-HALF, HALF)
+        q = (q - d) >> BITS;
         packed[s][pos >> 2] |= ((uint32_t)d & 0xFFu) << (8 * (pos & 3));
       }
       packed[0][pos >> 2] |= ((uint32_t)q & 0xFFu) << (8 * (pos & 3));   // |q| <= 64
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(256) slice_kernel(const double* __restrict__ x
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS, 1)
 square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, double* __restrict__ C,
-                 int64_t ldc, int n, int S, const int2* __restrict__ tiles, int ntiles, int wexp,
+                 int64_t ldc, int n, int S, int bits, const int2* __restrict__ tiles, int ntiles, int wexp,
                  double* const* __restrict__ peers, int npeers) {
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -323,8 +326,8 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int c0 = S - 2; c0 >= -1; c0 -= 2) {
         mbar_wait(bar_tfull, done & 1u);
         tc_fence_after();
-        const double w_hi = pow2(wexp - 7 * c0);          // accumulator c0   (TMEM columns 0..255)
-        const double w_lo = pow2(wexp - 7 * (c0 + 1));    // accumulator c0+1 (TMEM columns 256..511)
+        const double w_hi = pow2(wexp - bits * c0);          // accumulator c0   (TMEM columns 0..255)
+        const double w_lo = pow2(wexp - bits * (c0 + 1));    // accumulator c0+1 (TMEM columns 256..511)
         const bool first = (c0 == S - 2);
         const bool last = (c0 <= 0);
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
@@ -426,9 +429,12 @@ void build_tiles(int n, int nranks, int rank, std::vector<int2>& out) {
 }
 
 template <int S>
-void launch_slices(const double* X, size_t elems, int8_t* slices, double scale, cudaStream_t st) {
+void launch_slices(const double* X, size_t elems, int8_t* slices, double scale, int bits, cudaStream_t st) {
   const size_t chunks = elems / 16;
-  slice_kernel<S><<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(X, elems, slices, scale);
+  if (bits == 8)
+    slice_kernel<S, 8><<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(X, elems, slices, scale);
+  else
+    slice_kernel<S, 7><<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(X, elems, slices, scale);
 }
 
 }  // namespace
@@ -438,10 +444,18 @@ bool sdpsr_square_i8_supported(const sdpsr_ctx* ctx) { return ctx->n <= 32768; }
 // X2 = X * X for bit-for-bit symmetric X (checked by the caller).  *done = 0 when the values are out of
 // the range the slicing handles (Inf/NaN, extreme exponents, or -- unless force_range -- rows whose
 // largest entry is more than 2^8 below the global maximum): the caller then uses the DMMA path.
-int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, bool shard, bool force_range, int* done) {
+int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits, bool shard, bool force_range,
+                    int* done) {
   *done = 0;
-  SDPSR_REQUIRE(S >= 2 && S <= 8, SDPSR_E_INVALID, "number of int8 slices must be in [2, 8]");
   SDPSR_REQUIRE(ctx->n <= 32768, SDPSR_E_INVALID, "int8 square: int32 accumulators need N <= 32768");
+  // digit width: 8 bits while the int32 accumulators allow it (7 products of a group, K <= 16384), else 7
+  // (an explicit request for 8 slices means 8 x 7 bits)
+  if (bits == 0) bits = (ctx->n <= 16384 && S <= 7) ? 8 : 7;
+  SDPSR_REQUIRE(bits == 7 || (bits == 8 && ctx->n <= 16384), SDPSR_E_INVALID,
+                "int8 square: digits are 7 bits wide, or 8 bits for N <= 16384");
+  if (S == 0) S = bits == 8 ? 7 : 8;                     // 54 / 55 magnitude bits
+  SDPSR_REQUIRE(S >= 2 && S <= (bits == 8 ? 7 : 8), SDPSR_E_INVALID,
+                "number of int8 slices must be in [2, 8] (7-bit digits) or [2, 7] (8-bit digits)");
   const int64_t n = ctx->n, ld = ctx->ld;
   const size_t elems = ctx->elems;
   static bool attr_set_dev[64] = {false};
@@ -474,7 +488,7 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, bool shar
   }
   std::memcpy(&cmin, h_max + 1, sizeof(double));
   // one scale for the whole matrix: every non-zero row must reach within 2^-8 of the maximum, or its
-  // entries would keep fewer than 47 of their 53 bits (S = 8); the closure loop's X always does
+  // entries would keep fewer than 46 of their 53 bits; the closure loop's X always does
   if (!force_range && cmin < std::ldexp(vmax, -8)) return SDPSR_OK;
   const int e = std::ilogb(vmax) + 1;
   if (e < -400 || e > 400) return SDPSR_OK;
@@ -483,15 +497,15 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, bool shar
   SDPSR_TRY(sdpsr_scratch_t(ctx, 26, (size_t)S * elems, &slices));
   {
     Timed tm(ctx, SDPSR_K_MISC, (double)elems * (8.0 + S));
-    const double scale = std::ldexp(1.0, 7 * S - 1 - e);
+    const double scale = std::ldexp(1.0, bits * (S - 1) + 6 - e);
     switch (S) {
-      case 2: launch_slices<2>(X, elems, slices, scale, ctx->stream); break;
-      case 3: launch_slices<3>(X, elems, slices, scale, ctx->stream); break;
-      case 4: launch_slices<4>(X, elems, slices, scale, ctx->stream); break;
-      case 5: launch_slices<5>(X, elems, slices, scale, ctx->stream); break;
-      case 6: launch_slices<6>(X, elems, slices, scale, ctx->stream); break;
-      case 7: launch_slices<7>(X, elems, slices, scale, ctx->stream); break;
-      default: launch_slices<8>(X, elems, slices, scale, ctx->stream); break;
+      case 2: launch_slices<2>(X, elems, slices, scale, bits, ctx->stream); break;
+      case 3: launch_slices<3>(X, elems, slices, scale, bits, ctx->stream); break;
+      case 4: launch_slices<4>(X, elems, slices, scale, bits, ctx->stream); break;
+      case 5: launch_slices<5>(X, elems, slices, scale, bits, ctx->stream); break;
+      case 6: launch_slices<6>(X, elems, slices, scale, bits, ctx->stream); break;
+      case 7: launch_slices<7>(X, elems, slices, scale, bits, ctx->stream); break;
+      default: launch_slices<8>(X, elems, slices, scale, bits, ctx->stream); break;
     }
     count_launch(ctx);
   }
@@ -516,7 +530,7 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, bool shar
     // work = int8 operations issued: S(S+1)/2 products of 128 x 256 x K per tile
     const double kpad = (double)((n + TK - 1) / TK * TK);
     Timed tm(ctx, SDPSR_K_GEMM_I8, 2.0 * (double)ntiles * TM * TN * kpad * (double)(S * (S + 1) / 2));
-    square_i8_kernel<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, C, ld, (int)n, S, d_tiles, ntiles, 2 * e - 12,
+    square_i8_kernel<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, C, ld, (int)n, S, bits, d_tiles, ntiles, 2 * e - 12,
                                                                  peers, ctx->nranks);
     count_launch(ctx);
   }

@@ -103,7 +103,7 @@ struct sdpsr_ctx {
   int cur = 0;
   int64_t dim = 0;
 
-  int i8_slices = 8;    // int8 digits per entry of the INT8 square (gemm_i8.cu)
+  int i8_slices = 0;    // int8 digits per entry of the INT8 square (gemm_i8.cu); 0 = 7 x 8-bit / 8 x 7-bit
 
   double* X = nullptr;   // [elems]
   double* X2 = nullptr;  // [elems]
@@ -252,7 +252,8 @@ int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B
 int sdpsr_mirror_lower(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t n);
 
 // gemm_i8.cu : C = X * X for bit-for-bit symmetric X on the tcgen05 INT8 tensor path
-int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int slices, bool shard, bool force_range, int* done);
+int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int slices, int bits, bool shard, bool force_range,
+                    int* done);
 
 // project.cu
 int sdpsr_constraints_finalize(sdpsr_ctx* ctx);

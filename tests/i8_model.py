@@ -8,22 +8,24 @@ the kernel's order.  Test infrastructure only (used by tests/ and tools/i8_check
 import numpy as np
 
 
-def slices_of(X: np.ndarray, S: int):
+def slices_of(X: np.ndarray, S: int, bits: int = 7):
+    """Balanced digits of `bits` bits (7 or 8); the leading digit is at most 64 in magnitude."""
     vmax = float(np.max(np.abs(X)))
     e = int(np.frexp(vmax)[1])          # vmax = m * 2^e, m in [0.5, 1)  (== ilogb(vmax) + 1)
-    q = np.rint(X * 2.0 ** (7 * S - 1 - e)).astype(np.int64)
+    q = np.rint(X * 2.0 ** (bits * (S - 1) + 6 - e)).astype(np.int64)
+    half = 1 << (bits - 1)
     D = [None] * S
     for s in range(S - 1, 0, -1):
-        d = ((q + 64) & 127) - 64
-        q = (q - d) >> 7
+        d = ((q + half) & (2 * half - 1)) - half
+        q = (q - d) >> bits
         D[s] = d.astype(np.float64)
     assert np.max(np.abs(q)) <= 64
     D[0] = q.astype(np.float64)
     return D, e
 
 
-def exact_square(X: np.ndarray, S: int) -> np.ndarray:
-    D, e = slices_of(X, S)
+def exact_square(X: np.ndarray, S: int, bits: int = 7) -> np.ndarray:
+    D, e = slices_of(X, S, bits)
     P = []
     for c in range(S):
         acc = np.zeros_like(X)
@@ -33,8 +35,8 @@ def exact_square(X: np.ndarray, S: int) -> np.ndarray:
     out = np.zeros_like(X)
     c0 = S - 2
     while c0 >= -1:
-        out = out + 2.0 ** (2 * e - 12 - 7 * (c0 + 1)) * P[c0 + 1]
+        out = out + 2.0 ** (2 * e - 12 - bits * (c0 + 1)) * P[c0 + 1]
         if c0 >= 0:
-            out = out + 2.0 ** (2 * e - 12 - 7 * c0) * P[c0]
+            out = out + 2.0 ** (2 * e - 12 - bits * c0) * P[c0]
         c0 -= 2
     return out

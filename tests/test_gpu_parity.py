@@ -460,12 +460,12 @@ def test_int8_square_bit_exact_against_host_model(n, kind):
     ref = X @ X
     with B.Context(n) as ctx:
         ctx.set_matrix(B.MAT_X, X)
-        for S_ in (8, 7, 4, 2):
-            ctx.square(1, S_)
+        for method, bits, S_ in ((2, 7, 8), (2, 7, 7), (2, 7, 4), (2, 7, 2), (3, 8, 7), (3, 8, 5), (3, 8, 2), (1, 8, 0)):
+            ctx.square(method, S_)
             got = ctx.get_matrix(B.MAT_X2)
-            assert np.array_equal(got, exact_square(X, S_)), (n, kind, S_)
+            assert np.array_equal(got, exact_square(X, S_ or 7, bits)), (n, kind, bits, S_)
             assert np.array_equal(got, got.T)
-            if S_ == 8:
+            if S_ in (8, 0) or (bits, S_) == (8, 7):
                 assert np.max(np.abs(got - ref)) <= 1e-13 * np.abs(ref).max()
         ctx.square(0)                                            # DMMA on the same X
         assert np.max(np.abs(ctx.get_matrix(B.MAT_X2) - ref)) <= 1e-13 * max(np.abs(ref).max(), 1e-300)
@@ -490,6 +490,8 @@ def test_int8_square_degenerate_inputs():
         assert ei.value.code == B.E_UNSUPPORTED
         with pytest.raises(B.SdpsrError):
             ctx.set_square_slices(9)
+        with pytest.raises(B.SdpsrError):
+            ctx.square(3, 8)                                                   # 8-bit digits: at most 7 slices
         ctx.set_square_slices(6)
 
 
