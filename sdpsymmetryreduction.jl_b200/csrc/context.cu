@@ -179,6 +179,10 @@ extern "C" int sdpsr_create(sdpsr_ctx** out, int64_t n, int device, uint32_t fla
     const int v = atoi(sl);
     if (v >= 2 && v <= 8) ctx->i8_slices = v;
   }
+  if (const char* sg = getenv("SDPSR_I8_SEGBLOCKS")) {   // test hook: short K segments at small N
+    const int v = atoi(sg);
+    if (v >= 1) ctx->i8_segblocks = v;
+  }
   const int st = create_impl(ctx);
   if (st != SDPSR_OK) {
     g_create_error = ctx->err;
@@ -458,7 +462,7 @@ static int square_x(sdpsr_ctx* ctx, int method, int slices, int bits = 0) {
   if (method == 1) {
     SDPSR_REQUIRE(sym != 0, SDPSR_E_INVALID, "the INT8 square needs a bit-for-bit symmetric X");
     use_i8 = true;
-  } else if (method < 0 && sym && !(ctx->flags & (SDPSR_F_NO_I8 | SDPSR_F_NO_SYRK)) && ctx->n <= 32768) {
+  } else if (method < 0 && sym && !(ctx->flags & (SDPSR_F_NO_I8 | SDPSR_F_NO_SYRK)) && ctx->n <= 65536) {
     use_i8 = (ctx->flags & SDPSR_F_FORCE_I8) || ctx->n >= 2048;
   }
   if (use_i8) {

@@ -7,11 +7,12 @@
 //
 //   1. slice:  X = sigma * 2^-(b(S-1)+6) * sum_s D_s * 2^(b(S-1-s)),  balanced int8 digits of b bits
 //              (|D_0| <= 64, the others in [-2^(b-1), 2^(b-1))), sigma = 2^e the power of two above max|X|.
-//              b = 8, S = 7 (N <= 16384): 54 magnitude bits, every entry within 1/4 of the maximum is
-//              represented exactly, the rest to 2^-55 sigma;  b = 7, S = 8 (N <= 32768): 55 bits;
+//              b = 8, S = 7 (default): 54 magnitude bits, every entry within 1/4 of the maximum is
+//              represented exactly, the rest to 2^-55 sigma;  b = 7, S = 8: 55 bits;
 //   2. square: for c = 0..S-1   P_c = sum_{s+t=c} D_s * D_t   in EXACT int32 arithmetic
 //              (tcgen05.mma kind::i8, accumulators in TMEM; b = 8: |P_c| <= (2*64*128 + 5*128^2) K < 2^31
-//              for K <= 16384;  b = 7: |P_c| <= 8 * 64^2 * K < 2^31 for K <= 32768);
+//              for K <= 16384;  b = 7: |P_c| <= 8 * 64^2 * K < 2^31 for K <= 32768; a longer K is cut into
+//              segments of that length which are folded one after the other);
 //   3. fold:   X2 = sum_c 2^(2e-12-bc) * P_c, added from the smallest weight up in FP64.
 //
 // The truncated terms (s+t >= S) are below 2^-bS relative, the level of dgemm's own rounding error, and
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(256) slice_kernel(const double* __restrict__ x
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS, 1)
 square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, double* __restrict__ C,
-                 int64_t ldc, int n, int S, int bits, const int2* __restrict__ tiles, int ntiles, int wexp,
+                 int64_t ldc, int n, int S, int bits, int segblocks, const int2* __restrict__ tiles, int ntiles, int wexp,
                  double* const* __restrict__ peers, int npeers) {
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -221,6 +222,9 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int KB = (n + TK - 1) / TK;
+  // K is cut into segments short enough for the int32 accumulators; every (accumulator pair, segment)
+  // is one MMA phase followed by one fold
+  const int nseg = (KB + segblocks - 1) / segblocks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSLOT; ++s) {
@@ -255,7 +259,7 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int m0 = tile.x * TM, n0 = tile.y * TN;
         for (int c0 = S - 2; c0 >= -1; c0 -= 2) {
           const int nch = c0 + 2;
-          for (int kb = 0; kb < KB; ++kb) {
+          for (int kb = 0; kb < KB; ++kb) {      // (segments are contiguous: the producer just streams on)
             for (int i = 0; i < nch; ++i) {
               {   // T_{2i} = B_{c0+1-i}
                 const uint32_t slot = t % NSLOT, ph = (t / NSLOT) & 1u;
@@ -284,10 +288,12 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t t = 0, drained = 0;
     for (int w = blockIdx.x; w < ntiles; w += gridDim.x) {
       for (int c0 = S - 2; c0 >= -1; c0 -= 2) {
-        const int nprod = 2 * c0 + 3;
-        mbar_wait(bar_tempty, (drained & 1u) ^ 1u);      // the epilogue has read the previous pair
+       const int nprod = 2 * c0 + 3;
+       for (int seg = 0; seg < nseg; ++seg) {
+        const int kb0 = seg * segblocks, kb1 = min(KB, kb0 + segblocks);
+        mbar_wait(bar_tempty, (drained & 1u) ^ 1u);      // the epilogue has read the previous phase
         tc_fence_after();
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           for (int j = 0; j < nprod; ++j) {
             const uint32_t ta = t + j, tb = t + j + 1;    // consecutive tiles of the path
             if (j == 0) mbar_wait(bar_full + 8 * (ta % NSLOT), (ta / NSLOT) & 1u);
@@ -298,7 +304,7 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t adesc = smem_desc(slot_addr(a_tile % NSLOT));
             const uint64_t bdesc = smem_desc(slot_addr(b_tile % NSLOT));
             const uint32_t d = tmem + ((j & 1) ? 0u : (uint32_t)TN);
-            const uint32_t fresh = (kb == 0 && j < 2) ? 1u : 0u;
+            const uint32_t fresh = (kb == kb0 && j < 2) ? 1u : 0u;
             if (elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < TK / UK; ++ks)
@@ -313,6 +319,7 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) tc_commit(bar_tfull);
         __syncwarp();
         ++drained;
+       }
       }
     }
   } else if (warp >= 4) {
@@ -324,12 +331,13 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row = tile.x * TM + q * 32 + lane;
       const int n0 = tile.y * TN;
       for (int c0 = S - 2; c0 >= -1; c0 -= 2) {
+       for (int seg = 0; seg < nseg; ++seg) {
         mbar_wait(bar_tfull, done & 1u);
         tc_fence_after();
         const double w_hi = pow2(wexp - bits * c0);          // accumulator c0   (TMEM columns 0..255)
         const double w_lo = pow2(wexp - bits * (c0 + 1));    // accumulator c0+1 (TMEM columns 256..511)
-        const bool first = (c0 == S - 2);
-        const bool last = (c0 <= 0);
+        const bool first = (c0 == S - 2) && seg == 0;
+        const bool last = (c0 <= 0) && seg == nseg - 1;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
         for (int ch = 0; ch < TN / 32; ++ch) {
@@ -369,6 +377,7 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_before();
         mbar_arrive(bar_tempty);
         ++done;
+       }
       }
     }
   }
@@ -439,7 +448,6 @@ void launch_slices(const double* X, size_t elems, int8_t* slices, double scale, 
 
 }  // namespace
 
-bool sdpsr_square_i8_supported(const sdpsr_ctx* ctx) { return ctx->n <= 32768; }
 
 // X2 = X * X for bit-for-bit symmetric X (checked by the caller).  *done = 0 when the values are out of
 // the range the slicing handles (Inf/NaN, extreme exponents, or -- unless force_range -- rows whose
@@ -447,12 +455,15 @@ bool sdpsr_square_i8_supported(const sdpsr_ctx* ctx) { return ctx->n <= 32768; }
 int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits, bool shard, bool force_range,
                     int* done) {
   *done = 0;
-  SDPSR_REQUIRE(ctx->n <= 32768, SDPSR_E_INVALID, "int8 square: int32 accumulators need N <= 32768");
-  // digit width: 8 bits while the int32 accumulators allow it (7 products of a group, K <= 16384), else 7
-  // (an explicit request for 8 slices means 8 x 7 bits)
-  if (bits == 0) bits = (ctx->n <= 16384 && S <= 7) ? 8 : 7;
-  SDPSR_REQUIRE(bits == 7 || (bits == 8 && ctx->n <= 16384), SDPSR_E_INVALID,
-                "int8 square: digits are 7 bits wide, or 8 bits for N <= 16384");
+  SDPSR_REQUIRE(ctx->n <= 65536, SDPSR_E_INVALID, "int8 square: N <= 65536");
+  // digit width: 8 bits (an explicit request for 8 slices means 8 x 7 bits)
+  if (bits == 0) bits = S <= 7 ? 8 : 7;
+  SDPSR_REQUIRE(bits == 7 || bits == 8, SDPSR_E_INVALID, "int8 square: digits are 7 or 8 bits wide");
+  // int32 accumulators: a group of 7 products of 8-bit digits (two of them with the leading digit,
+  // |D_0| <= 64) stays below 2^31 for K <= 16384; eight products of 7-bit digits for K <= 32768.
+  // Longer K is cut into segments that are folded one after the other.
+  const int seg_max = (bits == 8 ? 16384 : 32768) / TK;
+  const int segblocks = ctx->i8_segblocks > 0 ? std::min(ctx->i8_segblocks, seg_max) : seg_max;
   if (S == 0) S = bits == 8 ? 7 : 8;                     // 54 / 55 magnitude bits
   SDPSR_REQUIRE(S >= 2 && S <= (bits == 8 ? 7 : 8), SDPSR_E_INVALID,
                 "number of int8 slices must be in [2, 8] (7-bit digits) or [2, 7] (8-bit digits)");
@@ -530,7 +541,7 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits,
     // work = int8 operations issued: S(S+1)/2 products of 128 x 256 x K per tile
     const double kpad = (double)((n + TK - 1) / TK * TK);
     Timed tm(ctx, SDPSR_K_GEMM_I8, 2.0 * (double)ntiles * TM * TN * kpad * (double)(S * (S + 1) / 2));
-    square_i8_kernel<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, C, ld, (int)n, S, bits, d_tiles, ntiles, 2 * e - 12,
+    square_i8_kernel<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, C, ld, (int)n, S, bits, segblocks, d_tiles, ntiles, 2 * e - 12,
                                                                  peers, ctx->nranks);
     count_launch(ctx);
   }

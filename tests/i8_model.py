@@ -24,19 +24,25 @@ def slices_of(X: np.ndarray, S: int, bits: int = 7):
     return D, e
 
 
-def exact_square(X: np.ndarray, S: int, bits: int = 7) -> np.ndarray:
+def exact_square(X: np.ndarray, S: int, bits: int = 7, kseg: int = 0) -> np.ndarray:
+    """kseg: length of the K segments (a multiple of 128; 0 = the device default, 16384 for 8-bit
+    digits and 32768 for 7-bit digits); every (accumulator pair, segment) is folded separately."""
     D, e = slices_of(X, S, bits)
-    P = []
-    for c in range(S):
-        acc = np.zeros_like(X)
-        for s in range(c + 1):
-            acc += D[s] @ D[c - s]
-        P.append(acc)
+    n = X.shape[0]
+    kseg = kseg or (16384 if bits == 8 else 32768)
     out = np.zeros_like(X)
     c0 = S - 2
     while c0 >= -1:
-        out = out + 2.0 ** (2 * e - 12 - bits * (c0 + 1)) * P[c0 + 1]
-        if c0 >= 0:
-            out = out + 2.0 ** (2 * e - 12 - bits * c0) * P[c0]
+        for k0 in range(0, max(n, 1), kseg):
+            sl = slice(k0, min(n, k0 + kseg))
+
+            def group(c):
+                acc = np.zeros_like(X)
+                for s in range(c + 1):
+                    acc += D[s][:, sl] @ D[c - s][sl, :]
+                return acc
+            out = out + 2.0 ** (2 * e - 12 - bits * (c0 + 1)) * group(c0 + 1)
+            if c0 >= 0:
+                out = out + 2.0 ** (2 * e - 12 - bits * c0) * group(c0)
         c0 -= 2
     return out

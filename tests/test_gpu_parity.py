@@ -471,6 +471,25 @@ def test_int8_square_bit_exact_against_host_model(n, kind):
         assert np.max(np.abs(ctx.get_matrix(B.MAT_X2) - ref)) <= 1e-13 * max(np.abs(ref).max(), 1e-300)
 
 
+@pytest.mark.parametrize("n", [200, 300, 515])
+def test_int8_square_with_k_segments(n, monkeypatch):
+    """Long K is cut into segments that fit the int32 accumulators (16384 for 8-bit digits); the test hook
+    SDPSR_I8_SEGBLOCKS makes the segments 128 long so that the same code runs at small N."""
+    from i8_model import exact_square
+    rng = np.random.default_rng(n)
+    X = _sym_matrix(n, rng, "wide")
+    monkeypatch.setenv("SDPSR_I8_SEGBLOCKS", "1")
+    with B.Context(n) as ctx:
+        ctx.set_matrix(B.MAT_X, X)
+        for method, bits, S_ in ((3, 8, 7), (2, 7, 8), (3, 8, 3)):
+            ctx.square(method, S_)
+            got = ctx.get_matrix(B.MAT_X2)
+            assert np.array_equal(got, exact_square(X, S_, bits, kseg=128)), (n, bits, S_)
+            assert np.array_equal(got, got.T)
+    ref = X @ X
+    assert np.max(np.abs(exact_square(X, 7, 8, kseg=128) - ref)) <= 1e-13 * np.abs(ref).max()
+
+
 def test_int8_square_degenerate_inputs():
     n = 40
     with B.Context(n) as ctx:
