@@ -279,6 +279,72 @@ __global__ void __launch_bounds__(256) basis_partial_kernel(const uint32_t* __re
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// basis_image for partitions with few classes and small blocks (association schemes): ONE pass
+// over the label matrix, no per-class index lists.  Every thread keeps private bins
+// [class][output element] in shared memory (layout [bin][thread]: conflict-free, no atomics), so
+// the accumulation order is a fixed function of the launch geometry; the host adds the per-CTA
+// partials in CTA order.   bins = d * npairs <= BS_MAX_BINS.
+// ---------------------------------------------------------------------------------------------
+constexpr int BS_THREADS = 128;
+constexpr int BS_MAX_BINS = 200;      // 200 * 128 * 8 B = 200 KB of shared memory
+constexpr int BS_MAX_PAIRS = 16;
+
+template <int NP>
+__global__ void __launch_bounds__(BS_THREADS) basis_small_kernel(const uint32_t* __restrict__ lab,
+                                                                 const uint32_t* __restrict__ rank, int64_t n, int64_t ld,
+                                                                 const double* __restrict__ Qt, int64_t S,
+                                                                 const int* __restrict__ ca, const int* __restrict__ cb,
+                                                                 int d, int64_t colw, double* __restrict__ partial) {
+  // CTA (x, y): rows x*128 .. +127 (one per thread, its Qt row lives in registers), columns
+  // y*colw .. +colw-1; the column's Qt row is a warp-uniform (broadcast) load.
+  extern __shared__ double bs_bins[];            // [d * NP][BS_THREADS]
+  const int tid = threadIdx.x;
+  const int nbins = d * NP;
+  for (int k = 0; k < nbins; ++k) bs_bins[k * BS_THREADS + tid] = 0.0;
+  int sb[NP];
+  double qa[NP];
+  const int64_t a = (int64_t)blockIdx.x * BS_THREADS + tid;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    sb[p] = cb[p];
+    qa[p] = a < n ? Qt[S * a + ca[p]] : 0.0;
+  }
+  const int64_t b0 = (int64_t)blockIdx.y * colw, b1 = min(n, b0 + colw);
+  if (a < n) {
+    uint32_t nxt = b0 < b1 ? lab[a + ld * b0] : 0u;
+    for (int64_t b = b0; b < b1; ++b) {
+      const uint32_t cur = nxt;
+      if (b + 1 < b1) nxt = lab[a + ld * (b + 1)];              // next label is in flight during the update
+      const uint32_t i = rank[cur];
+      if (i) {
+        const double* qbp = Qt + S * b;
+        double* bin = bs_bins + (size_t)(i - 1) * NP * BS_THREADS + tid;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) bin[p * BS_THREADS] += qa[p] * __ldg(qbp + sb[p]);
+      }
+    }
+  }
+  __syncthreads();
+  // fixed-order reduction of the private copies (rotated start: no bank conflicts)
+  const int64_t cta = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+  for (int k = tid; k < nbins; k += BS_THREADS) {
+    double s = 0.0;
+    for (int t = 0; t < BS_THREADS; ++t) s += bs_bins[k * BS_THREADS + ((t + tid) & (BS_THREADS - 1))];
+    partial[cta * nbins + k] = s;
+  }
+}
+
+template <int NP>
+int launch_basis_small(sdpsr_ctx* ctx, dim3 grid, size_t smem, const uint32_t* rank, const double* qt, int64_t S,
+                       const int* pairs, int d, int64_t colw, double* part) {
+  SDPSR_CUDA(cudaFuncSetAttribute(basis_small_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+  basis_small_kernel<NP><<<grid, BS_THREADS, smem, ctx->stream>>>(ctx->labels, rank, ctx->n, ctx->ld, qt, S, pairs, pairs + NP,
+                                                                 d, colw, part);
+  return SDPSR_OK;
+}
+
 int ensure_buffer(sdpsr_ctx* ctx, double** p) {
   if (!*p) {
     SDPSR_CUDA(cudaMalloc(p, ctx->elems * sizeof(double)));
@@ -623,13 +689,82 @@ extern "C" int sdpsr_basis_image(sdpsr_ctx* ctx, double atol, double* out, int64
   SDPSR_REQUIRE(out_len == d * Sq, SDPSR_E_INVALID, "out_len must be dim * sum(s_k^2)");
   if (d == 0) return SDPSR_OK;
   KeyTable& t = ctx->tab[ctx->cur];
+  if (d * Sq <= BS_MAX_BINS && Sq <= BS_MAX_PAIRS && !(ctx->flags & SDPSR_F_TINY_TABLE)) {
+    // ---- few classes, small blocks: one pass over the labels (basis_small_kernel) -----------
+    std::vector<int> hp;                    // [pa | pb]
+    std::vector<int64_t> poff;
+    {
+      std::vector<int> pa, pb;
+      int64_t colbase = 0, off = 0;
+      for (int64_t sz : ctx->blk_sizes) {
+        for (int64_t b = 0; b < sz; ++b)
+          for (int64_t a = 0; a < sz; ++a) {   // column-major s x s: element (a,b) at a + s*b
+            pa.push_back((int)(colbase + a));
+            pb.push_back((int)(colbase + b));
+            poff.push_back(off + a + sz * b);
+          }
+        colbase += sz;
+        off += sz * sz;
+      }
+      hp = pa;
+      hp.insert(hp.end(), pb.begin(), pb.end());
+    }
+    const int np = (int)Sq, nbins = (int)(d * Sq);
+    const size_t smem = (size_t)nbins * BS_THREADS * sizeof(double);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(200 * 1024) / std::max<size_t>(smem, 1)));
+    // grid: row blocks of 128 x column ranges, about per_sm CTAs per SM in total
+    const int64_t rowblocks = (n + BS_THREADS - 1) / BS_THREADS;
+    const int64_t want = std::max<int64_t>(1, ((int64_t)ctx->sm_count * per_sm + rowblocks - 1) / rowblocks);
+    const int64_t colsplit = std::min<int64_t>(want, std::max<int64_t>(1, n / 64));
+    const int64_t colw = (n + colsplit - 1) / colsplit;
+    const dim3 grid3((unsigned)rowblocks, (unsigned)((n + colw - 1) / colw));
+    const int grid = (int)(grid3.x * grid3.y);
+    double *d_qt = nullptr, *d_part = nullptr;
+    int* d_pairs = nullptr;
+    SDPSR_TRY(sdpsr_scratch_t(ctx, 4, (size_t)n * (size_t)S, &d_qt));
+    SDPSR_TRY(sdpsr_scratch_t(ctx, 3, (size_t)grid * nbins, &d_part));
+    SDPSR_TRY(sdpsr_scratch_t(ctx, 5, (size_t)2 * np, &d_pairs));
+    SDPSR_CUDA(cudaMemcpyAsync(d_pairs, hp.data(), hp.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<double> part((size_t)grid * nbins);
+    {
+      Timed tm(ctx, SDPSR_K_BASIS, (double)ctx->elems * 4.0);
+      qhat_rowmajor_kernel<<<dim3((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)S), 256, 0, ctx->stream>>>(
+          ctx->Qhat, n, ld, S, d_qt);
+      int st = SDPSR_OK;
+      switch (np) {
+#define BS_CASE(K) case K: st = launch_basis_small<K>(ctx, grid3, smem, t.rank, d_qt, S, d_pairs, (int)d, colw, d_part); break;
+        BS_CASE(1) BS_CASE(2) BS_CASE(3) BS_CASE(4) BS_CASE(5) BS_CASE(6) BS_CASE(7) BS_CASE(8)
+        BS_CASE(9) BS_CASE(10) BS_CASE(11) BS_CASE(12) BS_CASE(13) BS_CASE(14) BS_CASE(15) BS_CASE(16)
+#undef BS_CASE
+        default: st = ctx->fail(SDPSR_E_INVALID, "basis_small: bad pair count");
+      }
+      SDPSR_TRY(st);
+      count_launch(ctx, 2);
+    }
+    SDPSR_CUDA(cudaGetLastError());
+    SDPSR_CUDA(cudaMemcpyAsync(part.data(), d_part, part.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<double> result((size_t)(d * Sq), 0.0);
+    for (int64_t i = 0; i < d; ++i)
+      for (int p = 0; p < np; ++p) {
+        double sum = 0.0;
+        for (int c = 0; c < grid; ++c) sum += part[(size_t)c * nbins + (size_t)(i * np + p)];
+        if (std::fabs(sum) < atol) sum = 0.0;                // clamptol!, :85
+        result[(size_t)(i * Sq + poff[(size_t)p])] = sum;
+      }
+    SDPSR_CUDA(cudaMemcpy(out, result.data(), result.size() * 8, cudaMemcpyDefault));
+    return finish(ctx);
+  }
   // ---- CSR by canonical label (_constraints, :42-50) --------------------------------------
   unsigned long long* d_cnt = nullptr;
   SDPSR_TRY(sdpsr_scratch_t(ctx, 0, (size_t)d + 2, &d_cnt));
   SDPSR_CUDA(cudaMemsetAsync(d_cnt, 0, ((size_t)d + 2) * 8, ctx->stream));
   const unsigned g2 = (unsigned)std::min<int64_t>(n, (int64_t)ctx->sm_count * 8);
-  class_count_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->labels, t.rank, n, ld, d_cnt, d + 1);
-  count_launch(ctx);
+  {
+    Timed tm(ctx, SDPSR_K_BASIS, (double)ctx->elems * 4.0);
+    class_count_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->labels, t.rank, n, ld, d_cnt, d + 1);
+    count_launch(ctx);
+  }
   std::vector<unsigned long long> cnt((size_t)d + 2);
   SDPSR_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, cnt.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
   SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -641,8 +776,11 @@ extern "C" int sdpsr_basis_image(sdpsr_ctx* ctx, double atol, double* out, int64
   SDPSR_TRY(sdpsr_scratch_t(ctx, 1, std::max<size_t>(1, (size_t)nent) * 2, &d_rc));
   uint32_t* d_rows = d_rc;
   uint32_t* d_cols = d_rc + nent;
-  class_scatter_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->labels, t.rank, n, ld, d_cnt, d_rows, d_cols, d + 1);
-  count_launch(ctx);
+  {
+    Timed tm(ctx, SDPSR_K_BASIS, (double)ctx->elems * 12.0);
+    class_scatter_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->labels, t.rank, n, ld, d_cnt, d_rows, d_cols, d + 1);
+    count_launch(ctx);
+  }
   // chunks: class i owns chunks [cstart[i], cstart[i+1])
   std::vector<unsigned long long> cbeg, cend;
   std::vector<int64_t> cstart((size_t)d + 2, 0);

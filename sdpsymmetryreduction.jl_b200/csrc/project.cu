@@ -678,14 +678,20 @@ extern "C" int sdpsr_init_partition(sdpsr_ctx* ctx, const double* C, const doubl
 
   // CL = symmetrize(round(C - proj(C)))                                   (:129-134)
   if (ctx->ld != ctx->n) SDPSR_CUDA(cudaMemsetAsync(ctx->X, 0, ctx->elems * 8, ctx->stream));
-  SDPSR_CUDA(cudaMemcpy2DAsync(ctx->X, (size_t)ctx->ld * 8, C, (size_t)ctx->n * 8, (size_t)ctx->n * 8, (size_t)ctx->n,
-                               cudaMemcpyDefault, ctx->stream));
+  {
+    Timed tm(ctx, SDPSR_K_MISC, (double)ctx->elems * 16.0);              // staging copy (or the H2D upload)
+    SDPSR_CUDA(cudaMemcpy2DAsync(ctx->X, (size_t)ctx->ld * 8, C, (size_t)ctx->n * 8, (size_t)ctx->n * 8, (size_t)ctx->n,
+                                 cudaMemcpyDefault, ctx->stream));
+  }
   SDPSR_TRY(sdpsr_rowdots(ctx, ctx->X, nullptr, coef));
   SDPSR_TRY(sdpsr_solve_gram(ctx, coef));
   SDPSR_TRY(sdpsr_upload_tpat(ctx, coef));
-  init_elem_kernel<<<grid, 256, 0, ctx->stream>>>(0, ctx->X, c.d_pid, c.d_tpat, ctx->X2, ctx->elems, pw, do_snap, atol, scale);
-  symmetrize_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(ctx->X2, ctx->X, ctx->n, ctx->ld);
-  count_launch(ctx, 2);
+  {
+    Timed tm(ctx, SDPSR_K_MISC, (double)ctx->elems * (20.0 + 16.0));
+    init_elem_kernel<<<grid, 256, 0, ctx->stream>>>(0, ctx->X, c.d_pid, c.d_tpat, ctx->X2, ctx->elems, pw, do_snap, atol, scale);
+    symmetrize_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(ctx->X2, ctx->X, ctx->n, ctx->ld);
+    count_launch(ctx, 2);
+  }
   SDPSR_CUDA(cudaGetLastError());
   SDPSR_TRY(sdpsr_partition_reset(ctx));
   {
@@ -700,14 +706,20 @@ extern "C" int sdpsr_init_partition(sdpsr_ctx* ctx, const double* C, const doubl
   coef.assign(b, b + c.m);
   SDPSR_TRY(sdpsr_solve_gram(ctx, coef));
   SDPSR_TRY(sdpsr_upload_tpat(ctx, coef));
-  init_elem_kernel<<<grid, 256, 0, ctx->stream>>>(1, nullptr, c.d_pid, c.d_tpat, ctx->X2, ctx->elems, pw, do_snap, atol, scale);
-  symmetrize_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(ctx->X2, ctx->X, ctx->n, ctx->ld);
-  count_launch(ctx, 2);
+  {
+    Timed tm(ctx, SDPSR_K_MISC, (double)ctx->elems * (12.0 + 16.0));
+    init_elem_kernel<<<grid, 256, 0, ctx->stream>>>(1, nullptr, c.d_pid, c.d_tpat, ctx->X2, ctx->elems, pw, do_snap, atol, scale);
+    symmetrize_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(ctx->X2, ctx->X, ctx->n, ctx->ld);
+    count_launch(ctx, 2);
+  }
   SDPSR_TRY(sdpsr_rowdots(ctx, ctx->X, nullptr, coef));
   SDPSR_TRY(sdpsr_solve_gram(ctx, coef));
   SDPSR_TRY(sdpsr_upload_tpat(ctx, coef));
-  init_elem_kernel<<<grid, 256, 0, ctx->stream>>>(2, nullptr, c.d_pid, c.d_tpat, ctx->X2, ctx->elems, pw, do_snap, atol, scale);
-  count_launch(ctx);
+  {
+    Timed tm(ctx, SDPSR_K_MISC, (double)ctx->elems * 20.0);
+    init_elem_kernel<<<grid, 256, 0, ctx->stream>>>(2, nullptr, c.d_pid, c.d_tpat, ctx->X2, ctx->elems, pw, do_snap, atol, scale);
+    count_launch(ctx);
+  }
   SDPSR_CUDA(cudaGetLastError());
   SDPSR_TRY(sdpsr_generic_refine_values(ctx, ctx->X2, atol, false, nullptr, dim));   // refine!(S, Part(X0)) (:146)
   ctx->x_valid = false;
