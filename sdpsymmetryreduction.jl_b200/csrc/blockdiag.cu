@@ -312,17 +312,29 @@ __global__ void __launch_bounds__(BS_THREADS) basis_small_kernel(const uint32_t*
     qa[p] = a < n ? Qt[S * a + ca[p]] : 0.0;
   }
   const int64_t b0 = (int64_t)blockIdx.y * colw, b1 = min(n, b0 + colw);
-  if (a < n) {
-    uint32_t nxt = b0 < b1 ? lab[a + ld * b0] : 0u;
+  if (a < n && b0 < b1) {
+    // software pipeline: the label of column b+2, the class of column b+1 and the Qt row of column b+1
+    // are in flight while column b updates the bins (the update itself is shared-memory only)
+    uint32_t lab2 = b0 + 1 < b1 ? lab[a + ld * (b0 + 1)] : 0u;
+    uint32_t inext = rank[lab[a + ld * b0]];
+    double qn[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) qn[p] = __ldg(Qt + S * b0 + sb[p]);
     for (int64_t b = b0; b < b1; ++b) {
-      const uint32_t cur = nxt;
-      if (b + 1 < b1) nxt = lab[a + ld * (b + 1)];              // next label is in flight during the update
-      const uint32_t i = rank[cur];
+      const uint32_t i = inext;
+      double qb[NP];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) qb[p] = qn[p];
+      if (b + 1 < b1) {
+        inext = rank[lab2];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) qn[p] = __ldg(Qt + S * (b + 1) + sb[p]);
+        if (b + 2 < b1) lab2 = lab[a + ld * (b + 2)];
+      }
       if (i) {
-        const double* qbp = Qt + S * b;
         double* bin = bs_bins + (size_t)(i - 1) * NP * BS_THREADS + tid;
 #pragma unroll
-        for (int p = 0; p < NP; ++p) bin[p * BS_THREADS] += qa[p] * __ldg(qbp + sb[p]);
+        for (int p = 0; p < NP; ++p) bin[p * BS_THREADS] += qa[p] * qb[p];
       }
     }
   }
