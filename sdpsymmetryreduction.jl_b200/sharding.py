@@ -36,3 +36,25 @@ def work_balance(n: int, lower: bool, nranks: int):
     t = num_tiles(n)
     counts = [len(owned_tiles(t, t, lower, nranks, r)) for r in range(nranks)]
     return counts
+
+
+# ---- INT8 symmetric square (csrc/gemm_i8.cu) ------------------------------------------------------
+I8_TILE_M = 128      # tile rows    (UMMA M)
+I8_TILE_N = 256      # tile columns (UMMA N)
+I8_GROUP = 12        # tile rows walked together, so that the tiles in flight share operand panels
+
+
+def owned_tiles_i8(n: int, nranks: int, rank: int):
+    """(tm, tn) tiles of the lower triangle this rank computes -- same order as
+    csrc/gemm_i8.cu::build_tiles: 256-column tile-columns dealt round-robin, and a tile is kept when
+    it holds at least one entry on or below the diagonal."""
+    tiles_m = (n + I8_TILE_M - 1) // I8_TILE_M
+    tiles_n = (n + I8_TILE_N - 1) // I8_TILE_N
+    out = []
+    for g0 in range(0, tiles_m, I8_GROUP):
+        g1 = min(tiles_m, g0 + I8_GROUP)
+        for tn in range(rank, tiles_n, nranks):
+            for tm in range(g0, g1):
+                if (tm + 1) * I8_TILE_M - 1 >= tn * I8_TILE_N:
+                    out.append((tm, tn))
+    return out

@@ -31,6 +31,30 @@ def test_tile_deal_partitions_the_tiles(n, nranks, lower):
         assert max(counts) <= 1.15 * sum(counts) / nranks + 1
 
 
+@pytest.mark.parametrize("n", [1, 100, 257, 4096, 15504, 16384, 32768])
+@pytest.mark.parametrize("nranks", [1, 2, 4, 8])
+def test_int8_tile_deal_covers_the_lower_triangle(n, nranks):
+    """csrc/gemm_i8.cu::build_tiles: every entry on or below the diagonal lies in exactly one owned tile,
+    the owner of a tile is the owner of its 256-column tile-column, and the deal is balanced."""
+    seen = {}
+    for r in range(nranks):
+        for tm, tn in sh.owned_tiles_i8(n, nranks, r):
+            assert (tm, tn) not in seen and tn % nranks == r
+            seen[(tm, tn)] = r
+    for i, j in [(0, 0), (n - 1, 0), (n - 1, n - 1), (n // 2, n // 3), (min(n - 1, 255), min(n - 1, 255)),
+                 (min(n - 1, 256), min(n - 1, 255)), (min(n - 1, 127), min(n - 1, 100))]:
+        if i >= j:
+            assert (i // sh.I8_TILE_M, j // sh.I8_TILE_N) in seen
+    for tm, tn in seen:                                   # no tile lies wholly above the diagonal
+        assert (tm + 1) * sh.I8_TILE_M - 1 >= tn * sh.I8_TILE_N
+    tiles_m, tiles_n = -(-n // sh.I8_TILE_M), -(-n // sh.I8_TILE_N)
+    want = sum(1 for tn in range(tiles_n) for tm in range(tiles_m) if (tm + 1) * sh.I8_TILE_M - 1 >= tn * sh.I8_TILE_N)
+    assert len(seen) == want
+    counts = [sum(1 for v in seen.values() if v == r) for r in range(nranks)]
+    if tiles_n >= 8 * nranks:
+        assert max(counts) <= 1.15 * sum(counts) / nranks + 1
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
