@@ -179,6 +179,7 @@ extern "C" int sdpsr_create(sdpsr_ctx** out, int64_t n, int device, uint32_t fla
     const int v = atoi(sl);
     if (v >= 2 && v <= 8) ctx->i8_slices = v;
   }
+  if (const char* pr = getenv("SDPSR_I8_PAIR")) ctx->i8_pair = atoi(pr) != 0 ? 1 : 0;
   if (const char* sg = getenv("SDPSR_I8_SEGBLOCKS")) {   // test hook: short K segments at small N
     const int v = atoi(sg);
     if (v >= 1) ctx->i8_segblocks = v;

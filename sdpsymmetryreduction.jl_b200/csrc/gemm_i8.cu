@@ -390,6 +390,237 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+
+// --------------------------------------------------------------------------------------------
+// The same square on CTA PAIRS (tcgen05 cta_group::2): one cluster of two CTAs owns a 256 x 256 tile,
+// each CTA holds its 128 rows of A, HALF of the B tile (128 of the 256 columns) and its 128 x 256
+// halves of the two accumulators.  Per product a CTA now loads 16 KB instead of 24 KB on average and
+// the tensor core reads the B half of the partner from the partner's shared memory, so the L2 ->
+// shared-memory traffic and the shared-memory reads per MMA drop by a third; with uniform 16 KB
+// slots the ring is 12 tiles deep.  Protocol differences from the single-CTA kernel:
+//   * both CTAs run a TMA producer; every load signals the LEADER's full barrier (the leader expects
+//     the bytes of both), the MMA is issued by the leader alone;
+//   * tcgen05.commit multicasts to the empty / accumulator-full barriers of both CTAs;
+//   * the partner's epilogue arrives remotely on the leader's accumulator-empty barrier.
+// --------------------------------------------------------------------------------------------
+constexpr int T2_BYTES = 128 * TK;               // 16 KB: A tile, or one half of a B tile
+constexpr int NSLOT2 = 12;
+constexpr int SMEM2_BYTES = NSLOT2 * T2_BYTES + 1024 + 512;
+constexpr uint32_t IDESC2 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1,
+                                                int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {      // arrives on both CTAs' barrier at this offset
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mma_i8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(IDESC2), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+square_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmT, double* __restrict__ C, int64_t ldc, int n, int S, int bits,
+                      int segblocks, const int2* __restrict__ tiles, int ntiles, int wexp,
+                      double* const* __restrict__ peers, int npeers) {
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t bar_full = base + NSLOT2 * T2_BYTES;
+  const uint32_t bar_empty = bar_full + NSLOT2 * 8;
+  const uint32_t bar_tfull = bar_empty + NSLOT2 * 8;
+  const uint32_t bar_tempty = bar_tfull + 8;
+  const uint32_t tmem_slot = bar_tempty + 8;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int KB = (n + TK - 1) / TK;
+  const int nseg = (KB + segblocks - 1) / segblocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSLOT2; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tempty, 256);                  // the epilogue threads of both CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmT) : "memory");
+      uint32_t t = 0;
+      for (int w = cluster_id; w < ntiles; w += nclusters) {
+        const int2 tile = tiles[w];
+        const int m0 = tile.x * 256 + (int)crank * 128;       // this CTA's rows of A
+        const int n0 = tile.y * TN + (int)crank * 128;        // this CTA's half of the B columns
+        for (int c0 = S - 2; c0 >= -1; c0 -= 2) {
+          const int nch = c0 + 2;
+          for (int kb = 0; kb < KB; ++kb) {
+            for (int i = 0; i < 2 * nch; ++i) {               // even i: B_{c0+1-i/2}, odd i: A_{i/2}
+              const uint32_t slot = t % NSLOT2, ph = (t / NSLOT2) & 1u;
+              mbar_wait(bar_empty + 8 * slot, ph ^ 1u);
+              const uint32_t lead_full = map_to_cta(bar_full + 8 * slot, 0);
+              if (crank == 0) mbar_expect_tx(bar_full + 8 * slot, 2 * T2_BYTES);
+              if (i & 1)
+                tma_load_3d_2sm(base + slot * T2_BYTES, &tmT, lead_full, kb * TK, m0, i >> 1);
+              else
+                tma_load_3d_2sm(base + slot * T2_BYTES, &tmT, lead_full, kb * TK, n0, c0 + 1 - (i >> 1));
+              ++t;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (crank == 0) {
+      uint32_t t = 0, drained = 0;
+      for (int w = cluster_id; w < ntiles; w += nclusters) {
+        for (int c0 = S - 2; c0 >= -1; c0 -= 2) {
+          const int nprod = 2 * c0 + 3;
+          for (int seg = 0; seg < nseg; ++seg) {
+            const int kb0 = seg * segblocks, kb1 = min(KB, kb0 + segblocks);
+            mbar_wait(bar_tempty, (drained & 1u) ^ 1u);
+            tc_fence_after();
+            for (int kb = kb0; kb < kb1; ++kb) {
+              for (int j = 0; j < nprod; ++j) {
+                const uint32_t ta = t + j, tb = t + j + 1;
+                if (j == 0) mbar_wait(bar_full + 8 * (ta % NSLOT2), (ta / NSLOT2) & 1u);
+                mbar_wait(bar_full + 8 * (tb % NSLOT2), (tb / NSLOT2) & 1u);
+                tc_fence_after();
+                const uint32_t a_tile = (j & 1) ? ta : tb, b_tile = (j & 1) ? tb : ta;
+                const uint64_t adesc = smem_desc(base + (a_tile % NSLOT2) * T2_BYTES);
+                const uint64_t bdesc = smem_desc(base + (b_tile % NSLOT2) * T2_BYTES);
+                const uint32_t d = tmem + ((j & 1) ? 0u : (uint32_t)TN);
+                const uint32_t fresh = (kb == kb0 && j < 2) ? 1u : 0u;
+                if (elect_one()) {
+#pragma unroll
+                  for (int ks = 0; ks < TK / UK; ++ks)
+                    mma_i8_2sm(d, adesc + (uint64_t)(ks * (UK >> 4)), bdesc + (uint64_t)(ks * (UK >> 4)),
+                               (fresh && ks == 0) ? 0u : 1u);
+                  tc_commit_2sm(bar_empty + 8 * (ta % NSLOT2));
+                  if (j == nprod - 1) tc_commit_2sm(bar_empty + 8 * (tb % NSLOT2));
+                }
+                __syncwarp();
+              }
+              t += (uint32_t)nprod + 1u;
+            }
+            if (elect_one()) tc_commit_2sm(bar_tfull);
+            __syncwarp();
+            ++drained;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int q = warp & 3;
+    const uint32_t lead_tempty = map_to_cta(bar_tempty, 0);
+    uint32_t done = 0;
+    for (int w = cluster_id; w < ntiles; w += nclusters) {
+      const int2 tile = tiles[w];
+      const int row = tile.x * 256 + (int)crank * 128 + q * 32 + lane;
+      const int n0 = tile.y * TN;
+      for (int c0 = S - 2; c0 >= -1; c0 -= 2) {
+        for (int seg = 0; seg < nseg; ++seg) {
+          mbar_wait(bar_tfull, done & 1u);
+          tc_fence_after();
+          const double w_hi = pow2(wexp - bits * c0);
+          const double w_lo = pow2(wexp - bits * (c0 + 1));
+          const bool first = (c0 == S - 2) && seg == 0;
+          const bool last = (c0 <= 0) && seg == nseg - 1;
+          const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+          for (int ch = 0; ch < TN / 32; ++ch) {
+            uint32_t a0[32], a1[32];
+            tmem_ld32(trow + (uint32_t)(ch * 32), a0);
+            tmem_ld32(trow + (uint32_t)(TN + ch * 32), a1);
+            double v[32];
+            const int64_t off0 = (int64_t)row + ldc * (int64_t)(n0 + ch * 32);
+            double* const p0 = C + off0;
+            const int ncol = row < n ? min(32, n - (n0 + ch * 32)) : 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (!first && j < ncol) ? __ldcg(p0 + ldc * j) : 0.0;
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v[j] = fma(w_lo, (double)(int)a1[j], v[j]);
+              if (c0 >= 0) v[j] = fma(w_hi, (double)(int)a0[j], v[j]);
+            }
+            if (last && peers) {
+#pragma unroll 1
+              for (int r = 0; r < npeers; ++r) {
+                double* const pr = peers[r] + off0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncol) pr[ldc * j] = v[j];
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncol) __stcg(p0 + ldc * j, v[j]);
+            }
+          }
+          tc_fence_before();
+          mbar_arrive_cluster(lead_tempty);
+          ++done;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();           // the partner's shared memory and barriers stay alive until both are done
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 typedef CUresult (*PFN_tmapEncode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -437,6 +668,18 @@ void build_tiles(int n, int nranks, int rank, std::vector<int2>& out) {
   }
 }
 
+// 256 x 256 tiles of the lower triangle for the CTA-pair kernel (same grouping idea)
+void build_tiles_2cta(int n, int nranks, int rank, std::vector<int2>& out) {
+  const int t = (n + 255) / 256;
+  constexpr int GROUP = 8;
+  out.clear();
+  for (int g0 = 0; g0 < t; g0 += GROUP) {
+    const int g1 = std::min(t, g0 + GROUP);
+    for (int tn = rank; tn < t; tn += nranks)
+      for (int tm = std::max(g0, tn); tm < g1; ++tm) out.push_back(make_int2(tm, tn));
+  }
+}
+
 template <int S>
 void launch_slices(const double* X, size_t elems, int8_t* slices, double scale, int bits, cudaStream_t st) {
   const size_t chunks = elems / 16;
@@ -473,6 +716,7 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits,
   bool& attr_set = attr_set_dev[ctx->device & 63];
   if (!attr_set) {
     SDPSR_CUDA(cudaFuncSetAttribute(square_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SDPSR_CUDA(cudaFuncSetAttribute(square_i8_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
     attr_set = true;
   }
   // ---- scale: sigma = 2^e > max|X| ----
@@ -522,9 +766,15 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits,
   }
   SDPSR_CUDA(cudaGetLastError());
   // ---- tiles ----
-  std::vector<int2> tiles;
+  // CTA-pair kernel (256 x 256 tiles): measured equal to the single-CTA kernel at N = 16384 (both sit at
+  // the power cap) and 5 % faster at N = 32768, where the operand panels stress L2 more
+  const bool pair = ctx->i8_pair < 0 ? n > 16384 : ctx->i8_pair != 0;
   const bool sharded = shard && ctx->nranks > 1;
-  build_tiles((int)n, sharded ? ctx->nranks : 1, sharded ? ctx->rank : 0, tiles);
+  std::vector<int2> tiles;
+  if (pair)
+    build_tiles_2cta((int)n, sharded ? ctx->nranks : 1, sharded ? ctx->rank : 0, tiles);
+  else
+    build_tiles((int)n, sharded ? ctx->nranks : 1, sharded ? ctx->rank : 0, tiles);
   int2* d_tiles = nullptr;
   SDPSR_TRY(sdpsr_scratch_t(ctx, 27, std::max<size_t>(tiles.size(), 1024), &d_tiles));
   SDPSR_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
@@ -533,16 +783,37 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits,
   SDPSR_TRY(make_slice_map(ctx, &tmA, slices, n, ld, S, TM));
   SDPSR_TRY(make_slice_map(ctx, &tmB, slices, n, ld, S, TN));
   const int ntiles = (int)tiles.size();
-  const int grid = std::max(1, std::min(ctx->sm_count, ntiles));
   double* const* peers = sharded ? sdpsr_comm_peer_table(ctx, C) : nullptr;
   // nobody may still be reading the previous contents of C on any rank when remote stores begin
   if (peers) SDPSR_TRY(sdpsr_comm_barrier(ctx));
   {
-    // work = int8 operations issued: S(S+1)/2 products of 128 x 256 x K per tile
+    // work = int8 operations issued: S(S+1)/2 products of (tile rows x 256 x K) per tile
     const double kpad = (double)((n + TK - 1) / TK * TK);
-    Timed tm(ctx, SDPSR_K_GEMM_I8, 2.0 * (double)ntiles * TM * TN * kpad * (double)(S * (S + 1) / 2));
-    square_i8_kernel<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, C, ld, (int)n, S, bits, segblocks, d_tiles, ntiles, 2 * e - 12,
-                                                                 peers, ctx->nranks);
+    Timed tm(ctx, SDPSR_K_GEMM_I8, 2.0 * (double)ntiles * (pair ? 256 : TM) * TN * kpad * (double)(S * (S + 1) / 2));
+    if (pair) {
+      // co-resident CTA pairs: fewer than sm_count / 2 when a TPC has lost one of its SMs
+      static int max_pairs_dev[64] = {0};
+      int& max_pairs = max_pairs_dev[ctx->device & 63];
+      if (!max_pairs) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(ctx->sm_count & ~1));
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = SMEM2_BYTES;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, square_i8_2cta_kernel, &cfg) != cudaSuccess || nc < 1) {
+          cudaGetLastError();
+          nc = ctx->sm_count / 2;
+        }
+        max_pairs = nc;
+      }
+      const int nclusters = std::max(1, std::min(max_pairs, ntiles));
+      square_i8_2cta_kernel<<<2 * nclusters, THREADS, SMEM2_BYTES, ctx->stream>>>(tmA, C, ld, (int)n, S, bits, segblocks, d_tiles,
+                                                                                 ntiles, 2 * e - 12, peers, ctx->nranks);
+    } else {
+      const int grid = std::max(1, std::min(ctx->sm_count, ntiles));
+      square_i8_kernel<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, C, ld, (int)n, S, bits, segblocks, d_tiles, ntiles,
+                                                                   2 * e - 12, peers, ctx->nranks);
+    }
     count_launch(ctx);
   }
   SDPSR_CUDA(cudaGetLastError());

@@ -103,6 +103,7 @@ struct sdpsr_ctx {
   int cur = 0;
   int64_t dim = 0;
 
+  int i8_pair = -1;     // INT8 square on CTA pairs (cta_group::2): -1 = for N > 16384, 0 / 1 = SDPSR_I8_PAIR
   int i8_segblocks = 0; // test hook (SDPSR_I8_SEGBLOCKS): K segment length of the INT8 square in 128-byte blocks
   int i8_slices = 0;    // int8 digits per entry of the INT8 square (gemm_i8.cu); 0 = 7 x 8-bit / 8 x 7-bit
 

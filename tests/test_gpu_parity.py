@@ -490,6 +490,28 @@ def test_int8_square_with_k_segments(n, monkeypatch):
     assert np.max(np.abs(exact_square(X, 7, 8, kseg=128) - ref)) <= 1e-13 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("n", [1, 130, 257, 515, 700])
+def test_int8_square_cta_pair_kernel(n, monkeypatch):
+    """The cta_group::2 variant (256 x 256 tiles on CTA pairs, default for N > 16384) computes the same
+    bits; SDPSR_I8_PAIR=1 selects it at any N, SDPSR_I8_SEGBLOCKS=2 adds K segments."""
+    from i8_model import exact_square
+    rng = np.random.default_rng(50 + n)
+    X = _sym_matrix(n, rng, "wide")
+    monkeypatch.setenv("SDPSR_I8_PAIR", "1")
+    with B.Context(n, 0, B.F_TIMING) as ctx:
+        ctx.set_matrix(B.MAT_X, X)
+        for method, bits, S_ in ((3, 8, 7), (2, 7, 8), (3, 8, 2)):
+            ctx.square(method, S_)
+            got = ctx.get_matrix(B.MAT_X2)
+            assert np.array_equal(got, exact_square(X, S_, bits)), (n, bits, S_)
+            assert np.array_equal(got, got.T)
+    monkeypatch.setenv("SDPSR_I8_SEGBLOCKS", "2")
+    with B.Context(n) as ctx:
+        ctx.set_matrix(B.MAT_X, X)
+        ctx.square(3, 7)
+        assert np.array_equal(ctx.get_matrix(B.MAT_X2), exact_square(X, 7, 8, kseg=256))
+
+
 def test_int8_square_degenerate_inputs():
     n = 40
     with B.Context(n) as ctx:
