@@ -141,6 +141,15 @@ function SR.admissible_subspace(::Type{CuPartition}, C::AbstractVector{T}, A::Ab
     return CuPartition(c, d[])
 end
 
+"""
+    square_digits!(c::Ctx, k)
+
+Number of int8 digits per entry the INT8 tensor-path square uses for `mul!(X², X, X)` (symmetric X):
+`0` = default (FP64-grade: 7 digits of 8 bits), `2..7` = coarser coefficients, `8` = eight 7-bit digits.
+The integer products are exact whatever `k` is, so the classes found do not depend on it.
+"""
+square_digits!(c::Ctx, k::Integer) = check(c, ccall((:sdpsr_set_square_slices, LIB), Cint, (Ptr{Cvoid}, Cint), c.h, k))
+
 "Drop-in with the reference's signature: returns a host Partition{UInt16} (src/partitions.jl:77-85)."
 admissible_subspace_cuda(C, A, b; kw...) = SR.Partition{UInt16}(SR.admissible_subspace(CuPartition, C, A, b; kw...))
 
