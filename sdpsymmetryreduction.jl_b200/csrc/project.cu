@@ -677,18 +677,29 @@ extern "C" int sdpsr_init_partition(sdpsr_ctx* ctx, const double* C, const doubl
   std::vector<double> coef;
 
   // CL = symmetrize(round(C - proj(C)))                                   (:129-134)
-  if (ctx->ld != ctx->n) SDPSR_CUDA(cudaMemsetAsync(ctx->X, 0, ctx->elems * 8, ctx->stream));
+  // C is read in place when it already lives on this device in the engine's own layout (ld == N);
+  // otherwise it is staged into X (the H2D upload of a host matrix, or the re-striding copy)
+  const double* Csrc = ctx->X;
   {
-    Timed tm(ctx, SDPSR_K_MISC, (double)ctx->elems * 16.0);              // staging copy (or the H2D upload)
-    SDPSR_CUDA(cudaMemcpy2DAsync(ctx->X, (size_t)ctx->ld * 8, C, (size_t)ctx->n * 8, (size_t)ctx->n * 8, (size_t)ctx->n,
-                                 cudaMemcpyDefault, ctx->stream));
+    cudaPointerAttributes pa;
+    const bool on_device = cudaPointerGetAttributes(&pa, C) == cudaSuccess && pa.type == cudaMemoryTypeDevice &&
+                           pa.device == ctx->device;
+    cudaGetLastError();
+    if (on_device && ctx->ld == ctx->n && ((uintptr_t)C % 16 == 0)) {
+      Csrc = C;
+    } else {
+      if (ctx->ld != ctx->n) SDPSR_CUDA(cudaMemsetAsync(ctx->X, 0, ctx->elems * 8, ctx->stream));
+      Timed tm(ctx, SDPSR_K_MISC, (double)ctx->elems * 16.0);              // staging copy (or the H2D upload)
+      SDPSR_CUDA(cudaMemcpy2DAsync(ctx->X, (size_t)ctx->ld * 8, C, (size_t)ctx->n * 8, (size_t)ctx->n * 8, (size_t)ctx->n,
+                                   cudaMemcpyDefault, ctx->stream));
+    }
   }
-  SDPSR_TRY(sdpsr_rowdots(ctx, ctx->X, nullptr, coef));
+  SDPSR_TRY(sdpsr_rowdots(ctx, Csrc, nullptr, coef));
   SDPSR_TRY(sdpsr_solve_gram(ctx, coef));
   SDPSR_TRY(sdpsr_upload_tpat(ctx, coef));
   {
     Timed tm(ctx, SDPSR_K_MISC, (double)ctx->elems * (20.0 + 16.0));
-    init_elem_kernel<<<grid, 256, 0, ctx->stream>>>(0, ctx->X, c.d_pid, c.d_tpat, ctx->X2, ctx->elems, pw, do_snap, atol, scale);
+    init_elem_kernel<<<grid, 256, 0, ctx->stream>>>(0, Csrc, c.d_pid, c.d_tpat, ctx->X2, ctx->elems, pw, do_snap, atol, scale);
     symmetrize_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(ctx->X2, ctx->X, ctx->n, ctx->ld);
     count_launch(ctx, 2);
   }

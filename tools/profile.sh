@@ -3,7 +3,7 @@
 set -u
 TAG=${1:-r1}
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
-MINE='regex:^(void )?(<unnamed>::)?(refine_|gemm_f64|square_i8|slice_kernel|maxabs|mirror_lower|fill_kernel|rowdot|init_elem|symmetrize|basis_partial|block_max|class_|transpose_kernel|rank_brute|bitmap_|gather_|build_lut|canonical|pattern_|relabel|symcheck|clamp_kernel|pair_|labels_|qhat_|count_zero|reduce_)'
+MINE='regex:^(void )?(<unnamed>::)?(refine_|gemm_f64|square_i8|slice_kernel|colmax|basis_small|labmv|kr_|mirror_lower|fill_kernel|rowdot|init_elem|symmetrize|basis_partial|block_max|class_|transpose_kernel|rank_brute|bitmap_|gather_|build_lut|canonical|pattern_|relabel|symcheck|clamp_kernel|pair_|labels_|qhat_|count_zero|reduce_)'
 $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain.log; exit 1; }
 tail -c 400 gpurun_out/plain.log
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$MINE" -c 600 --csv \
