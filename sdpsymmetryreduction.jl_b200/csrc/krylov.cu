@@ -58,10 +58,6 @@ struct Krylov {
   double* U = nullptr;          // device: ld x ne work                              (scratch 23)
   double* w = nullptr;          // device: ld work vector                            (scratch 24)
   double* small = nullptr;      // device: dots / coefficients / S matrix            (scratch 25)
-  // dim(P) <= 255: the canonical labels as bytes, so that a matrix-vector product reads 1 B/entry
-  uint8_t* lab8 = nullptr;      // device: ld x n canonical labels                   (scratch 28)
-  double* lutc = nullptr;       // device: [2][256] coefficient LUTs by canonical label: current, A1  (scratch 29)
-  int dim8 = 0;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -93,62 +89,6 @@ __global__ void __launch_bounds__(256) labmv_kernel(const uint32_t* __restrict__
       b1 = fma(__ldg(lut + l1.y), v0.y, b1);
       b0 = fma(__ldg(lut + l1.z), v1.x, b0);
       b1 = fma(__ldg(lut + l1.w), v1.y, b1);
-    }
-    double a = a0 + a1, b = b0 + b1;
-    for (int o = 16; o; o >>= 1) {
-      a += __shfl_down_sync(0xffffffffu, a, o);
-      b += __shfl_down_sync(0xffffffffu, b, o);
-    }
-    if (lane == 0) {
-      y[j0] = a;
-      if (two) y[j0 + 1] = b;
-    }
-  }
-}
-
-// canonical labels as bytes (dim <= 255): lab8 = rank[lab]
-__global__ void __launch_bounds__(256) lab8_kernel(const uint32_t* __restrict__ lab, const uint32_t* __restrict__ rank,
-                                                   uint8_t* __restrict__ out, uint64_t elems) {
-  for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < elems; i += (uint64_t)gridDim.x * blockDim.x * 4) {
-    const uint4 l = *reinterpret_cast<const uint4*>(lab + i);
-    const uint32_t packed = (rank[l.x] & 0xFFu) | ((rank[l.y] & 0xFFu) << 8) | ((rank[l.z] & 0xFFu) << 16) | (rank[l.w] << 24);
-    *reinterpret_cast<uint32_t*>(out + i) = packed;
-  }
-}
-
-// The same product from byte labels: 16 rows per lane and step, LUT in shared memory.
-__global__ void __launch_bounds__(256) labmv8_kernel(const uint8_t* __restrict__ lab, const double* __restrict__ lutc,
-                                                     const double* __restrict__ v, double* __restrict__ y, int64_t n,
-                                                     int64_t ld) {
-  __shared__ double sl[256];
-  sl[threadIdx.x] = lutc[threadIdx.x];
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t j0 = warp * 2; j0 < n; j0 += nwarps * 2) {
-    const bool two = j0 + 1 < n;
-    const uint8_t* c0 = lab + ld * j0;
-    const uint8_t* c1 = lab + ld * (two ? j0 + 1 : j0);
-    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-    for (int64_t i = (int64_t)lane * 16; i < ld; i += 512) {
-      const uint4 l0 = __ldcs(reinterpret_cast<const uint4*>(c0 + i));
-      const uint4 l1 = __ldcs(reinterpret_cast<const uint4*>(c1 + i));
-      const uint32_t w0[4] = {l0.x, l0.y, l0.z, l0.w};
-      const uint32_t w1[4] = {l1.x, l1.y, l1.z, l1.w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const double2 va = __ldg(reinterpret_cast<const double2*>(v + i + 4 * q));
-        const double2 vb = __ldg(reinterpret_cast<const double2*>(v + i + 4 * q + 2));
-        a0 = fma(sl[w0[q] & 0xFFu], va.x, a0);
-        a1 = fma(sl[(w0[q] >> 8) & 0xFFu], va.y, a1);
-        a0 = fma(sl[(w0[q] >> 16) & 0xFFu], vb.x, a0);
-        a1 = fma(sl[w0[q] >> 24], vb.y, a1);
-        b0 = fma(sl[w1[q] & 0xFFu], va.x, b0);
-        b1 = fma(sl[(w1[q] >> 8) & 0xFFu], va.y, b1);
-        b0 = fma(sl[(w1[q] >> 16) & 0xFFu], vb.x, b0);
-        b1 = fma(sl[w1[q] >> 24], vb.y, b1);
-      }
     }
     double a = a0 + a1, b = b0 + b1;
     for (int o = 16; o; o >>= 1) {
@@ -307,15 +247,10 @@ struct LanczosOut {
 };
 
 int matvec(sdpsr_ctx* ctx, const double* lut, const double* v, double* y) {
-  const Krylov* kr = reinterpret_cast<const Krylov*>(ctx->krylov);
-  const bool bytes = kr && kr->lab8 && kr->dim8 == ctx->dim;
-  Timed tm(ctx, SDPSR_K_KRYLOV, (double)ctx->elems * (bytes ? 1.0 : 4.0));
+  Timed tm(ctx, SDPSR_K_KRYLOV, (double)ctx->elems * 4.0);
   const int64_t warps = (ctx->n + 1) / 2;
   const int grid = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)ctx->sm_count * 8);
-  if (bytes)      // lut is ctx->lut (current coefficients) or kr->lut1 (A1): same choice among the byte-label LUTs
-    labmv8_kernel<<<grid, 256, 0, ctx->stream>>>(kr->lab8, kr->lutc + (lut == kr->lut1 ? 256 : 0), v, y, ctx->n, ctx->ld);
-  else
-    labmv_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->labels, lut, v, y, ctx->n, ctx->ld);
+  labmv_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->labels, lut, v, y, ctx->n, ctx->ld);
   count_launch(ctx);
   SDPSR_CUDA(cudaGetLastError());
   return SDPSR_OK;
@@ -411,11 +346,6 @@ int build_lut_from(sdpsr_ctx* ctx, const double* r, int64_t len) {
   SDPSR_TRY(sdpsr_upload_values(ctx, r, len));
   SDPSR_TRY(sdpsr_build_lut(ctx, ctx->d_values, len));
   ctx->x_is_fill = false;   // the lut no longer belongs to X
-  Krylov* kr = reinterpret_cast<Krylov*>(ctx->krylov);
-  if (kr && kr->lutc && len <= 255) {     // the same coefficients by canonical label: lutc[c] = r[c-1], lutc[0] = 0
-    SDPSR_CUDA(cudaMemsetAsync(kr->lutc, 0, 256 * sizeof(double), ctx->stream));
-    if (len) SDPSR_CUDA(cudaMemcpyAsync(kr->lutc + 1, ctx->d_values, (size_t)len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  }
   return SDPSR_OK;
 }
 
@@ -473,29 +403,11 @@ extern "C" int sdpsr_eig_krylov(sdpsr_ctx* ctx, const double* r1, int64_t len, i
   kr->ready = false;
   kr->tol = tol;
   const int64_t n = ctx->n, ld = ctx->ld;
-  // few classes: keep the canonical labels as bytes, a matrix-vector product then reads 1 B/entry
-  kr->lab8 = nullptr;
-  kr->dim8 = 0;
-  if (ctx->dim <= 255 && !(ctx->flags & SDPSR_F_TINY_TABLE)) {
-    SDPSR_TRY(sdpsr_scratch_t(ctx, 29, (size_t)512, &kr->lutc));
-    uint8_t* l8 = nullptr;
-    SDPSR_TRY(sdpsr_scratch_t(ctx, 28, ctx->elems, &l8));
-    {
-      Timed tm(ctx, SDPSR_K_KRYLOV, (double)ctx->elems * 5.0);
-      lab8_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->labels, ctx->tab[ctx->cur].rank, l8, (uint64_t)ctx->elems);
-      count_launch(ctx);
-    }
-    SDPSR_CUDA(cudaGetLastError());
-    kr->lab8 = l8;
-    kr->dim8 = (int)ctx->dim;
-  }
   // A1 = fill(S, r1) as a LUT (kept for the later calls; ctx->lut is overwritten by r2 / r3)
   SDPSR_TRY(build_lut_from(ctx, r1, len));
   const size_t lut_len = (size_t)ctx->tab[ctx->cur].cap + 1;
   SDPSR_TRY(sdpsr_scratch_t(ctx, 20, lut_len, &kr->lut1));
   SDPSR_CUDA(cudaMemcpyAsync(kr->lut1, ctx->lut, lut_len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  if (kr->lab8)
-    SDPSR_CUDA(cudaMemcpyAsync(kr->lutc + 256, kr->lutc, 256 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   // generic start vector: fixed pseudo-random sequence (identical on every rank).  Start vectors live
   // in the spare last column of the basis buffer (Lanczos uses columns 0 .. KR_MAX-1 only).
   double* startv = kr->V + ld * KR_MAX;

@@ -291,13 +291,13 @@ KRYLOV_PROBLEMS = [pr.petersen(), pr.lovasz_er(3), pr.lovasz_er(5), pr.lovasz_er
                    pr.kneser(10, 4), pr.hamming(3, 8), pr.hamming(5, 4)]
 
 
-@pytest.mark.parametrize("flags", [0, B.F_TINY_TABLE], ids=["byte-labels+single-pass-basis", "u32-labels+list-basis"])
+@pytest.mark.parametrize("flags", [0, B.F_TINY_TABLE], ids=["single-pass-basis", "list-basis"])
 @pytest.mark.parametrize("prob", KRYLOV_PROBLEMS, ids=lambda p: p.name)
 def test_krylov_block_diagonalize_matches_oracle_and_dense(prob, flags):
     """The matrix-free variant (csrc/krylov.cu) must be applicable on these few-eigenspace problems and
     reproduce the oracle's blocks, block order, multiplicities and the dense path's results.  With few
-    classes the products read byte labels and basis_image is the single-pass kernel; the TINY_TABLE hook
-    keeps the general kernels (u32 labels, per-class lists) under test."""
+    classes basis_image is the single-pass kernel; the TINY_TABLE hook keeps the general kernel
+    (per-class lists) under test."""
     Po = O.admissible_subspace(*prob, Coeffs(31))
     so, bo = O.blockDiagonalize(Po, Coeffs(32))
     Pk = S.Partition(Po.nparts, Po.matrix.astype(np.uint32))
