@@ -22,7 +22,8 @@
 //
 // Kernel structure (one persistent CTA per SM, 128 x 256 output tiles of the lower triangle):
 //   warp 0   TMA producer: cp.async.bulk.tensor.3d (k, row, slice) into a ring of SWIZZLE_128B tiles
-//   warp 1   one thread issues tcgen05.mma (M128 N256 K32) and tcgen05.commit
+//   warp 1   walks the schedule warp-uniformly; one elected lane issues tcgen05.mma (M128 N256 K32) and
+//            tcgen05.commit
 //   warp 2   TMEM allocation (512 columns = two 128 x 256 int32 accumulators: c and c+1)
 //   warps 4-7 epilogue: tcgen05.ld -> I2F -> FP64 fold into C (read-modify-write, L2 resident)
 // Two accumulators c0, c0+1 are live at a time, and the products that feed them form a path
@@ -31,6 +32,9 @@
 // needs exactly ONE new operand tile, so the L2 -> shared-memory traffic per MMA is half of what a
 // product-by-product schedule would load.  Because X is symmetric its slices serve as both the K-major
 // A operand (rows of X) and the K-major B operand (columns of X) with no transpose.
+// A second kernel runs the same schedule on CTA pairs (cta_group::2, 256 x 256 tiles); it is the default
+// for N > 16384 (see square_i8_2cta_kernel below and DESIGN.md 5b).  tests/i8_model.py is the host model
+// both kernels are held to, bit for bit.
 #include <cuda.h>
 
 #include <algorithm>
