@@ -753,7 +753,13 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits,
   if (e < -400 || e > 400) return SDPSR_OK;
   // ---- slices ----
   int8_t* slices = nullptr;
-  SDPSR_TRY(sdpsr_scratch_t(ctx, 26, (size_t)S * elems, &slices));
+  {
+    const int st = sdpsr_scratch_t(ctx, 26, (size_t)S * elems, &slices);
+    if (st != SDPSR_OK) {
+      if (force_range) return st;              // the caller asked for this path explicitly
+      return SDPSR_OK;                         // no room for the digit matrices: the DMMA path needs none
+    }
+  }
   {
     Timed tm(ctx, SDPSR_K_MISC, (double)elems * (8.0 + S));
     const double scale = std::ldexp(1.0, bits * (S - 1) + 6 - e);
