@@ -58,3 +58,33 @@ def owned_tiles_i8(n: int, nranks: int, rank: int):
                 if (tm + 1) * I8_TILE_M - 1 >= tn * I8_TILE_N:
                     out.append((tm, tn))
     return out
+
+
+def i8_product_path(c0: int):
+    """The operand-tile stream and the products of one accumulator pair (c0, c0+1) of the INT8 square,
+    as csrc/gemm_i8.cu walks them for one k-block: tiles T_0 = B_{c0+1}, T_1 = A_0, T_2 = B_{c0}, T_3 = A_1,
+    ..., and product j multiplies the consecutive tiles (T_j, T_{j+1}).  Returns (tiles, products) with
+    tiles = [("B"|"A", slice)] and products = [(s, t, accumulator)] (accumulator 0 holds c0, 1 holds c0+1).
+    c0 = -1 (odd number of slices) degenerates to the single product (A_0, B_0)."""
+    nch = c0 + 2
+    tiles = []
+    for i in range(nch):
+        tiles.append(("B", c0 + 1 - i))
+        tiles.append(("A", i))
+    products = []
+    for j in range(2 * c0 + 3):
+        ta, tb = tiles[j], tiles[j + 1]
+        a, b = (ta, tb) if ta[0] == "A" else (tb, ta)
+        assert a[0] == "A" and b[0] == "B"
+        products.append((a[1], b[1], 0 if j & 1 else 1))
+    return tiles, products
+
+
+def i8_schedule(slices: int):
+    """All products of one output tile and k-block: accumulator pairs from the smallest weight up."""
+    out = []
+    c0 = slices - 2
+    while c0 >= -1:
+        out.append((c0, *i8_product_path(c0)))
+        c0 -= 2
+    return out

@@ -55,6 +55,29 @@ def test_int8_tile_deal_covers_the_lower_triangle(n, nranks):
         assert max(counts) <= 1.15 * sum(counts) / nranks + 1
 
 
+@pytest.mark.parametrize("slices", [2, 3, 4, 5, 6, 7, 8])
+def test_int8_product_schedule_covers_every_pair_once(slices):
+    """csrc/gemm_i8.cu's zig-zag schedule: every ordered pair (s, t) with s + t < S is multiplied exactly
+    once into the accumulator of its weight, each product after the first of a path needs exactly one new
+    operand tile, and the paths have even length (B and A tiles alternate in the shared-memory ring)."""
+    seen = {}
+    loads = 0
+    for c0, tiles, products in sh.i8_schedule(slices):
+        assert len(tiles) == 2 * (c0 + 2) and len(products) == 2 * c0 + 3
+        assert [t[0] for t in tiles] == ["B", "A"] * (c0 + 2)
+        assert all(0 <= sl < slices for _, sl in tiles)
+        loads += len(tiles)
+        for s, t, acc in products:
+            assert (s, t) not in seen
+            assert s + t == c0 + acc                       # accumulator 0 <-> c0, accumulator 1 <-> c0 + 1
+            seen[(s, t)] = c0 + acc
+    want = {(s, t) for s in range(slices) for t in range(slices) if s + t < slices}
+    assert set(seen) == want
+    assert len(want) == slices * (slices + 1) // 2
+    # one new tile per product except the first of each path: loads = products + number of paths
+    assert loads == len(want) + len(sh.i8_schedule(slices))
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
