@@ -445,6 +445,9 @@ def main():
         "metric": METRIC, "value": sec_res, "unit": "s", "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": ms_res / K, "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "dtype_note": "values, rounding, keys and the block-diagonalisation are f64; X*X of a symmetric X runs as exact "
+                      "s8 x s8 -> s32 products of its digit slices (54 magnitude bits by default) folded in f64, "
+                      "an FP64-grade product (DESIGN.md 5b); every other product is f64 DMMA",
         "config": {"workload": args.workload, "N": N, "m": 2, "dim": dim, "blocks": sizes,
                    "iterations": tr.get("iterations"), "atol": ATOL, "eig": tr.get("eig_mode"),
                    "l2": "inputs larger than L2 (X is %.1f GB)" % (N * N * 8 / 1e9),
