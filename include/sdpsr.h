@@ -48,7 +48,7 @@ typedef enum sdpsr_status {
                                   src/eigen_decomposition.jl:247-253)                  */
   SDPSR_E_CUSOLVER = -7,       /* cuSOLVER syevd failed / did not converge              */
   SDPSR_E_STATE = -8,          /* call sequence error (e.g. square before fill)         */
-  SDPSR_E_SINGULAR = -9,       /* constraint rows linearly dependent (Gram singular)    */
+  SDPSR_E_SINGULAR = -9,       /* the constraint matrix has rank 0 (A == 0)             */
   SDPSR_E_NCCL = -10,          /* NCCL failure / NCCL library not loadable              */
   SDPSR_E_UNSUPPORTED = -11,   /* valid request outside this build's limits             */
   SDPSR_E_KRYLOV = -12         /* the Krylov block-diagonalisation path is not applicable
@@ -100,9 +100,9 @@ int sdpsr_device_count(int* count);
 
 /* ------------------------------------------------------------- constraints A
  * The `A` argument of admissible_subspace (src/partitions.jl:112).  The engine
- * derives from it the per-entry constraint pattern ids, the pattern table and a
- * factorisation of the Gram matrix A A' that replace `qr(A')` (src/partitions.jl:124)
- * in project_colspace! (src/utils.jl:62-66).
+ * derives from it the per-entry constraint pattern ids, the pattern table and a rank-revealing
+ * (pivoted Cholesky, extended precision) factorisation of the Gram matrix A A' that replace
+ * `qr(A')` (src/partitions.jl:124) in project_colspace! (src/utils.jl:62-66).
  *   dense: A is m x N^2 column-major (a Julia Matrix{Float64}), ld = m.
  *   csr  : row k holds entries rowptr[k]..rowptr[k+1]-1; this is the CSC storage of
  *          A' (N^2 x m), i.e. `SparseMatrixCSC(transpose(A))` in Julia.
@@ -115,6 +115,10 @@ int sdpsr_set_constraints_csc(sdpsr_ctx* ctx, int64_t m, const int64_t* colptr,
                               const int64_t* rowval, const double* nzval, int index_base);
 /* number of distinct non-empty constraint column patterns found */
 int sdpsr_constraint_patterns(sdpsr_ctx* ctx, int64_t* npatterns);
+/* numerical rank of A: rows that depend on the others (negligible pivot of the pivoted Cholesky of
+ * A A') are dropped from the projector, as the rank-revealing sparse `qr(A')` of the reference does
+ * (src/partitions.jl:124); the projection onto the row space is unchanged by that.              */
+int sdpsr_constraint_rank(sdpsr_ctx* ctx, int64_t* rank);
 
 /* ------------------------------------------------------------- Partition state
  * The context holds one Partition S (src/partitions.jl:6-9): labels 0..dim.         */
@@ -267,6 +271,14 @@ int sdpsr_launch_count(sdpsr_ctx* ctx, int64_t* launches);
 int sdpsr_comm_unique_id(void* id128 /* 128 bytes out */);
 int sdpsr_comm_init(sdpsr_ctx* ctx, int nranks, int rank, const void* id128);
 int sdpsr_comm_info(sdpsr_ctx* ctx, int* nranks, int* rank);
+/* In-process transport: `nranks` contexts of ONE process, each driven by its own host thread, on the
+ * same device or on different devices of the process (the sharded path must run with G
+ * ranks mapped onto one GPU).  Same sharding, same kernels and the same call sequence as with NCCL; the
+ * collectives are pointer exchanges + cudaMemcpy and the barrier is a host barrier, so no kernel waits
+ * for another rank's kernel.  Create one group, then every rank's thread calls sdpsr_comm_init_local
+ * (collective).  The group is freed when its last context is destroyed (sdpsr_destroy is collective).   */
+int sdpsr_comm_local_group(void** group, int nranks);
+int sdpsr_comm_init_local(sdpsr_ctx* ctx, void* group, int rank);
 
 #ifdef __cplusplus
 }

@@ -180,16 +180,23 @@ class RowSpaceProjector:
         G = self.A @ self.A.T
         self.G = np.asarray(G.todense() if self.sparse else G, dtype=np.float64)
         self._qr = None
-        if not self.sparse and self.m * self.m * self.n2 <= 2e8:
+        # Rank-deficient A (redundant constraint rows): the reference's sparse path is SuiteSparse's
+        # rank-revealing QR, whose projection is A' G^+ A; any least-squares solution of G c = A v gives
+        # the same A' c, so the minimum-norm one (lstsq) is used.
+        sv = np.linalg.svd(self.G, compute_uv=False)
+        self.rank_deficient = bool(sv.size and sv[-1] <= 1e-12 * sv[0])
+        if not self.sparse and self.m * self.m * self.n2 <= 2e8 and not self.rank_deficient:
             self._qr = np.linalg.qr(self.A.T)       # (N^2 x m) reduced QR
 
     def coefficients(self, v: np.ndarray) -> np.ndarray:
         if self._qr is not None:
             Q, R = self._qr
             return np.linalg.solve(R, Q.T @ v)
-        return np.linalg.solve(self.G, np.asarray(self.A @ v).reshape(-1))
+        return self.solve_gram(np.asarray(self.A @ v).reshape(-1))
 
     def solve_gram(self, b: np.ndarray) -> np.ndarray:
+        if self.rank_deficient:
+            return np.linalg.lstsq(self.G, b, rcond=1e-12)[0]
         return np.linalg.solve(self.G, b)
 
     def apply_transpose(self, coef: np.ndarray) -> np.ndarray:

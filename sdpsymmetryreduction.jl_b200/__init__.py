@@ -23,6 +23,7 @@ from .api import (  # noqa: F401
     randomize,
     reduce_problem,
     refine,
+    run_local_ranks,
     unSymmetrize,
 )
 from .binding import LibraryNotBuilt, SdpsrError, lib_path, load_library  # noqa: F401

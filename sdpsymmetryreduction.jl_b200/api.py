@@ -88,6 +88,40 @@ def clear_context_pool():
     _CTX_POOL.clear()
 
 
+def run_local_ranks(n: int, nranks: int, fn: Callable, *, devices=None, flags: int = 0):
+    """Run ``fn(ctx, rank)`` on ``nranks`` ranks of ONE process, one host thread per rank, joined by the
+    in-process communicator (``sdpsr_comm_init_local``).  ``devices[r]`` is the CUDA device of rank r
+    (default: all on device 0 -- the sharded path with G ranks mapped onto one GPU, SURVEY.md section 4;
+    with distinct devices it is the single-process multi-GPU mode).  Returns the list of results; the
+    first rank's exception is re-raised after every thread has finished."""
+    import threading
+    devices = list(devices) if devices is not None else [0] * nranks
+    group = B.Context.local_group(nranks)
+    results, errors = [None] * nranks, [None] * nranks
+
+    def worker(r):
+        ctx = None
+        try:
+            ctx = B.Context(n, devices[r], flags)
+            ctx.comm_init_local(group, r)
+            results[r] = fn(ctx, r)
+        except BaseException as e:          # noqa: BLE001 -- re-raised below
+            errors[r] = e
+        finally:
+            if ctx is not None:
+                ctx.close()                  # collective: every rank detaches
+
+    threads = [threading.Thread(target=worker, args=(r,), name=f"sdpsr-rank{r}") for r in range(nranks)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in errors:
+        if e is not None:
+            raise e
+    return results
+
+
 def _default_rand():
     rng = np.random.default_rng()
     return lambda n: rng.random(int(n))

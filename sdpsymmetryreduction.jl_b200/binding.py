@@ -55,6 +55,7 @@ _SIGNATURES = {
     "sdpsr_set_constraints_csr": ([_p, _i64, _p, _p, _p, C.c_int], C.c_int),
     "sdpsr_set_constraints_csc": ([_p, _i64, _p, _p, _p, C.c_int], C.c_int),
     "sdpsr_constraint_patterns": ([_p, C.POINTER(_i64)], C.c_int),
+    "sdpsr_constraint_rank": ([_p, C.POINTER(_i64)], C.c_int),
     "sdpsr_partition_reset": ([_p], C.c_int),
     "sdpsr_partition_set_labels": ([_p, _p, C.c_int, C.POINTER(_i64)], C.c_int),
     "sdpsr_partition_get_labels": ([_p, _p, C.c_int], C.c_int),
@@ -95,6 +96,8 @@ _SIGNATURES = {
     "sdpsr_comm_unique_id": ([_p], C.c_int),
     "sdpsr_comm_init": ([_p, C.c_int, C.c_int, _p], C.c_int),
     "sdpsr_comm_info": ([_p, C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
+    "sdpsr_comm_local_group": ([C.POINTER(_p), C.c_int], C.c_int),
+    "sdpsr_comm_init_local": ([_p, _p, C.c_int], C.c_int),
 }
 
 
@@ -215,6 +218,12 @@ class Context:
     def constraint_patterns(self) -> int:
         v = _i64(0)
         self._check(self.lib.sdpsr_constraint_patterns(self._h, C.byref(v)))
+        return v.value
+
+    def constraint_rank(self) -> int:
+        """Numerical rank of A (dependent rows are dropped by the projector)."""
+        v = _i64(0)
+        self._check(self.lib.sdpsr_constraint_rank(self._h, C.byref(v)))
         return v.value
 
     # -- partition ---------------------------------------------------------------
@@ -509,6 +518,19 @@ class Context:
     def comm_init(self, nranks: int, rank: int, uid: bytes):
         buf = C.create_string_buffer(uid, 128)
         self._check(self.lib.sdpsr_comm_init(self._h, nranks, rank, buf))
+
+    @staticmethod
+    def local_group(nranks: int):
+        """Handle of an in-process communicator for ``nranks`` contexts (one host thread per rank)."""
+        lib = load_library()
+        g = _p()
+        st = lib.sdpsr_comm_local_group(C.byref(g), int(nranks))
+        if st != OK:
+            raise SdpsrError(st, "sdpsr_comm_local_group failed")
+        return g
+
+    def comm_init_local(self, group, rank: int):
+        self._check(self.lib.sdpsr_comm_init_local(self._h, group, int(rank)))
 
     def comm_info(self):
         a, b = C.c_int(0), C.c_int(0)

@@ -1,10 +1,20 @@
-// comm.cu -- multi-GPU plumbing: one context per process / GPU, NCCL loaded with dlopen
-// so that single-GPU users need no NCCL at all.  The reference has no distributed code;
-// this is new surface.
+// comm.cu -- multi-GPU plumbing.  The reference has no distributed code; this is new surface
+// (SURVEY.md 8e).  Two transports behind one internal interface:
+//   * NCCL   one context per PROCESS / GPU (torchrun); libnccl is loaded with dlopen so that single-GPU
+//            users need no NCCL at all; big buffers move through CUDA-IPC peer mappings over NVLink;
+//   * local  G contexts of ONE process, one host thread per rank, on the same or on different devices
+//            ("the sharded path must also run with G ranks mapped onto one device").
+//            Collectives are pointer exchanges through a shared group object plus cudaMemcpy; the
+//            barrier is a host barrier after a stream synchronise.  No kernel ever waits for another
+//            rank's kernel, so G ranks can share one GPU.
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "sdpsr_internal.cuh"
@@ -54,6 +64,65 @@ NcclApi& api() {
   return a;
 }
 
+// ---- the in-process transport ------------------------------------------------------------------
+struct LocalGroup {
+  int nranks = 0;
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0;
+  uint64_t generation = 0;
+  int attached = 0;
+  bool broken = false;                         // a rank failed: every later collective errors out
+  void* posted[sdpsr_ctx::MAX_RANKS] = {};     // pointer exchange slots (valid between two barriers)
+  sdpsr_ctx* ctxs[sdpsr_ctx::MAX_RANKS] = {};
+};
+
+// false when a rank did not show up within the timeout (10 minutes, SDPSR_LOCAL_BARRIER_TIMEOUT_S; it failed or its thread died): the caller
+// reports an error instead of hanging the process
+bool local_host_barrier(LocalGroup* g) {
+  std::unique_lock<std::mutex> lk(g->mu);
+  if (g->broken) return false;
+  const uint64_t gen = g->generation;
+  if (++g->arrived == g->nranks) {
+    g->arrived = 0;
+    ++g->generation;
+    g->cv.notify_all();
+    return true;
+  }
+  static const int timeout_s = [] {
+    const char* e = getenv("SDPSR_LOCAL_BARRIER_TIMEOUT_S");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 600;
+  }();
+  if (!g->cv.wait_for(lk, std::chrono::seconds(timeout_s), [&] { return g->generation != gen || g->broken; }) || g->broken) {
+    g->broken = true;
+    g->cv.notify_all();
+    return false;
+  }
+  return true;
+}
+
+LocalGroup* local_of(sdpsr_ctx* ctx) { return reinterpret_cast<LocalGroup*>(ctx->local_group); }
+
+// stream-drain + host barrier: every rank's previously enqueued work is complete afterwards
+int local_barrier(sdpsr_ctx* ctx) {
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (!local_host_barrier(local_of(ctx)))
+    return ctx->fail(SDPSR_E_NCCL, "local communicator: a rank did not reach the barrier (it failed or left)");
+  return SDPSR_OK;
+}
+
+// copy `bytes` from rank r's device pointer into mine (same or another device of this process)
+int local_copy_from(sdpsr_ctx* ctx, void* dst, int r, const void* src, size_t bytes) {
+  LocalGroup* g = local_of(ctx);
+  const int sdev = g->ctxs[r]->device;
+  if (sdev == ctx->device)
+    SDPSR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  else
+    SDPSR_CUDA(cudaMemcpyPeerAsync(dst, ctx->device, src, sdev, bytes, ctx->stream));
+  return SDPSR_OK;
+}
+
 }  // namespace
 
 constexpr int NCCL_UINT8 = 1, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_MAX = 2;
@@ -72,6 +141,20 @@ int sdpsr_comm_exchange_tilecols(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t
                                  int ntilecols) {
   if (ctx->nranks <= 1) return SDPSR_OK;
   Timed tm(ctx, SDPSR_K_MISC, (double)ldc * (double)ncols * 8.0);
+  if (ctx->local_group) {
+    LocalGroup* g = local_of(ctx);
+    g->posted[ctx->rank] = C;
+    SDPSR_TRY(local_barrier(ctx));                 // every owner's slabs are complete and posted
+    for (int tn = 0; tn < ntilecols; ++tn) {
+      const int owner = tn % ctx->nranks;
+      if (owner == ctx->rank) continue;
+      const int64_t c0 = (int64_t)tn * tile_cols;
+      const int64_t w = std::min<int64_t>(tile_cols, ncols - c0);
+      SDPSR_TRY(local_copy_from(ctx, C + ldc * c0, owner, reinterpret_cast<double*>(g->posted[owner]) + ldc * c0,
+                                (size_t)(ldc * w) * sizeof(double)));
+    }
+    return local_barrier(ctx);                     // nobody overwrites a slab that is still being read
+  }
   NCCL_TRY(api().GroupStart());
   for (int tn = 0; tn < ntilecols; ++tn) {
     const int64_t c0 = (int64_t)tn * tile_cols;
@@ -86,18 +169,54 @@ int sdpsr_comm_exchange_tilecols(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t
 
 int sdpsr_comm_bcast(sdpsr_ctx* ctx, void* buf, size_t bytes, int root) {
   if (ctx->nranks <= 1) return SDPSR_OK;
+  if (ctx->local_group) {
+    LocalGroup* g = local_of(ctx);
+    g->posted[ctx->rank] = buf;
+    SDPSR_TRY(local_barrier(ctx));
+    if (ctx->rank != root) SDPSR_TRY(local_copy_from(ctx, buf, root, g->posted[root], bytes));
+    return local_barrier(ctx);
+  }
   NCCL_TRY(api().Broadcast(buf, buf, bytes, NCCL_UINT8, root, (ncclComm_t)ctx->nccl, ctx->stream));
   return SDPSR_OK;
 }
 
-int sdpsr_comm_allreduce_max_u64(sdpsr_ctx* ctx, unsigned long long* buf, size_t count) {
+// recv holds nranks blocks of `bytes`; block `rank` is this rank's contribution (already in place)
+int sdpsr_comm_allgather(sdpsr_ctx* ctx, void* recv, size_t bytes) {
   if (ctx->nranks <= 1) return SDPSR_OK;
-  NCCL_TRY(api().AllReduce(buf, buf, count, NCCL_UINT64, NCCL_MAX, (ncclComm_t)ctx->nccl, ctx->stream));
+  unsigned char* base = reinterpret_cast<unsigned char*>(recv);
+  if (ctx->local_group) {
+    LocalGroup* g = local_of(ctx);
+    g->posted[ctx->rank] = recv;
+    SDPSR_TRY(local_barrier(ctx));
+    for (int r = 0; r < ctx->nranks; ++r)
+      if (r != ctx->rank)
+        SDPSR_TRY(local_copy_from(ctx, base + bytes * r, r, reinterpret_cast<unsigned char*>(g->posted[r]) + bytes * r, bytes));
+    return local_barrier(ctx);
+  }
+  NCCL_TRY(api().AllGather(base + bytes * ctx->rank, base, bytes, NCCL_UINT8, (ncclComm_t)ctx->nccl, ctx->stream));
+  return SDPSR_OK;
+}
+
+// Every rank passes a host flag; all receive the minimum (used to agree on a code path: a branch that
+// contains collectives must be taken by every rank or by none).  Blocking.
+int sdpsr_comm_agree_min(sdpsr_ctx* ctx, int* flag) {
+  if (ctx->nranks <= 1) return SDPSR_OK;
+  int* d_all = nullptr;
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 28, (size_t)sdpsr_ctx::MAX_RANKS, &d_all));
+  SDPSR_CUDA(cudaMemcpyAsync(d_all + ctx->rank, flag, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  SDPSR_TRY(sdpsr_comm_allgather(ctx, d_all, sizeof(int)));
+  int h[sdpsr_ctx::MAX_RANKS];
+  SDPSR_CUDA(cudaMemcpyAsync(h, d_all, sizeof(int) * (size_t)ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  int m = h[0];
+  for (int r = 1; r < ctx->nranks; ++r) m = std::min(m, h[r]);
+  *flag = m;
   return SDPSR_OK;
 }
 
 int sdpsr_comm_barrier(sdpsr_ctx* ctx) {
   if (ctx->nranks <= 1) return SDPSR_OK;
+  if (ctx->local_group) return local_barrier(ctx);
   NCCL_TRY(api().AllReduce(ctx->d_barrier, ctx->d_barrier, 1, /*ncclInt32*/ 2, /*ncclSum*/ 0, (ncclComm_t)ctx->nccl,
                            ctx->stream));
   return SDPSR_OK;
@@ -110,6 +229,38 @@ double* const* sdpsr_comm_peer_table(sdpsr_ctx* ctx, const double* C) {
   for (int b = 0; b < 3; ++b)
     if (C == mine[b]) return ctx->d_peer + b * sdpsr_ctx::MAX_RANKS;
   return nullptr;
+}
+
+// local transport: the peers are contexts of this process, their buffers are plain device pointers
+static int setup_peer_buffers_local(sdpsr_ctx* ctx) {
+  LocalGroup* g = local_of(ctx);
+  const int G = ctx->nranks;
+  SDPSR_TRY(sdpsr_ensure_matrix(ctx, &ctx->T));
+  SDPSR_TRY(sdpsr_ensure_matrix(ctx, &ctx->W));
+  SDPSR_TRY(local_barrier(ctx));                   // every rank has registered and allocated
+  bool ok = true;
+  for (int r = 0; r < G; ++r) {
+    sdpsr_ctx* o = g->ctxs[r];
+    if (o->device != ctx->device) {
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, ctx->device, o->device) != cudaSuccess || !can) ok = false;
+      if (ok) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+        cudaGetLastError();
+      }
+    }
+    ctx->peer_ptr[0][r] = o->X2;
+    ctx->peer_ptr[1][r] = o->T;
+    ctx->peer_ptr[2][r] = o->W;
+  }
+  SDPSR_CUDA(cudaMalloc(&ctx->d_peer, sizeof(double*) * 3 * sdpsr_ctx::MAX_RANKS));
+  SDPSR_CUDA(cudaMemcpyAsync(ctx->d_peer, ctx->peer_ptr, sizeof(double*) * 3 * sdpsr_ctx::MAX_RANKS,
+                             cudaMemcpyHostToDevice, ctx->stream));
+  int flag = ok ? 1 : 0;
+  SDPSR_TRY(sdpsr_comm_agree_min(ctx, &flag));
+  ctx->peer_ok = flag == 1 && !(ctx->flags & SDPSR_F_NCCL_EXCHANGE);
+  return SDPSR_OK;
 }
 
 // Map every rank's X2 / T / W into this process (CUDA IPC over NVLink peer access).
@@ -170,6 +321,21 @@ void sdpsr_comm_free(sdpsr_ctx* ctx) {
   // (freeing exported memory that is still mapped elsewhere is undefined).  Every rank must destroy its
   // context (collective, like the communicator itself).
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->local_group) {
+    // collective: nobody frees a buffer that a peer's kernel may still be storing into
+    LocalGroup* g = local_of(ctx);
+    local_host_barrier(g);
+    bool last;
+    {
+      std::lock_guard<std::mutex> lk(g->mu);
+      g->ctxs[ctx->rank] = nullptr;
+      last = --g->attached == 0;
+    }
+    if (last) delete g;
+    ctx->local_group = nullptr;
+    for (int b = 0; b < 3; ++b)
+      for (int r = 0; r < sdpsr_ctx::MAX_RANKS; ++r) ctx->peer_ptr[b][r] = nullptr;
+  }
   for (int b = 0; b < 3; ++b)
     for (int r = 0; r < sdpsr_ctx::MAX_RANKS; ++r) {
       if (ctx->peer_ptr[b][r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->peer_ptr[b][r]);
@@ -218,6 +384,33 @@ extern "C" int sdpsr_comm_init(sdpsr_ctx* ctx, int nranks, int rank, const void*
   ctx->nranks = nranks;
   ctx->rank = rank;
   if (nranks > 1) SDPSR_TRY(setup_peer_buffers(ctx));
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_comm_local_group(void** group, int nranks) {
+  if (!group || nranks < 1 || nranks > sdpsr_ctx::MAX_RANKS) return SDPSR_E_INVALID;
+  LocalGroup* g = new LocalGroup();
+  g->nranks = nranks;
+  *group = g;
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_comm_init_local(sdpsr_ctx* ctx, void* group, int rank) {
+  if (!ctx) return SDPSR_E_INVALID;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return ctx->fail(SDPSR_E_CUDA, "cudaSetDevice failed");
+  LocalGroup* g = reinterpret_cast<LocalGroup*>(group);
+  SDPSR_REQUIRE(g && rank >= 0 && rank < g->nranks, SDPSR_E_INVALID, "bad local communicator arguments");
+  sdpsr_comm_free(ctx);
+  {
+    std::lock_guard<std::mutex> lk(g->mu);
+    SDPSR_REQUIRE(g->ctxs[rank] == nullptr, SDPSR_E_INVALID, "rank already attached to this group");
+    g->ctxs[rank] = ctx;
+    ++g->attached;
+  }
+  ctx->local_group = g;
+  ctx->nranks = g->nranks;
+  ctx->rank = rank;
+  if (g->nranks > 1) SDPSR_TRY(setup_peer_buffers_local(ctx));
   return SDPSR_OK;
 }
 

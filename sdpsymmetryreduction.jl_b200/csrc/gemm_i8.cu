@@ -755,8 +755,13 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits,
   int8_t* slices = nullptr;
   {
     const int st = sdpsr_scratch_t(ctx, 26, (size_t)S * elems, &slices);
-    if (st != SDPSR_OK) {
-      if (force_range) return st;              // the caller asked for this path explicitly
+    // Allocation success is the one rank-LOCAL condition on this path (everything above is a function of
+    // the replicated X): with several ranks the branch is agreed on, because both continuations contain
+    // collectives (peer stores + barriers here, the sharded DMMA GEMM's own sequence otherwise).
+    int have = st == SDPSR_OK ? 1 : 0;
+    if (shard && ctx->nranks > 1) SDPSR_TRY(sdpsr_comm_agree_min(ctx, &have));
+    if (!have) {
+      if (force_range) return st != SDPSR_OK ? st : ctx->fail(SDPSR_E_ALLOC, "int8 square: another rank has no room for the digit matrices");
       return SDPSR_OK;                         // no room for the digit matrices: the DMMA path needs none
     }
   }

@@ -10,7 +10,8 @@
 //     with a pattern id, and t[p] = sum_k A[k,p] c[k] (ascending k, separate multiply and
 //     add -- the order of Julia's sparse mul!) is evaluated once per pattern on the host;
 //   * A v needs only the stored non-zeros: a deterministic chunked gather-dot.
-// The m x m Gram system is solved on the host (m <= a few hundred).
+// The m x m Gram system is solved on the host (m <= a few hundred) with a rank-revealing pivoted
+// Cholesky in extended precision: dependent constraint rows are dropped, as a rank-revealing QR would.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -293,48 +294,67 @@ int sdpsr_symmetric_check(sdpsr_ctx* ctx, int* is_sym) {
   return SDPSR_OK;
 }
 
-// LU with partial pivoting of the m x m Gram matrix (row-major), in place
-static bool lu_factor(std::vector<double>& a, std::vector<int>& piv, int m) {
-  piv.resize(m);
-  double amax = 0.0;
-  for (double v : a) amax = std::max(amax, std::fabs(v));
+// Rank-revealing factorisation of the Gram matrix G = A A' (symmetric positive semidefinite): Cholesky
+// with diagonal pivoting in extended precision.  The reference projects with `qr(A')`
+// (src/partitions.jl:124, src/utils.jl:62-66), which for sparse A is SuiteSparse's rank-revealing QR; a
+// constraint row that depends (numerically) on the rows kept so far shows up here as a negligible pivot
+// of the Schur complement and is dropped: the projector onto the row space -- and the minimum-norm
+// solution of a consistent A x = b -- do not change when such a row is left out.  Extended precision
+// (64-bit mantissa) keeps the solve of the squared-condition system at the accuracy a QR of A' has in
+// double: the error of the PROJECTION A' G^-1 (A v) is governed by cond(A), not cond(A)^2, once the
+// solve itself is exact to working precision.
+static void gram_factor(ConstraintSet& c, const std::vector<long double>& G, int m) {
+  std::vector<long double> a(G);
+  c.gram_chol.assign((size_t)m * m, 0.0L);
+  c.gram_perm.resize((size_t)m);
+  for (int i = 0; i < m; ++i) c.gram_perm[(size_t)i] = i;
+  long double dmax = 0.0L;
+  for (int i = 0; i < m; ++i) dmax = std::max(dmax, a[(size_t)i * m + i]);
+  const long double tol = 1e-13L * dmax;
+  int rank = 0;
+  std::vector<long double>& L = c.gram_chol;
   for (int k = 0; k < m; ++k) {
     int p = k;
-    double best = std::fabs(a[(size_t)k * m + k]);
     for (int i = k + 1; i < m; ++i)
-      if (std::fabs(a[(size_t)i * m + k]) > best) {
-        best = std::fabs(a[(size_t)i * m + k]);
-        p = i;
-      }
-    if (!(best > 1e-13 * amax)) return false;
-    piv[k] = p;
-    if (p != k)
+      if (a[(size_t)i * m + i] > a[(size_t)p * m + p]) p = i;
+    if (!(a[(size_t)p * m + p] > tol)) break;            // the remaining rows depend on the ones kept
+    if (p != k) {                                         // symmetric interchange of k and p
       for (int j = 0; j < m; ++j) std::swap(a[(size_t)k * m + j], a[(size_t)p * m + j]);
-    for (int i = k + 1; i < m; ++i) {
-      const double f = a[(size_t)i * m + k] / a[(size_t)k * m + k];
-      a[(size_t)i * m + k] = f;
-      for (int j = k + 1; j < m; ++j) a[(size_t)i * m + j] -= f * a[(size_t)k * m + j];
+      for (int i = 0; i < m; ++i) std::swap(a[(size_t)i * m + k], a[(size_t)i * m + p]);
+      for (int j = 0; j < k; ++j) std::swap(L[(size_t)k * m + j], L[(size_t)p * m + j]);
+      std::swap(c.gram_perm[(size_t)k], c.gram_perm[(size_t)p]);
     }
+    const long double d = std::sqrt(a[(size_t)k * m + k]);
+    L[(size_t)k * m + k] = d;
+    for (int i = k + 1; i < m; ++i) L[(size_t)i * m + k] = a[(size_t)i * m + k] / d;
+    for (int i = k + 1; i < m; ++i)
+      for (int j = k + 1; j <= i; ++j) {
+        a[(size_t)i * m + j] -= L[(size_t)i * m + k] * L[(size_t)j * m + k];
+        a[(size_t)j * m + i] = a[(size_t)i * m + j];
+      }
+    rank = k + 1;
   }
-  return true;
+  c.gram_rank = rank;
 }
 
+// x <- G^+ x restricted to the retained rows (dropped rows get coefficient 0)
 int sdpsr_solve_gram(sdpsr_ctx* ctx, std::vector<double>& x) {
   ConstraintSet& c = ctx->cons;
-  const int m = (int)c.m;
-  const std::vector<double>& a = c.gram_lu;
-  for (int k = 0; k < m; ++k)
-    if (c.gram_piv[k] != k) std::swap(x[k], x[c.gram_piv[k]]);
-  for (int i = 1; i < m; ++i) {
-    double s = x[i];
-    for (int j = 0; j < i; ++j) s -= a[(size_t)i * m + j] * x[j];
-    x[i] = s;
+  const int m = (int)c.m, r = c.gram_rank;
+  const std::vector<long double>& L = c.gram_chol;
+  std::vector<long double> y((size_t)r);
+  for (int i = 0; i < r; ++i) {
+    long double s = (long double)x[(size_t)c.gram_perm[(size_t)i]];
+    for (int j = 0; j < i; ++j) s -= L[(size_t)i * m + j] * y[(size_t)j];
+    y[(size_t)i] = s / L[(size_t)i * m + i];
   }
-  for (int i = m - 1; i >= 0; --i) {
-    double s = x[i];
-    for (int j = i + 1; j < m; ++j) s -= a[(size_t)i * m + j] * x[j];
-    x[i] = s / a[(size_t)i * m + i];
+  for (int i = r - 1; i >= 0; --i) {
+    long double s = y[(size_t)i];
+    for (int j = i + 1; j < r; ++j) s -= L[(size_t)j * m + i] * y[(size_t)j];
+    y[(size_t)i] = s / L[(size_t)i * m + i];
   }
+  std::fill(x.begin(), x.end(), 0.0);
+  for (int i = 0; i < r; ++i) x[(size_t)c.gram_perm[(size_t)i]] = (double)y[(size_t)i];
   return SDPSR_OK;
 }
 
@@ -496,13 +516,16 @@ int sdpsr_constraints_finalize(sdpsr_ctx* ctx) {
     SDPSR_REQUIRE(tot == nnz, SDPSR_E_CUDA, "internal: constraint pattern signature collision");
   }
   // ---- Gram matrix G = A A' = sum_p cnt[p] v_p v_p' and its LU ----------------------------
-  c.gram_lu.assign((size_t)m * m, 0.0);
-  for (int64_t p = 1; p <= npat; ++p)
-    for (int64_t e1 = c.pat_ptr[p]; e1 < c.pat_ptr[p + 1]; ++e1)
-      for (int64_t e2 = c.pat_ptr[p]; e2 < c.pat_ptr[p + 1]; ++e2)
-        c.gram_lu[(size_t)c.pat_row[e1] * m + c.pat_row[e2]] += (double)cnt[(size_t)p] * c.pat_val[e1] * c.pat_val[e2];
-  SDPSR_REQUIRE(lu_factor(c.gram_lu, c.gram_piv, (int)m), SDPSR_E_SINGULAR,
-                "constraint rows are linearly dependent (A A' is singular)");
+  {
+    std::vector<long double> G((size_t)m * m, 0.0L);
+    for (int64_t p = 1; p <= npat; ++p)
+      for (int64_t e1 = c.pat_ptr[p]; e1 < c.pat_ptr[p + 1]; ++e1)
+        for (int64_t e2 = c.pat_ptr[p]; e2 < c.pat_ptr[p + 1]; ++e2)
+          G[(size_t)c.pat_row[e1] * m + c.pat_row[e2]] +=
+              (long double)cnt[(size_t)p] * (long double)c.pat_val[e1] * (long double)c.pat_val[e2];
+    gram_factor(c, G, (int)m);
+  }
+  SDPSR_REQUIRE(c.gram_rank >= 1, SDPSR_E_SINGULAR, "the constraint matrix A is zero");
   SDPSR_TRY(sdpsr_scratch_t(ctx, 14, (size_t)npat + 1, &c.d_tpat));
   SDPSR_CUDA(cudaMemsetAsync(c.d_tpat, 0, ((size_t)npat + 1) * sizeof(double), ctx->stream));
   c.ready = true;
@@ -606,6 +629,13 @@ extern "C" int sdpsr_constraint_patterns(sdpsr_ctx* ctx, int64_t* npatterns) {
   CTX_ENTER();
   SDPSR_REQUIRE(ctx->cons.ready && npatterns, SDPSR_E_STATE, "constraints not set");
   *npatterns = ctx->cons.npat;
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_constraint_rank(sdpsr_ctx* ctx, int64_t* rank) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(ctx->cons.ready && rank, SDPSR_E_STATE, "constraints not set");
+  *rank = ctx->cons.gram_rank;
   return SDPSR_OK;
 }
 

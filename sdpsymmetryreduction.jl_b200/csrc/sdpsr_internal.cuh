@@ -68,8 +68,9 @@ struct ConstraintSet {
   std::vector<double> pat_val;
   std::vector<int64_t> pat_cnt;  // [npat+1]
   std::vector<uint32_t> chunk_row;   // host copy
-  std::vector<double> gram_lu;   // m x m LU factors (row-major) of A A'
-  std::vector<int> gram_piv;
+  std::vector<long double> gram_chol;   // m x m pivoted Cholesky factor (row-major) of A A'
+  std::vector<int> gram_perm;           // pivot order: gram_perm[i] = constraint row eliminated i-th
+  int gram_rank = 0;                    // numerical rank of A; rows gram_perm[rank..] are dependent (dropped)
   double* d_tpat = nullptr;      // [npat+1]
   // host CSR copy (needed to read pattern columns)
   std::vector<int64_t> h_rowptr;
@@ -157,6 +158,7 @@ struct sdpsr_ctx {
 
   // comm (multi-GPU)
   void* nccl = nullptr;
+  void* local_group = nullptr;  // in-process transport (comm.cu): G contexts of one process, one thread each
   int nranks = 1, rank = 0;
   void* d_tiles = nullptr;      // this rank's (tm, tn) tile list for sharded GEMMs
   size_t tile_alloc = 0;
@@ -277,7 +279,8 @@ void sdpsr_krylov_free(sdpsr_ctx* ctx);
 void sdpsr_comm_free(sdpsr_ctx* ctx);
 int sdpsr_comm_exchange_tilecols(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t ncols, int tile_cols, int ntilecols);
 int sdpsr_comm_bcast(sdpsr_ctx* ctx, void* buf, size_t bytes, int root);
-int sdpsr_comm_allreduce_max_u64(sdpsr_ctx* ctx, unsigned long long* buf, size_t count);
+int sdpsr_comm_allgather(sdpsr_ctx* ctx, void* recv, size_t bytes_per_rank);
+int sdpsr_comm_agree_min(sdpsr_ctx* ctx, int* flag);
 int sdpsr_comm_barrier(sdpsr_ctx* ctx);
 double* const* sdpsr_comm_peer_table(sdpsr_ctx* ctx, const double* C);
 int sdpsr_ensure_matrix(sdpsr_ctx* ctx, double** p);

@@ -190,6 +190,20 @@ def krawtchouk(d: int, q: int) -> np.ndarray:
     return K
 
 
+def eberlein(v: int, k: int) -> np.ndarray:
+    """E[i, j] = E_i(j): eigenvalue of the relation |A & B| = k - i of the Johnson scheme J(v,k) on the
+    j-th eigenspace (Eberlein polynomial; value pin for the Kneser configs, SURVEY.md 8(d) cfg 4).
+    Row k is the Kneser graph K(v,k): (-1)^j C(v-k-j, k-j)."""
+    from math import comb
+    d = min(k, v - k)
+    E = np.zeros((d + 1, d + 1))
+    for i in range(d + 1):
+        for j in range(d + 1):
+            E[i, j] = sum((-1) ** h * comb(j, h) * comb(k - j, i - h) * comb(v - k - j, i - h)
+                          for h in range(0, i + 1) if i - h <= k - j and i - h <= v - k - j)
+    return E
+
+
 # ----------------------------------------------------------------------------
 # QAP relaxation
 # ----------------------------------------------------------------------------

@@ -13,6 +13,22 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: full-size configuration that takes minutes (N = 32768)")
+
+
+def _cuda_device_present() -> bool:
+    """True when this machine has an NVIDIA device node.  Deliberately NOT a call into the engine: on
+    a GPU box a missing / unloadable libsdpsr_cuda.so must fail the GPU tests loudly, not skip them."""
+    return os.path.exists("/dev/nvidiactl") or os.path.exists("/dev/nvidia0")
+
+
+def pytest_collection_modifyitems(config, items):
+    if _cuda_device_present():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device on this machine (the engine has no CPU fallback)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
 
 
 class Coeffs:

@@ -753,9 +753,54 @@ def test_argument_errors():
         with pytest.raises(B.SdpsrError) as e:
             ctx.square_round_refine(ATOL)                          # no X yet
         assert e.value.code == B.E_STATE
+        with pytest.raises(B.SdpsrError) as e:
+            ctx.set_constraints(np.zeros((2, 16)))                 # A == 0: nothing to project onto
+        assert e.value.code == B.E_SINGULAR
         A = np.zeros((2, 16))
         A[0, :4] = 1.0
-        A[1, :4] = 2.0                                             # dependent rows: A A' singular
-        with pytest.raises(B.SdpsrError) as e:
-            ctx.set_constraints(A)
-        assert e.value.code == B.E_SINGULAR
+        A[1, :4] = 2.0                                             # dependent rows: the second one is dropped
+        ctx.set_constraints(A)
+        assert ctx.constraint_rank() == 1
+
+
+def _with_extra_rows(prob, rows, rhs):
+    import scipy.sparse as sp
+    A = prob.A
+    if sp.issparse(A):
+        A2 = sp.vstack([A] + [sp.csr_matrix(r) for r in rows]).tocsr()
+    else:
+        A2 = np.vstack([A] + [np.asarray(r).reshape(1, -1) for r in rows])
+    return A2, np.concatenate([prob.b, np.asarray(rhs, dtype=np.float64)])
+
+
+@pytest.mark.parametrize("prob", [pr.lovasz_er(5), pr.qap_esc16j(os.path.join(GOLDEN, "esc16j.npz"))],
+                         ids=lambda p: p.name)
+def test_redundant_constraint_rows(prob):
+    """A row that is a combination of other rows does not change the row space: same partition as the
+    original problem (the reference's sparse `qr(A')` is rank-revealing, src/partitions.jl:124).  The
+    engine's pivoted Cholesky of A A' must drop it instead of failing."""
+    A = prob.A
+    r0 = A[0] + A[1] if not hasattr(A, "tocsr") else (A.tocsr()[0] + A.tocsr()[1])
+    A2, b2 = _with_extra_rows(prob, [r0, r0 * 0.5], [prob.b[0] + prob.b[1], 0.5 * (prob.b[0] + prob.b[1])])
+    Po = O.admissible_subspace(prob.C, prob.A, prob.b, Coeffs(21))
+    Pg = S.admissible_subspace(prob.C, A2, b2, rand=Coeffs(21))
+    assert Pg._ctx.constraint_rank() == prob.A.shape[0]
+    assert Pg.nparts == Po.nparts == prob.expected_dim
+    assert np.array_equal(Pg.matrix, Po.matrix)
+    Po2 = O.admissible_subspace(prob.C, A2, b2, Coeffs(21))      # the oracle's least-squares route agrees
+    assert np.array_equal(Po2.matrix, Po.matrix)
+    Pg.release()
+
+
+@pytest.mark.parametrize("eps", [1e-3, 1e-5])
+def test_nearly_dependent_constraint_rows(eps):
+    """Rows (a0, a0 + eps*a1) span the same space as (a0, a1) with cond(A) ~ 1/eps: the projection must not
+    lose cond(A)^2 digits (normal equations in double would)."""
+    prob = pr.lovasz_er(7)
+    A = np.asarray(prob.A, dtype=np.float64)
+    A2 = np.vstack([A[0], A[0] + eps * A[1]])
+    b2 = np.array([prob.b[0], prob.b[0] + eps * prob.b[1]])
+    Po = O.admissible_subspace(prob.C, prob.A, prob.b, Coeffs(22))
+    Pg = S.admissible_subspace(prob.C, A2, b2, rand=Coeffs(22), keep_context=False)
+    assert Pg.nparts == Po.nparts == prob.expected_dim
+    assert np.array_equal(Pg.matrix, Po.matrix)
