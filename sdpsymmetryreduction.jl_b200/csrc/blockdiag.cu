@@ -8,8 +8,10 @@
 // The scalar decisions in between (eigenvalue clustering, Otsu threshold, union-find,
 // consistency check) stay in the host language, exactly as the reference has them.
 #include <cusolverDn.h>
+#include <dlfcn.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 
@@ -371,6 +373,63 @@ int sdpsr_ensure_matrix(sdpsr_ctx* ctx, double** p) { return ensure_buffer(ctx, 
 
 namespace {
 
+// cuSOLVER is loaded with dlopen, the CUDA toolkit's copy first.  A host framework loaded into the same
+// process may bring an older libcusolver.so.11 under the same SONAME (PyTorch 2.11+cu128 bundles 11.7.3,
+// whose 64-bit Xsyevd_bufferSize rejects n = 32768 with INVALID_VALUE); binding by SONAME would silently
+// pick that one.  Order: $SDPSR_CUSOLVER_LIB, the toolkit path this library was built against, the SONAME.
+struct SolverApi {
+  void* lib = nullptr;
+  std::string path;
+  decltype(&cusolverDnCreate) Create = nullptr;
+  decltype(&cusolverDnDestroy) Destroy = nullptr;
+  decltype(&cusolverDnSetStream) SetStream = nullptr;
+  decltype(&cusolverDnCreateParams) CreateParams = nullptr;
+  decltype(&cusolverDnDestroyParams) DestroyParams = nullptr;
+  decltype(&cusolverDnXsyevd_bufferSize) Xsyevd_bufferSize = nullptr;
+  decltype(&cusolverDnXsyevd) Xsyevd = nullptr;
+  decltype(&cusolverDnXgeev_bufferSize) Xgeev_bufferSize = nullptr;
+  decltype(&cusolverDnXgeev) Xgeev = nullptr;
+  bool ok = false;
+};
+
+SolverApi& sapi() {
+  static SolverApi a;
+  static bool tried = false;
+  if (tried) return a;
+  tried = true;
+  std::vector<std::string> names;
+  if (const char* e = getenv("SDPSR_CUSOLVER_LIB")) names.push_back(e);
+  names.push_back("/usr/local/cuda/lib64/libcusolver.so.11");
+  names.push_back("libcusolver.so.11");
+  names.push_back("libcusolver.so");
+  for (const std::string& nme : names) {
+    void* h = dlopen(nme.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!h) continue;
+    SolverApi t;
+    t.lib = h;
+    t.path = nme;
+#define SDPSR_SYM(field, sym) t.field = reinterpret_cast<decltype(t.field)>(dlsym(h, #sym))
+    SDPSR_SYM(Create, cusolverDnCreate);
+    SDPSR_SYM(Destroy, cusolverDnDestroy);
+    SDPSR_SYM(SetStream, cusolverDnSetStream);
+    SDPSR_SYM(CreateParams, cusolverDnCreateParams);
+    SDPSR_SYM(DestroyParams, cusolverDnDestroyParams);
+    SDPSR_SYM(Xsyevd_bufferSize, cusolverDnXsyevd_bufferSize);
+    SDPSR_SYM(Xsyevd, cusolverDnXsyevd);
+    SDPSR_SYM(Xgeev_bufferSize, cusolverDnXgeev_bufferSize);
+    SDPSR_SYM(Xgeev, cusolverDnXgeev);
+#undef SDPSR_SYM
+    t.ok = t.Create && t.Destroy && t.SetStream && t.CreateParams && t.DestroyParams && t.Xsyevd_bufferSize &&
+           t.Xsyevd && t.Xgeev_bufferSize && t.Xgeev;
+    if (t.ok) {
+      a = t;
+      break;
+    }
+    dlclose(h);
+  }
+  return a;
+}
+
 struct Solver {
   cusolverDnHandle_t h = nullptr;
   cusolverDnParams_t params = nullptr;
@@ -382,8 +441,8 @@ struct Solver {
 void sdpsr_blockdiag_free(sdpsr_ctx* ctx) {
   if (ctx->solver) {
     Solver* s = reinterpret_cast<Solver*>(ctx->solver);
-    if (s->params) cusolverDnDestroyParams(s->params);
-    if (s->h) cusolverDnDestroy(s->h);
+    if (s->params) sapi().DestroyParams(s->params);
+    if (s->h) sapi().Destroy(s->h);
     cudaFree(s->d_vals);
     delete s;
     ctx->solver = nullptr;
@@ -407,7 +466,7 @@ void sdpsr_blockdiag_free(sdpsr_ctx* ctx) {
 }
 
 void sdpsr_blockdiag_rebind(sdpsr_ctx* ctx) {
-  if (ctx->solver) cusolverDnSetStream(reinterpret_cast<Solver*>(ctx->solver)->h, ctx->stream);
+  if (ctx->solver) sapi().SetStream(reinterpret_cast<Solver*>(ctx->solver)->h, ctx->stream);
 }
 
 #define CTX_ENTER()                 \
@@ -443,21 +502,25 @@ extern "C" int sdpsr_eig(sdpsr_ctx* ctx, const double* r1, int64_t len, double* 
   if (!ctx->solver) {
     Solver* s = new Solver();
     ctx->solver = s;
-    SDPSR_REQUIRE(cusolverDnCreate(&s->h) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER, "cusolverDnCreate failed");
-    SDPSR_REQUIRE(cusolverDnSetStream(s->h, ctx->stream) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
+    SDPSR_REQUIRE(sapi().ok, SDPSR_E_CUSOLVER, "libcusolver.so.11 could not be loaded");
+    SDPSR_REQUIRE(sapi().Create(&s->h) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER, "cusolverDnCreate failed");
+    SDPSR_REQUIRE(sapi().SetStream(s->h, ctx->stream) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
                   "cusolverDnSetStream failed");
-    SDPSR_REQUIRE(cusolverDnCreateParams(&s->params) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
+    SDPSR_REQUIRE(sapi().CreateParams(&s->params) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
                   "cusolverDnCreateParams failed");
     SDPSR_CUDA(cudaMalloc(&s->d_vals, (size_t)ctx->n * sizeof(double)));
     SDPSR_CUDA(cudaMalloc(&ctx->solver_info, sizeof(int)));
   }
   Solver* s = reinterpret_cast<Solver*>(ctx->solver);
   size_t wdev = 0, whost = 0;
-  if (ctx->rank == 0)
-  SDPSR_REQUIRE(cusolverDnXsyevd_bufferSize(s->h, s->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, ctx->n,
-                                            CUDA_R_64F, ctx->Q, ctx->ld, CUDA_R_64F, s->d_vals, CUDA_R_64F, &wdev,
-                                            &whost) == CUSOLVER_STATUS_SUCCESS,
-                SDPSR_E_CUSOLVER, "cusolverDnXsyevd_bufferSize failed");
+  if (ctx->rank == 0) {
+    const cusolverStatus_t bs =
+        sapi().Xsyevd_bufferSize(s->h, s->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, ctx->n, CUDA_R_64F,
+                                    ctx->Q, ctx->ld, CUDA_R_64F, s->d_vals, CUDA_R_64F, &wdev, &whost);
+    SDPSR_REQUIRE(bs == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
+                  "cusolverDnXsyevd_bufferSize failed (status " + std::to_string((int)bs) + ", n = " +
+                      std::to_string(ctx->n) + ", " + sapi().path + ")");
+  }
   if (wdev > ctx->solver_work_bytes) {
     cudaFree(ctx->solver_work);
     ctx->solver_work = nullptr;
@@ -473,7 +536,7 @@ extern "C" int sdpsr_eig(sdpsr_ctx* ctx, const double* r1, int64_t len, double* 
   cusolverStatus_t st = CUSOLVER_STATUS_SUCCESS;
   if (ctx->rank == 0) {          // multi-GPU: one rank factorises, all receive (identical Q everywhere)
     Timed tm(ctx, SDPSR_K_EIG, 0.0);
-    st = cusolverDnXsyevd(s->h, s->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, ctx->n, CUDA_R_64F, ctx->Q,
+    st = sapi().Xsyevd(s->h, s->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, ctx->n, CUDA_R_64F, ctx->Q,
                           ctx->ld, CUDA_R_64F, s->d_vals, CUDA_R_64F, ctx->solver_work, wdev, ctx->solver_hwork, whost,
                           ctx->solver_info);
   }
@@ -1112,10 +1175,11 @@ extern "C" int sdpsr_eig_complex(sdpsr_ctx* ctx, const double* r1, int64_t len, 
   if (!ctx->solver) {
     Solver* s = new Solver();
     ctx->solver = s;
-    SDPSR_REQUIRE(cusolverDnCreate(&s->h) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER, "cusolverDnCreate failed");
-    SDPSR_REQUIRE(cusolverDnSetStream(s->h, ctx->stream) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
+    SDPSR_REQUIRE(sapi().ok, SDPSR_E_CUSOLVER, "libcusolver.so.11 could not be loaded");
+    SDPSR_REQUIRE(sapi().Create(&s->h) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER, "cusolverDnCreate failed");
+    SDPSR_REQUIRE(sapi().SetStream(s->h, ctx->stream) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
                   "cusolverDnSetStream failed");
-    SDPSR_REQUIRE(cusolverDnCreateParams(&s->params) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
+    SDPSR_REQUIRE(sapi().CreateParams(&s->params) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
                   "cusolverDnCreateParams failed");
     SDPSR_CUDA(cudaMalloc(&s->d_vals, (size_t)ctx->n * sizeof(double)));
     SDPSR_CUDA(cudaMalloc(&ctx->solver_info, sizeof(int)));
@@ -1144,7 +1208,7 @@ extern "C" int sdpsr_eig_complex(sdpsr_ctx* ctx, const double* r1, int64_t len, 
     interleave_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->X, ctx->Xi, Az, ctx->elems);
     count_launch(ctx);
     size_t wd = 0, wh = 0;
-    if (cusolverDnXgeev_bufferSize(s->h, s->params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_VECTOR, n, CUDA_C_64F,
+    if (sapi().Xgeev_bufferSize(s->h, s->params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_VECTOR, n, CUDA_C_64F,
                                    Az, ld, CUDA_C_64F, Wz, CUDA_C_64F, nullptr, ld, CUDA_C_64F, VR, ld, CUDA_C_64F, &wd,
                                    &wh) != CUSOLVER_STATUS_SUCCESS) {
       status = ctx->fail(SDPSR_E_CUSOLVER, "cusolverDnXgeev_bufferSize failed");
@@ -1158,7 +1222,7 @@ extern "C" int sdpsr_eig_complex(sdpsr_ctx* ctx, const double* r1, int64_t len, 
     cusolverStatus_t st;
     {
       Timed tm(ctx, SDPSR_K_EIG, 0.0);
-      st = cusolverDnXgeev(s->h, s->params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_VECTOR, n, CUDA_C_64F, Az, ld,
+      st = sapi().Xgeev(s->h, s->params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_VECTOR, n, CUDA_C_64F, Az, ld,
                            CUDA_C_64F, Wz, CUDA_C_64F, nullptr, ld, CUDA_C_64F, VR, ld, CUDA_C_64F, dwork, wd, hwork, wh,
                            ctx->solver_info);
     }

@@ -250,6 +250,8 @@ extern "C" int sdpsr_partition_reset(sdpsr_ctx* ctx) {
   ctx->dim = 0;
   ctx->x_is_fill = false;
   ctx->x_valid = false;
+  ctx->key_decodable = false;
+  ctx->sym_state = 1;          // the empty partition is transpose-invariant
   return finish(ctx);
 }
 
@@ -453,12 +455,20 @@ extern "C" int sdpsr_fill(sdpsr_ctx* ctx, const double* values, int64_t len) {
 }
 
 // X2 = X * X.  method -1: automatic (INT8 tensor path for symmetric X where it is the faster one,
-// else DMMA), 0: DMMA, 1: INT8 (error if X is not symmetric).
-static int square_x(sdpsr_ctx* ctx, int method, int slices, int bits = 0) {
+// else DMMA), 0: DMMA, 1: INT8 (error if X is not symmetric).  While X is still the un-materialised
+// fill(S, lut) its symmetry is the partition's (cached, 4 B/entry when it has to be checked) and the INT8
+// path gathers its digit slices straight from the labels; X is only written out for the DMMA path.
+static int square_x(sdpsr_ctx* ctx, int method, int slices, int bits, int* was_symmetric) {
   // X symmetric (bit for bit) => X*X symmetric: compute the lower tiles only and mirror them,
   // which also makes X2 exactly symmetric (SYRK-style, half the flops)
   int sym = 0;
-  if (!(ctx->flags & SDPSR_F_NO_SYRK) || method == 1) SDPSR_TRY(sdpsr_matrix_symmetric(ctx, ctx->X, &sym));
+  if (!(ctx->flags & SDPSR_F_NO_SYRK) || method == 1) {
+    if (ctx->x_is_fill)
+      SDPSR_TRY(sdpsr_symmetric_check(ctx, &sym));
+    else
+      SDPSR_TRY(sdpsr_matrix_symmetric(ctx, ctx->X, &sym));
+  }
+  if (was_symmetric) *was_symmetric = sym;
   bool use_i8 = false;
   if (method == 1) {
     SDPSR_REQUIRE(sym != 0, SDPSR_E_INVALID, "the INT8 square needs a bit-for-bit symmetric X");
@@ -468,10 +478,12 @@ static int square_x(sdpsr_ctx* ctx, int method, int slices, int bits = 0) {
   }
   if (use_i8) {
     int done = 0;
-    SDPSR_TRY(sdpsr_square_i8(ctx, ctx->X, ctx->X2, slices, bits, /*shard=*/true, /*force_range=*/method == 1, &done));
+    SDPSR_TRY(sdpsr_square_i8(ctx, ctx->x_is_fill ? nullptr : ctx->X, ctx->X2, slices, bits, /*shard=*/true,
+                              /*force_range=*/method == 1, &done));
     if (done) return SDPSR_OK;
     SDPSR_REQUIRE(method != 1, SDPSR_E_UNSUPPORTED, "the INT8 square does not handle Inf/NaN or extreme exponents");
   }
+  if (ctx->x_is_fill) SDPSR_TRY(sdpsr_materialize_fill(ctx, ctx->X));     // S is unchanged: X stays a valid fill
   SDPSR_TRY(sdpsr_gemm_f64(ctx, ctx->X, ctx->ld, ctx->X, ctx->ld, ctx->X2, ctx->ld, ctx->ld, ctx->n, ctx->n,
                            sym != 0 && !(ctx->flags & SDPSR_F_NO_SYRK), /*shard=*/true));
   return SDPSR_OK;
@@ -480,12 +492,11 @@ static int square_x(sdpsr_ctx* ctx, int method, int slices, int bits = 0) {
 extern "C" int sdpsr_square_round_refine(sdpsr_ctx* ctx, double atol, int64_t* dim) {
   CTX_ENTER();
   SDPSR_REQUIRE(ctx->x_valid, SDPSR_E_STATE, "X is not defined yet (call sdpsr_fill first)");
-  if (ctx->x_is_fill) {
-    SDPSR_TRY(sdpsr_materialize_fill(ctx, ctx->X));
-    // S is unchanged, so X stays a valid fill; keep the flag for a later projection
-  }
-  SDPSR_TRY(square_x(ctx, /*method=*/-1, ctx->i8_slices));
-  SDPSR_TRY(sdpsr_generic_refine_values(ctx, ctx->X2, atol, true, nullptr, dim));
+  int sym = 0;
+  SDPSR_TRY(square_x(ctx, /*method=*/-1, ctx->i8_slices, 0, &sym));
+  // X symmetric => X2 symmetric bit for bit (mirrored lower tiles): the refined partition stays symmetric
+  SDPSR_TRY(sdpsr_generic_refine_values(ctx, ctx->X2, atol, true, nullptr, dim,
+                                        /*keeps_symmetry=*/sym != 0 && !(ctx->flags & SDPSR_F_NO_SYRK)));
   return finish(ctx);
 }
 
@@ -494,8 +505,8 @@ extern "C" int sdpsr_square(sdpsr_ctx* ctx, int method, int slices) {
   SDPSR_REQUIRE(ctx->x_valid, SDPSR_E_STATE, "X is not defined yet (call sdpsr_fill or sdpsr_set_matrix first)");
   SDPSR_REQUIRE(method >= 0 && method <= 3, SDPSR_E_INVALID,
                 "method must be 0 (DMMA), 1 (INT8), 2 (INT8, 7-bit digits) or 3 (INT8, 8-bit digits)");
-  if (ctx->x_is_fill) SDPSR_TRY(sdpsr_materialize_fill(ctx, ctx->X));
-  SDPSR_TRY(square_x(ctx, method ? 1 : 0, slices > 0 ? slices : ctx->i8_slices, method == 2 ? 7 : method == 3 ? 8 : 0));
+  SDPSR_TRY(square_x(ctx, method ? 1 : 0, slices > 0 ? slices : ctx->i8_slices, method == 2 ? 7 : method == 3 ? 8 : 0,
+                     nullptr));
   return finish(ctx);
 }
 

@@ -209,6 +209,81 @@ __global__ void __launch_bounds__(256) slice_kernel(const double* __restrict__ x
 }
 
 // --------------------------------------------------------------------------------------------
+// The same digit slices straight from the partition: X = fill(S, lut) is never materialised.
+//   dlut[id] = the S digit bytes of lut[id] packed into one 64-bit word (byte s = digit s)
+//   slice_labels_kernel: 4 B/entry in (provisional id), S B/entry out; the 8-byte table lookups hit L1/L2
+// Per-column maxima for the range guard come from the labels as well (colmax_labels_kernel).
+// --------------------------------------------------------------------------------------------
+template <int BITS>
+__global__ void dlut_kernel(const double* __restrict__ lut, uint32_t len, int S, double scale,
+                            unsigned long long* __restrict__ dlut) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  long long q = __double2ll_rn(lut[i] * scale);
+  unsigned long long w = 0ull;
+  constexpr long long HALF = 1ll << (BITS - 1);
+  for (int s = S - 1; s >= 1; --s) {
+    const long long d = ((q + HALF) & (2 * HALF - 1)) - HALF;
+    q = (q - d) >> BITS;
+    w |= ((unsigned long long)d & 0xFFull) << (8 * s);
+  }
+  w |= (unsigned long long)q & 0xFFull;
+  dlut[i] = w;
+}
+
+template <int S>
+__global__ void __launch_bounds__(256) slice_labels_kernel(const uint32_t* __restrict__ labels,
+                                                           const unsigned long long* __restrict__ dlut, size_t elems,
+                                                           int8_t* __restrict__ slices) {
+  const size_t chunk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // 16 consecutive entries
+  if (chunk * 16 >= elems) return;
+  const uint4* src = reinterpret_cast<const uint4*>(labels + chunk * 16);
+  uint32_t packed[S][4];
+#pragma unroll
+  for (int s = 0; s < S; ++s) packed[s][0] = packed[s][1] = packed[s][2] = packed[s][3] = 0u;
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const uint4 l = __ldcs(src + h);
+    const uint32_t lv[4] = {l.x, l.y, l.z, l.w};
+    unsigned long long w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) w[u] = __ldg(dlut + lv[u]);
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+      packed[s][h] = (uint32_t)((w[0] >> (8 * s)) & 0xFFull) | ((uint32_t)((w[1] >> (8 * s)) & 0xFFull) << 8) |
+                     ((uint32_t)((w[2] >> (8 * s)) & 0xFFull) << 16) | ((uint32_t)((w[3] >> (8 * s)) & 0xFFull) << 24);
+  }
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+    __stcs(reinterpret_cast<uint4*>(slices + (size_t)s * elems + chunk * 16),
+           make_uint4(packed[s][0], packed[s][1], packed[s][2], packed[s][3]));
+}
+
+// out[1] = the smallest non-zero column maximum of |lut[labels]| (one warp per column)
+__global__ void __launch_bounds__(256) colmax_labels_kernel(const uint32_t* __restrict__ labels,
+                                                            const double* __restrict__ lut, int n, int64_t ld,
+                                                            unsigned long long* out) {
+  const int lane = threadIdx.x & 31;
+  for (int col = blockIdx.x * 8 + (threadIdx.x >> 5); col < n; col += gridDim.x * 8) {
+    const uint4* src = reinterpret_cast<const uint4*>(labels + ld * (int64_t)col);
+    unsigned long long m = 0;
+    for (int i = lane; i < (int)(ld / 4); i += 32) {
+      const uint4 l = src[i];
+      const uint32_t lv[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        m = max(m, (unsigned long long)__double_as_longlong(__ldg(lut + lv[u])) & 0x7FFFFFFFFFFFFFFFull);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if (lane == 0 && m) {
+      atomicMax(out, m);
+      atomicMin(out + 1, m);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
 // the square
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS, 1)
@@ -685,6 +760,13 @@ void build_tiles_2cta(int n, int nranks, int rank, std::vector<int2>& out) {
 }
 
 template <int S>
+void launch_slices_labels(const uint32_t* labels, const unsigned long long* dlut, size_t elems, int8_t* slices,
+                          cudaStream_t st) {
+  const size_t chunks = elems / 16;
+  slice_labels_kernel<S><<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(labels, dlut, elems, slices);
+}
+
+template <int S>
 void launch_slices(const double* X, size_t elems, int8_t* slices, double scale, int bits, cudaStream_t st) {
   const size_t chunks = elems / 16;
   if (bits == 8)
@@ -699,6 +781,8 @@ void launch_slices(const double* X, size_t elems, int8_t* slices, double scale, 
 // X2 = X * X for bit-for-bit symmetric X (checked by the caller).  *done = 0 when the values are out of
 // the range the slicing handles (Inf/NaN, extreme exponents, or -- unless force_range -- rows whose
 // largest entry is more than 2^8 below the global maximum): the caller then uses the DMMA path.
+// X == nullptr: X is fill(S, ctx->lut) and is not materialised; the digit slices are gathered straight from
+// the label matrix (4 B/entry in) and the scale comes from the coefficient table.
 int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits, bool shard, bool force_range,
                     int* done) {
   *done = 0;
@@ -724,28 +808,45 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits,
     attr_set = true;
   }
   // ---- scale: sigma = 2^e > max|X| ----
+  const bool from_labels = X == nullptr;
   unsigned long long* d_max = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 40);
   unsigned long long* h_max = reinterpret_cast<unsigned long long*>(ctx->h_pinned) + 40;
-  h_max[0] = 0ull;
-  h_max[1] = ~0ull;
-  SDPSR_CUDA(cudaMemcpyAsync(d_max, h_max, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
-  {
-    Timed tm(ctx, SDPSR_K_MISC, (double)elems * 8.0);
-    colmax_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(X, (int)n, ld, d_max);
-    count_launch(ctx);
-  }
-  SDPSR_CUDA(cudaGetLastError());
-  SDPSR_CUDA(cudaMemcpyAsync(h_max, d_max, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
   double vmax, cmin;
-  std::memcpy(&vmax, h_max, sizeof(double));
+  bool need_colmax = true;
+  if (from_labels) {
+    // max over the classes; when even the smallest non-zero coefficient is within 2^-8 of it every
+    // non-zero column is too, and no pass over the matrix is needed for the guard
+    double vmin_nz;
+    SDPSR_TRY(sdpsr_lut_stats(ctx, &vmax, &vmin_nz));
+    cmin = vmin_nz;
+    need_colmax = !force_range && vmax < INFINITY && vmax > 0.0 && vmin_nz < std::ldexp(vmax, -8);
+  }
+  if (need_colmax) {
+    h_max[0] = 0ull;
+    h_max[1] = ~0ull;
+    SDPSR_CUDA(cudaMemcpyAsync(d_max, h_max, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+    {
+      Timed tm(ctx, SDPSR_K_MISC, (double)elems * (from_labels ? 4.0 : 8.0));
+      if (from_labels)
+        colmax_labels_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->labels, ctx->lut, (int)n, ld, d_max);
+      else
+        colmax_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(X, (int)n, ld, d_max);
+      count_launch(ctx);
+    }
+    SDPSR_CUDA(cudaGetLastError());
+    SDPSR_CUDA(cudaMemcpyAsync(h_max, d_max, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+    double cm;
+    std::memcpy(&cm, h_max, sizeof(double));
+    if (!from_labels) vmax = cm;          // (from labels: every class is non-empty, the class maximum IS max|X|)
+    std::memcpy(&cmin, h_max + 1, sizeof(double));
+  }
   if (!(vmax < INFINITY)) return SDPSR_OK;                 // Inf / NaN: not handled here
   if (vmax == 0.0) {     // (X is replicated bit for bit, so every rank takes the same branch)
     SDPSR_CUDA(cudaMemsetAsync(C, 0, elems * sizeof(double), ctx->stream));
     *done = 1;
     return SDPSR_OK;
   }
-  std::memcpy(&cmin, h_max + 1, sizeof(double));
   // one scale for the whole matrix: every non-zero row must reach within 2^-8 of the maximum, or its
   // entries would keep fewer than 46 of their 53 bits; the closure loop's X always does
   if (!force_range && cmin < std::ldexp(vmax, -8)) return SDPSR_OK;
@@ -765,7 +866,29 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits,
       return SDPSR_OK;                         // no room for the digit matrices: the DMMA path needs none
     }
   }
-  {
+  if (from_labels) {
+    KeyTable& t = ctx->tab[ctx->cur];
+    unsigned long long* dlut = nullptr;
+    const uint32_t len = t.cap + 1;
+    SDPSR_TRY(sdpsr_scratch_t(ctx, 29, (size_t)len, &dlut));
+    const double scale = std::ldexp(1.0, bits * (S - 1) + 6 - e);
+    Timed tm(ctx, SDPSR_K_MISC, (double)elems * (4.0 + S));
+    // (unoccupied ids hold stale lut values; they are never referenced by a label)
+    if (bits == 8)
+      dlut_kernel<8><<<(len + 255) / 256, 256, 0, ctx->stream>>>(ctx->lut, len, S, scale, dlut);
+    else
+      dlut_kernel<7><<<(len + 255) / 256, 256, 0, ctx->stream>>>(ctx->lut, len, S, scale, dlut);
+    switch (S) {
+      case 2: launch_slices_labels<2>(ctx->labels, dlut, elems, slices, ctx->stream); break;
+      case 3: launch_slices_labels<3>(ctx->labels, dlut, elems, slices, ctx->stream); break;
+      case 4: launch_slices_labels<4>(ctx->labels, dlut, elems, slices, ctx->stream); break;
+      case 5: launch_slices_labels<5>(ctx->labels, dlut, elems, slices, ctx->stream); break;
+      case 6: launch_slices_labels<6>(ctx->labels, dlut, elems, slices, ctx->stream); break;
+      case 7: launch_slices_labels<7>(ctx->labels, dlut, elems, slices, ctx->stream); break;
+      default: launch_slices_labels<8>(ctx->labels, dlut, elems, slices, ctx->stream); break;
+    }
+    count_launch(ctx, 2);
+  } else {
     Timed tm(ctx, SDPSR_K_MISC, (double)elems * (8.0 + S));
     const double scale = std::ldexp(1.0, bits * (S - 1) + 6 - e);
     switch (S) {

@@ -280,17 +280,34 @@ void sdpsr_constraints_free(sdpsr_ctx* ctx) {
   ctx->cons = ConstraintSet();      // device arrays live in scratch slots 8-14 (freed with the context)
 }
 
-int sdpsr_symmetric_check(sdpsr_ctx* ctx, int* is_sym) {
+// 1 iff the N x N u32 array (padded layout) equals its transpose
+static int u32_symmetric(sdpsr_ctx* ctx, const uint32_t* arr, int* is_sym) {
   uint32_t* bad = ctx->d_scalars + 8;
   SDPSR_CUDA(cudaMemsetAsync(bad, 0, sizeof(uint32_t), ctx->stream));
   const unsigned nb = (unsigned)((ctx->n + 31) / 32);
-  symcheck_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(ctx->labels, ctx->n, ctx->ld, bad);
-  count_launch(ctx);
+  {
+    Timed tm(ctx, SDPSR_K_MISC, (double)ctx->elems * 4.0);
+    symcheck_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(arr, ctx->n, ctx->ld, bad);
+    count_launch(ctx);
+  }
   SDPSR_CUDA(cudaGetLastError());
   uint32_t* hb = reinterpret_cast<uint32_t*>(ctx->h_pinned) + 32;
   SDPSR_CUDA(cudaMemcpyAsync(hb, bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
   *is_sym = (*hb == 0u) ? 1 : 0;
+  return SDPSR_OK;
+}
+
+// Is the partition transpose-invariant?  Provisional ids are a relabelling of the classes, so the test runs
+// on them directly.  The answer is cached: a refine by values that are symmetric by construction keeps it
+// (sdpsr_refine_pass, RefineSpec::keeps_symmetry); anything else resets it to "unknown".
+int sdpsr_symmetric_check(sdpsr_ctx* ctx, int* is_sym) {
+  if (ctx->sym_state < 0) {
+    int s = 0;
+    SDPSR_TRY(u32_symmetric(ctx, ctx->labels, &s));
+    ctx->sym_state = s;
+  }
+  *is_sym = ctx->sym_state;
   return SDPSR_OK;
 }
 
@@ -528,6 +545,9 @@ int sdpsr_constraints_finalize(sdpsr_ctx* ctx) {
   SDPSR_REQUIRE(c.gram_rank >= 1, SDPSR_E_SINGULAR, "the constraint matrix A is zero");
   SDPSR_TRY(sdpsr_scratch_t(ctx, 14, (size_t)npat + 1, &c.d_tpat));
   SDPSR_CUDA(cudaMemsetAsync(c.d_tpat, 0, ((size_t)npat + 1) * sizeof(double), ctx->stream));
+  // A' c is a symmetric matrix for every c iff the pattern ids are transpose-invariant: then the projection
+  // of a symmetric element is symmetric and the refined partition stays transpose-invariant
+  SDPSR_TRY(u32_symmetric(ctx, c.d_pid, &c.pid_sym));
   c.ready = true;
   return SDPSR_OK;
 }
@@ -655,17 +675,24 @@ extern "C" int sdpsr_project_round_refine(sdpsr_ctx* ctx, double atol, int64_t* 
   sp.lut = ctx->lut;
   sp.tpat = c.d_tpat;
   sp.pid = c.d_pid;
-  sp.vals_out = ctx->X;          // the projected, rounded element stays as X (:163)
   sp.atol = atol;
   sp.do_round = true;
+  sp.keeps_symmetry = c.pid_sym == 1;
   double sc;
   long long isc;
   int qb;
   SDPSR_TRY(sdpsr_round_params(ctx, atol, &sc, &isc, &qb));
   if (12 + qb + bits_for((uint64_t)ctx->tab[ctx->cur].cap) <= 64) {
+    // The projected, rounded element stays as X (:163) -- but not as N^2 doubles: the keys of the pass carry
+    // the rounded values, so X = fill(S_new, lut) with lut decoded from the new table (12 B/entry pass).
     sp.mode = KM_ROUND;
     SDPSR_TRY(sdpsr_refine_pass(ctx, sp, dim));
+    SDPSR_TRY(sdpsr_decode_lut(ctx, atol));
+    ctx->x_valid = true;
+    ctx->x_is_fill = true;
+    return finish(ctx);
   } else {
+    sp.vals_out = ctx->X;
     // wide rounding grid: materialise X first, then the generic two-step refine
     SDPSR_TRY(sdpsr_ensure_tmp_labels(ctx));
     KeyTable& scratch = ctx->tab_scratch;   // reused across calls, freed with the context
@@ -678,6 +705,7 @@ extern "C" int sdpsr_project_round_refine(sdpsr_ctx* ctx, double atol, int64_t* 
       pr.mode = KM_PAIR;
       pr.lab2 = ctx->labels_tmp;
       pr.do_round = false;
+      pr.keeps_symmetry = sp.keeps_symmetry;
       st = sdpsr_refine_pass(ctx, pr, dim);
     }
     SDPSR_TRY(st);
@@ -741,6 +769,7 @@ extern "C" int sdpsr_init_partition(sdpsr_ctx* ctx, const double* C, const doubl
     sp.vals = ctx->X;
     sp.do_round = false;
     sp.ignore_labels = true;
+    sp.keeps_symmetry = true;                                             // CL was symmetrised
     SDPSR_TRY(sdpsr_refine_pass(ctx, sp, nullptr));
   }
   // X0 = round(proj(symmetrize(x0))), x0 = A' (A A')^-1 b                   (:137-142)
@@ -762,7 +791,8 @@ extern "C" int sdpsr_init_partition(sdpsr_ctx* ctx, const double* C, const doubl
     count_launch(ctx);
   }
   SDPSR_CUDA(cudaGetLastError());
-  SDPSR_TRY(sdpsr_generic_refine_values(ctx, ctx->X2, atol, false, nullptr, dim));   // refine!(S, Part(X0)) (:146)
+  SDPSR_TRY(sdpsr_generic_refine_values(ctx, ctx->X2, atol, false, nullptr, dim,
+                                        /*keeps_symmetry=*/c.pid_sym == 1));          // refine!(S, Part(X0)) (:146)
   ctx->x_valid = false;
   ctx->x_is_fill = false;
   return finish(ctx);

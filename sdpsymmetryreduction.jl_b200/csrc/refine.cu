@@ -592,6 +592,60 @@ __global__ void build_lut_kernel(const uint32_t* __restrict__ occ, const uint32_
   }
 }
 
+// lut[slot + 1] = the rounded value encoded in the key of `slot` (the value every entry of that class holds
+// after `_clamp_round!`): after a round+refine pass the rounded matrix IS fill(S_new, lut), so it never has
+// to be written to HBM (src/partitions.jl:160-164: "X stays the projected, rounded element").
+//   fast layout   hi = sign | e11 | q>>4,  lo = (q & 15) << 28 | old id          (refine_fast_kernel)
+//   generic       key = (sign | e11 | q) << lbits | old id                        (refine_kernel<KM_ROUND>)
+__global__ void decode_lut_kernel(const uint32_t* __restrict__ occ, const uint64_t* __restrict__ keys, uint32_t count,
+                                  int fast, int lbits, int qbits, double scale, double* __restrict__ lut) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) lut[0] = 0.0;
+  if (i >= count) return;
+  const uint32_t s = occ[i];
+  const uint64_t k = keys[s];
+  uint64_t aq, e11, sign;
+  if (fast) {
+    const uint32_t hi = (uint32_t)(k >> 32), lo = (uint32_t)k;
+    aq = ((uint64_t)(hi & 0xFFFFFu) << 4) | (lo >> 28);
+    e11 = (hi >> 20) & 0x7ffu;
+    sign = hi >> 31;
+  } else {
+    const uint64_t code = k >> lbits;
+    aq = code & ((1ull << qbits) - 1ull);
+    e11 = (code >> qbits) & 0x7ffull;
+    sign = (code >> (11 + qbits)) & 1ull;
+  }
+  double v = 0.0;
+  if (aq != 0ull || e11 != 0ull) {
+    const double y = __ddiv_rn((double)(long long)aq, scale);
+    const int n = (int)e11 - 1022;
+    const int n1 = n / 2, n2 = n - n1;
+    v = y * __longlong_as_double((long long)(1023 + n1) << 52) * __longlong_as_double((long long)(1023 + n2) << 52);
+    if (sign) v = -v;
+  }
+  lut[s + 1] = v;
+}
+
+// out[0] = max |lut| over the occupied ids, out[1] = min non-zero |lut| (bit patterns of non-negative doubles)
+__global__ void lut_stats_kernel(const uint32_t* __restrict__ occ, const double* __restrict__ lut, uint32_t count,
+                                 unsigned long long* __restrict__ out) {
+  unsigned long long mx = 0ull, mn = ~0ull;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const unsigned long long a = (unsigned long long)__double_as_longlong(lut[occ[i] + 1]) & 0x7FFFFFFFFFFFFFFFull;
+    mx = max(mx, a);
+    if (a) mn = min(mn, a);
+  }
+  for (int o = 16; o; o >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (mx) atomicMax(out, mx);
+    atomicMin(out + 1, mn);
+  }
+}
+
 __global__ void __launch_bounds__(256) fill_kernel(const uint32_t* __restrict__ labels,
                                                    const double* __restrict__ lut, double* __restrict__ X,
                                                    uint64_t total) {
@@ -750,6 +804,7 @@ int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
   const size_t cap_max = std::max<size_t>(64, next_pow2(2 * (uint64_t)ctx->elems));
   const uint64_t ntiles = (ctx->elems + TILE - 1) / TILE;
   const int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count);
+  bool last_fast = false;
 
   for (;;) {
     SDPSR_TRY(sdpsr_table_alloc(ctx, tnew, cap));
@@ -766,6 +821,7 @@ int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
       const bool wb = a.vals_out != nullptr;
       const bool fast = spec.mode == KM_ROUND && a.iscale == 10000000ll && a.lbits <= 28 &&
                         !(ctx->flags & SDPSR_F_NO_SMEM_CACHE);
+      last_fast = fast;
       if (fast) {
         if (a.fillproj) {
           if (wb) refine_fast_kernel<true, true><<<grid, RT, smem, ctx->stream>>>(a);
@@ -805,6 +861,11 @@ int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
     ctx->cur ^= 1;
     ctx->dim = tnew.count;
     ctx->x_is_fill = false;
+    // value-coded keys: the class values can be decoded from the table (sdpsr_decode_lut)
+    ctx->key_decodable = spec.mode == KM_ROUND;
+    ctx->key_fast = last_fast;
+    ctx->key_lbits = a.lbits;
+    ctx->sym_state = spec.keeps_symmetry && ctx->sym_state == 1 ? 1 : -1;
   }
   if (dim) *dim = tnew.count;
   return SDPSR_OK;
@@ -822,7 +883,7 @@ int sdpsr_ensure_tmp_labels(sdpsr_ctx* ctx) {
 // Fused single pass when the (id, value code) pair fits 64 bits, otherwise the
 // reference's own two steps: ids of Part(M) first, then the pair pass.
 int sdpsr_generic_refine_values(sdpsr_ctx* ctx, const double* dvals, double atol, bool do_round,
-                                double* vals_out, int64_t* dim) {
+                                double* vals_out, int64_t* dim, bool keeps_symmetry) {
   bool fused = do_round;
   if (fused) {
     double sc;
@@ -836,6 +897,7 @@ int sdpsr_generic_refine_values(sdpsr_ctx* ctx, const double* dvals, double atol
   sp.vals_out = vals_out;
   sp.atol = atol;
   sp.do_round = do_round;
+  sp.keeps_symmetry = keeps_symmetry;
   if (fused) {
     sp.mode = KM_ROUND;
     return sdpsr_refine_pass(ctx, sp, dim);
@@ -858,6 +920,7 @@ int sdpsr_generic_refine_values(sdpsr_ctx* ctx, const double* dvals, double atol
     pr.mode = KM_PAIR;
     pr.lab2 = ctx->labels_tmp;
     pr.do_round = false;
+    pr.keeps_symmetry = keeps_symmetry;
     st = sdpsr_refine_pass(ctx, pr, dim);
   }
   return st;
@@ -876,20 +939,66 @@ int sdpsr_upload_values(sdpsr_ctx* ctx, const double* values, int64_t len) {
   return SDPSR_OK;
 }
 
+static int ensure_lut(sdpsr_ctx* ctx, size_t need);
+
 int sdpsr_build_lut(sdpsr_ctx* ctx, const double* d_values, int64_t len) {
   KeyTable& t = ctx->tab[ctx->cur];
   SDPSR_REQUIRE(len == (int64_t)t.count, SDPSR_E_INVALID, "length(values) != dim(P) (src/partitions.jl:69)");
-  const size_t need = (size_t)t.cap + 1;
+  SDPSR_TRY(ensure_lut(ctx, (size_t)t.cap + 1));
+  const int blocks = (int)std::max<uint32_t>(1, (t.count + 255) / 256);
+  build_lut_kernel<<<blocks, 256, 0, ctx->stream>>>(t.occ, t.rank, d_values, ctx->lut, t.count);
+  count_launch(ctx);
+  SDPSR_CUDA(cudaGetLastError());
+  return SDPSR_OK;
+}
+
+static int ensure_lut(sdpsr_ctx* ctx, size_t need) {
   if (ctx->lut_alloc < need) {
     cudaFree(ctx->lut);
     ctx->lut = nullptr;
     SDPSR_CUDA(cudaMalloc(&ctx->lut, need * sizeof(double)));
     ctx->lut_alloc = need;
   }
+  return SDPSR_OK;
+}
+
+// After a fused round+refine pass (KM_ROUND keys): ctx->lut[provisional id] = the rounded value of the class.
+int sdpsr_decode_lut(sdpsr_ctx* ctx, double atol) {
+  KeyTable& t = ctx->tab[ctx->cur];
+  SDPSR_REQUIRE(ctx->key_decodable, SDPSR_E_STATE, "the last refine pass did not use value-coded keys");
+  SDPSR_TRY(ensure_lut(ctx, (size_t)t.cap + 1));
+  double scale;
+  long long iscale;
+  int qbits;
+  SDPSR_TRY(sdpsr_round_params(ctx, atol, &scale, &iscale, &qbits));
   const int blocks = (int)std::max<uint32_t>(1, (t.count + 255) / 256);
-  build_lut_kernel<<<blocks, 256, 0, ctx->stream>>>(t.occ, t.rank, d_values, ctx->lut, t.count);
+  decode_lut_kernel<<<blocks, 256, 0, ctx->stream>>>(t.occ, t.keys, t.count, ctx->key_fast ? 1 : 0, ctx->key_lbits, qbits,
+                                                      scale, ctx->lut);
   count_launch(ctx);
   SDPSR_CUDA(cudaGetLastError());
+  return SDPSR_OK;
+}
+
+// max |lut| and the smallest non-zero |lut| over the classes of S (host doubles)
+int sdpsr_lut_stats(sdpsr_ctx* ctx, double* vmax, double* vmin_nz) {
+  KeyTable& t = ctx->tab[ctx->cur];
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 44);
+  unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_pinned) + 44;
+  h[0] = 0ull;
+  h[1] = ~0ull;
+  SDPSR_CUDA(cudaMemcpyAsync(d, h, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+  if (t.count) {
+    const int blocks = (int)std::min<uint32_t>(64, (t.count + 255) / 256);
+    lut_stats_kernel<<<blocks, 256, 0, ctx->stream>>>(t.occ, ctx->lut, t.count, d);
+    count_launch(ctx);
+  }
+  SDPSR_CUDA(cudaMemcpyAsync(h, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::memcpy(vmax, h, sizeof(double));
+  if (h[1] == ~0ull)
+    *vmin_nz = 0.0;
+  else
+    std::memcpy(vmin_nz, h + 1, sizeof(double));
   return SDPSR_OK;
 }
 

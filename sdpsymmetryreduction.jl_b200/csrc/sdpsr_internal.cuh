@@ -72,6 +72,8 @@ struct ConstraintSet {
   std::vector<int> gram_perm;           // pivot order: gram_perm[i] = constraint row eliminated i-th
   int gram_rank = 0;                    // numerical rank of A; rows gram_perm[rank..] are dependent (dropped)
   double* d_tpat = nullptr;      // [npat+1]
+  int pid_sym = -1;              // pattern ids transpose-invariant? (checked once; decides whether the
+                                 // projection keeps a symmetric partition symmetric)
   // host CSR copy (needed to read pattern columns)
   std::vector<int64_t> h_rowptr;
   std::vector<int64_t> h_col;    // unpadded linear index
@@ -132,6 +134,14 @@ struct sdpsr_ctx {
   size_t values_alloc = 0;
   bool x_is_fill = false;       // X == fill(S, lut) and S unchanged since
   bool x_valid = false;
+  // layout of the keys of tab[cur] (set by the last refine pass): value-coded keys can be decoded back
+  // into the rounded class values (sdpsr_decode_lut)
+  bool key_decodable = false;
+  bool key_fast = false;
+  int key_lbits = 0;
+  // Is the label matrix transpose-invariant?  1 yes, 0 no, -1 unknown (checked lazily, 4 B/entry).  A refine
+  // by a matrix that is symmetric by construction keeps a symmetric partition symmetric.
+  int sym_state = -1;
 
   // ranking scratch
   uint32_t* rk_mi = nullptr;    // dense minidx list
@@ -233,17 +243,20 @@ struct RefineSpec {
   bool raw_bits = false;            // KM_RAW: key = the 64 bits of vals[idx] verbatim (signatures, not floats)
   double atol = 0;
   bool ignore_labels = false;       // treat the current labels as all-zero (fresh partition)
+  bool keeps_symmetry = false;      // the refining values are symmetric by construction
   uint32_t* out_override = nullptr; // write provisional ids here instead of labels_alt (no swap)
   KeyTable* table_override = nullptr;
 };
 int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim);
 int sdpsr_generic_refine_values(sdpsr_ctx* ctx, const double* dvals, double atol, bool do_round,
-                                double* vals_out, int64_t* dim);
+                                double* vals_out, int64_t* dim, bool keeps_symmetry = false);
 int sdpsr_table_alloc(sdpsr_ctx* ctx, KeyTable& t, size_t cap);
 void sdpsr_table_free(KeyTable& t);
 int sdpsr_rank_table(sdpsr_ctx* ctx, KeyTable& t);
 int sdpsr_build_lut(sdpsr_ctx* ctx, const double* d_values, int64_t len);
 int sdpsr_materialize_fill(sdpsr_ctx* ctx, double* dst);
+int sdpsr_decode_lut(sdpsr_ctx* ctx, double atol);
+int sdpsr_lut_stats(sdpsr_ctx* ctx, double* vmax, double* vmin_nz);
 int sdpsr_canonical_labels(sdpsr_ctx* ctx, uint32_t* dst_unpadded);
 int sdpsr_round_params(sdpsr_ctx* ctx, double atol, double* scale, long long* iscale, int* qbits);
 int sdpsr_ensure_tmp_labels(sdpsr_ctx* ctx);

@@ -34,6 +34,7 @@ def _setup(name):
     truth_dev, _ = canonical_truth_on_device(torch, truth, N)
     del truth
     prob.meta = None
+    torch.cuda.empty_cache()          # the canonicalisation's temporaries go back to the driver, not to torch's cache
     return torch, prob, truth_dev, eigmat, N
 
 
