@@ -67,6 +67,9 @@ typedef enum sdpsr_status {
 #define SDPSR_F_NO_I8 64u            /* never square on the INT8 tensor path (always DMMA)    */
 #define SDPSR_F_FORCE_I8 128u        /* square every symmetric X on the INT8 tensor path, whatever
                                         N (default: only where it is faster, N >= 2048)       */
+#define SDPSR_F_REPLICATED_REFINE 256u /* multi-rank: every rank runs the streaming passes on the full
+                                        matrix (round-1 behaviour) instead of sharding the partition by
+                                        column blocks with a key-table merge (A/B switch)      */
 
 /* which device-resident matrix sdpsr_get_matrix / sdpsr_set_matrix address */
 #define SDPSR_MAT_X 0   /* current element X (src/partitions.jl:121)      */

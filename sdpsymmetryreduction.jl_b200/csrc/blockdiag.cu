@@ -763,6 +763,7 @@ extern "C" int sdpsr_basis_image(sdpsr_ctx* ctx, double atol, double* out, int64
   for (int64_t s : ctx->blk_sizes) Sq += s * s;
   SDPSR_REQUIRE(out_len == d * Sq, SDPSR_E_INVALID, "out_len must be dim * sum(s_k^2)");
   if (d == 0) return SDPSR_OK;
+  SDPSR_TRY(sdpsr_shard_ensure_full_labels(ctx));
   KeyTable& t = ctx->tab[ctx->cur];
   if (d * Sq <= BS_MAX_BINS && Sq <= BS_MAX_PAIRS && !(ctx->flags & SDPSR_F_TINY_TABLE)) {
     // ---- few classes, small blocks: one pass over the labels (basis_small_kernel) -----------
@@ -1422,6 +1423,7 @@ extern "C" int sdpsr_irreducible_complex(sdpsr_ctx* ctx, const double* r3, int64
 // out: interleaved complex, packed [i][k] s_k x s_k column-major; out_len counts complex numbers
 extern "C" int sdpsr_basis_image_complex(sdpsr_ctx* ctx, double atol, double* out, int64_t out_len) {
   CTX_ENTER();
+  SDPSR_TRY(sdpsr_shard_ensure_full_labels(ctx));
   SDPSR_REQUIRE(ctx->Qhat && ctx->Qhat_i && out, SDPSR_E_STATE, "no complex Qhat (call sdpsr_irreducible_complex first)");
   const int64_t n = ctx->n, ld = ctx->ld, S = ctx->qhat_cols, d = ctx->dim;
   int64_t Sq = 0;

@@ -197,6 +197,27 @@ int sdpsr_comm_allgather(sdpsr_ctx* ctx, void* recv, size_t bytes) {
   return SDPSR_OK;
 }
 
+// In-place all-gather of unequal blocks: rank r owns bytes [offset[r], offset[r] + bytes[r]) of `base`
+int sdpsr_comm_allgatherv(sdpsr_ctx* ctx, void* base, const size_t* offset, const size_t* bytes) {
+  if (ctx->nranks <= 1) return SDPSR_OK;
+  unsigned char* b = reinterpret_cast<unsigned char*>(base);
+  if (ctx->local_group) {
+    LocalGroup* g = local_of(ctx);
+    g->posted[ctx->rank] = base;
+    SDPSR_TRY(local_barrier(ctx));
+    for (int r = 0; r < ctx->nranks; ++r)
+      if (r != ctx->rank && bytes[r])
+        SDPSR_TRY(local_copy_from(ctx, b + offset[r], r, reinterpret_cast<unsigned char*>(g->posted[r]) + offset[r], bytes[r]));
+    return local_barrier(ctx);
+  }
+  NCCL_TRY(api().GroupStart());
+  for (int r = 0; r < ctx->nranks; ++r)
+    if (bytes[r])
+      NCCL_TRY(api().Broadcast(b + offset[r], b + offset[r], bytes[r], NCCL_UINT8, r, (ncclComm_t)ctx->nccl, ctx->stream));
+  NCCL_TRY(api().GroupEnd());
+  return SDPSR_OK;
+}
+
 // Every rank passes a host flag; all receive the minimum (used to agree on a code path: a branch that
 // contains collectives must be taken by every rank or by none).  Blocking.
 int sdpsr_comm_agree_min(sdpsr_ctx* ctx, int* flag) {

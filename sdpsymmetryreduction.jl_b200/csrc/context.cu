@@ -207,6 +207,8 @@ extern "C" int sdpsr_destroy(sdpsr_ctx* ctx) {
   sdpsr_table_free(ctx->tab[0]);
   sdpsr_table_free(ctx->tab[1]);
   sdpsr_table_free(ctx->tab_scratch);
+  sdpsr_table_free(ctx->tab_merge);
+  cudaFree(ctx->clabels);
   cudaFree(ctx->labels);
   cudaFree(ctx->labels_alt);
   cudaFree(ctx->labels_tmp);
@@ -252,6 +254,8 @@ extern "C" int sdpsr_partition_reset(sdpsr_ctx* ctx) {
   ctx->x_valid = false;
   ctx->key_decodable = false;
   ctx->sym_state = 1;          // the empty partition is transpose-invariant
+  ctx->labels_full = true;     // all zero everywhere
+  ctx->clabels_valid = false;
   return finish(ctx);
 }
 
@@ -348,6 +352,7 @@ extern "C" int sdpsr_partition_dim(sdpsr_ctx* ctx, int64_t* dim) {
 extern "C" int sdpsr_partition_zero_count(sdpsr_ctx* ctx, int64_t* count) {
   CTX_ENTER();
   SDPSR_REQUIRE(count != nullptr, SDPSR_E_INVALID, "count is NULL");
+  SDPSR_TRY(sdpsr_shard_ensure_full_labels(ctx));
   unsigned long long* d = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 2);
   SDPSR_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream));
   dim3 grid((unsigned)std::min<int64_t>((ctx->n + 255) / 256, 64), (unsigned)ctx->n);

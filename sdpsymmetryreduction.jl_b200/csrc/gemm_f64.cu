@@ -235,9 +235,9 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // C[j, i] = C[i, j] for i > j, tile by tile through shared memory (coalesced both ways)
-__global__ void __launch_bounds__(256) mirror_lower_kernel(double* __restrict__ C, int64_t ldc, int n) {
+__global__ void __launch_bounds__(256) mirror_lower_kernel(double* __restrict__ C, int64_t ldc, int n, int bi0) {
   __shared__ double t[32][33];
-  const int bi = blockIdx.x, bj = blockIdx.y;
+  const int bi = blockIdx.x + bi0, bj = blockIdx.y;
   if (bi < bj) return;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int r = ty; r < 32; r += 8) {
@@ -366,11 +366,14 @@ int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B
   return SDPSR_OK;
 }
 
-// C[j, i] = C[i, j] for i > j
-int sdpsr_mirror_lower(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t n) {
-  Timed tm(ctx, SDPSR_K_MISC, (double)n * (double)n * 8.0);
-  dim3 g((unsigned)((n + 31) / 32), (unsigned)((n + 31) / 32));
-  mirror_lower_kernel<<<g, 256, 0, ctx->stream>>>(C, ldc, (int)n);
+// C[j, i] = C[i, j] for i > j, restricted to the destination columns [col_begin, col_end) (col_end < 0: all)
+int sdpsr_mirror_lower(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t n, int64_t col_begin, int64_t col_end) {
+  if (col_end < 0) col_end = n;
+  if (col_end <= col_begin) return SDPSR_OK;
+  const int bi0 = (int)(col_begin / 32), bi1 = (int)((col_end + 31) / 32);
+  Timed tm(ctx, SDPSR_K_MISC, (double)n * (double)(col_end - col_begin) * 8.0);
+  dim3 g((unsigned)(bi1 - bi0), (unsigned)((n + 31) / 32));
+  mirror_lower_kernel<<<g, 256, 0, ctx->stream>>>(C, ldc, (int)n, bi0);
   count_launch(ctx);
   SDPSR_CUDA(cudaGetLastError());
   return SDPSR_OK;

@@ -231,23 +231,51 @@ __global__ void dlut_kernel(const double* __restrict__ lut, uint32_t len, int S,
   dlut[i] = w;
 }
 
-template <int S>
-__global__ void __launch_bounds__(256) slice_labels_kernel(const uint32_t* __restrict__ labels,
+// LT = label storage type: uint32_t (the partition's own id matrix) or uint8_t / uint16_t (the compact canonical
+// labels a sharded run gathers from the other ranks, shard.cu: 1 or 2 B/entry in)
+template <int S, typename LT>
+__global__ void __launch_bounds__(256) slice_labels_kernel(const LT* __restrict__ labels,
                                                            const unsigned long long* __restrict__ dlut, size_t elems,
                                                            int8_t* __restrict__ slices) {
   const size_t chunk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // 16 consecutive entries
   if (chunk * 16 >= elems) return;
-  const uint4* src = reinterpret_cast<const uint4*>(labels + chunk * 16);
+  uint32_t lv[16];
+  if (sizeof(LT) == 4) {
+    const uint4* src = reinterpret_cast<const uint4*>(labels + chunk * 16);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const uint4 l = __ldcs(src + h);
+      lv[4 * h] = l.x; lv[4 * h + 1] = l.y; lv[4 * h + 2] = l.z; lv[4 * h + 3] = l.w;
+    }
+  } else if (sizeof(LT) == 2) {
+    const uint4* src = reinterpret_cast<const uint4*>(labels + chunk * 16);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint4 l = __ldcs(src + h);
+      const uint32_t w[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        lv[8 * h + 2 * u] = w[u] & 0xFFFFu;
+        lv[8 * h + 2 * u + 1] = w[u] >> 16;
+      }
+    }
+  } else {
+    const uint4 l = __ldcs(reinterpret_cast<const uint4*>(labels + chunk * 16));
+    const uint32_t w[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      lv[4 * u] = w[u] & 0xFFu;
+      lv[4 * u + 1] = (w[u] >> 8) & 0xFFu;
+      lv[4 * u + 2] = (w[u] >> 16) & 0xFFu;
+      lv[4 * u + 3] = w[u] >> 24;
+    }
+  }
   uint32_t packed[S][4];
 #pragma unroll
-  for (int s = 0; s < S; ++s) packed[s][0] = packed[s][1] = packed[s][2] = packed[s][3] = 0u;
-#pragma unroll
   for (int h = 0; h < 4; ++h) {
-    const uint4 l = __ldcs(src + h);
-    const uint32_t lv[4] = {l.x, l.y, l.z, l.w};
     unsigned long long w[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) w[u] = __ldg(dlut + lv[u]);
+    for (int u = 0; u < 4; ++u) w[u] = __ldg(dlut + lv[4 * h + u]);
 #pragma unroll
     for (int s = 0; s < S; ++s)
       packed[s][h] = (uint32_t)((w[0] >> (8 * s)) & 0xFFull) | ((uint32_t)((w[1] >> (8 * s)) & 0xFFull) << 8) |
@@ -759,11 +787,18 @@ void build_tiles_2cta(int n, int nranks, int rank, std::vector<int2>& out) {
   }
 }
 
+// width: bytes per label (4: u32 ids, 1 / 2: compact canonical labels)
 template <int S>
-void launch_slices_labels(const uint32_t* labels, const unsigned long long* dlut, size_t elems, int8_t* slices,
+void launch_slices_labels(const void* labels, int width, const unsigned long long* dlut, size_t elems, int8_t* slices,
                           cudaStream_t st) {
   const size_t chunks = elems / 16;
-  slice_labels_kernel<S><<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(labels, dlut, elems, slices);
+  const unsigned grid = (unsigned)((chunks + 255) / 256);
+  if (width == 1)
+    slice_labels_kernel<S, uint8_t><<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(labels), dlut, elems, slices);
+  else if (width == 2)
+    slice_labels_kernel<S, uint16_t><<<grid, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(labels), dlut, elems, slices);
+  else
+    slice_labels_kernel<S, uint32_t><<<grid, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(labels), dlut, elems, slices);
 }
 
 template <int S>
@@ -821,6 +856,22 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits,
     cmin = vmin_nz;
     need_colmax = !force_range && vmax < INFINITY && vmax > 0.0 && vmin_nz < std::ldexp(vmax, -8);
   }
+  // Sharded partition (shard.cu): this rank holds only its own column block of the labels.  The other blocks
+  // arrive as 1- / 2-byte canonical labels (one all-gather of N^2 bytes per square) and the digit slices are
+  // gathered straight from those; only the rare column-maximum guard needs the u32 matrix.
+  const void* lab_src = ctx->labels;
+  int lab_width = 4;
+  if (from_labels && sdpsr_shard_active(ctx) && !ctx->labels_full) {
+    if (need_colmax) {
+      SDPSR_TRY(sdpsr_shard_ensure_full_labels(ctx));
+    } else {
+      SDPSR_TRY(sdpsr_shard_gather_compact(ctx));
+      if (!ctx->labels_full) {
+        lab_src = ctx->clabels;
+        lab_width = ctx->clabel_width;
+      }
+    }
+  }
   if (need_colmax) {
     h_max[0] = 0ull;
     h_max[1] = ~0ull;
@@ -872,20 +923,20 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits,
     const uint32_t len = t.cap + 1;
     SDPSR_TRY(sdpsr_scratch_t(ctx, 29, (size_t)len, &dlut));
     const double scale = std::ldexp(1.0, bits * (S - 1) + 6 - e);
-    Timed tm(ctx, SDPSR_K_MISC, (double)elems * (4.0 + S));
+    Timed tm(ctx, SDPSR_K_MISC, (double)elems * ((double)lab_width + S));
     // (unoccupied ids hold stale lut values; they are never referenced by a label)
     if (bits == 8)
       dlut_kernel<8><<<(len + 255) / 256, 256, 0, ctx->stream>>>(ctx->lut, len, S, scale, dlut);
     else
       dlut_kernel<7><<<(len + 255) / 256, 256, 0, ctx->stream>>>(ctx->lut, len, S, scale, dlut);
     switch (S) {
-      case 2: launch_slices_labels<2>(ctx->labels, dlut, elems, slices, ctx->stream); break;
-      case 3: launch_slices_labels<3>(ctx->labels, dlut, elems, slices, ctx->stream); break;
-      case 4: launch_slices_labels<4>(ctx->labels, dlut, elems, slices, ctx->stream); break;
-      case 5: launch_slices_labels<5>(ctx->labels, dlut, elems, slices, ctx->stream); break;
-      case 6: launch_slices_labels<6>(ctx->labels, dlut, elems, slices, ctx->stream); break;
-      case 7: launch_slices_labels<7>(ctx->labels, dlut, elems, slices, ctx->stream); break;
-      default: launch_slices_labels<8>(ctx->labels, dlut, elems, slices, ctx->stream); break;
+      case 2: launch_slices_labels<2>(lab_src, lab_width, dlut, elems, slices, ctx->stream); break;
+      case 3: launch_slices_labels<3>(lab_src, lab_width, dlut, elems, slices, ctx->stream); break;
+      case 4: launch_slices_labels<4>(lab_src, lab_width, dlut, elems, slices, ctx->stream); break;
+      case 5: launch_slices_labels<5>(lab_src, lab_width, dlut, elems, slices, ctx->stream); break;
+      case 6: launch_slices_labels<6>(lab_src, lab_width, dlut, elems, slices, ctx->stream); break;
+      case 7: launch_slices_labels<7>(lab_src, lab_width, dlut, elems, slices, ctx->stream); break;
+      default: launch_slices_labels<8>(lab_src, lab_width, dlut, elems, slices, ctx->stream); break;
     }
     count_launch(ctx, 2);
   } else {

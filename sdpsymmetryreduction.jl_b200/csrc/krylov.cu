@@ -393,6 +393,7 @@ extern "C" int sdpsr_eig_krylov(sdpsr_ctx* ctx, const double* r1, int64_t len, i
   SDPSR_REQUIRE(vals && mult && ne_out, SDPSR_E_INVALID, "vals / mult / ne is NULL");
   SDPSR_REQUIRE(max_steps >= 1, SDPSR_E_INVALID, "max_steps must be positive");
   SDPSR_REQUIRE(tol > 0.0 && tol < 1e-4, SDPSR_E_INVALID, "tol must be in (0, 1e-4)");
+  SDPSR_TRY(sdpsr_shard_ensure_full_labels(ctx));
   int sym = 0;
   SDPSR_TRY(sdpsr_symmetric_check(ctx, &sym));
   SDPSR_REQUIRE(sym, SDPSR_E_NOT_SYMMETRIC,

@@ -304,6 +304,7 @@ static int u32_symmetric(sdpsr_ctx* ctx, const uint32_t* arr, int* is_sym) {
 int sdpsr_symmetric_check(sdpsr_ctx* ctx, int* is_sym) {
   if (ctx->sym_state < 0) {
     int s = 0;
+    SDPSR_TRY(sdpsr_shard_ensure_full_labels(ctx));
     SDPSR_TRY(u32_symmetric(ctx, ctx->labels, &s));
     ctx->sym_state = s;
   }
@@ -391,8 +392,75 @@ int sdpsr_upload_tpat(sdpsr_ctx* ctx, const std::vector<double>& coef) {
   return SDPSR_OK;
 }
 
+// C3: A x for x = lut[labels] with the partition sharded by column blocks.  Every rank reduces the stored
+// non-zeros that fall into ITS block (per constraint row a contiguous sub-range: column indices ascend),
+// the per-chunk partial sums are all-gathered and added in (rank, chunk) order on every rank: identical
+// coefficients everywhere, no label of another rank's block is read.
+static int rowdots_sharded_setup(sdpsr_ctx* ctx) {
+  ConstraintSet& c = ctx->cons;
+  if (c.sh_nranks == ctx->nranks && c.sh_rank == ctx->rank) return SDPSR_OK;
+  const int G = ctx->nranks;
+  const int64_t n = ctx->n;
+  c.sh_chunk_row.assign((size_t)G, {});
+  std::vector<uint32_t> beg, end;
+  for (int r = 0; r < G; ++r) {
+    const int64_t c0 = n * r / G, c1 = n * (r + 1) / G;          // columns of rank r
+    const int64_t lo = c0 * n, hi = c1 * n;                       // unpadded linear index range
+    for (int64_t k = 0; k < c.m; ++k) {
+      const int64_t* b = c.h_col.data() + c.h_rowptr[k];
+      const int64_t* e = c.h_col.data() + c.h_rowptr[k + 1];
+      const int64_t e0 = std::lower_bound(b, e, lo) - c.h_col.data();
+      const int64_t e1 = std::lower_bound(b, e, hi) - c.h_col.data();
+      for (int64_t x = e0; x < e1; x += CHUNK) {
+        c.sh_chunk_row[(size_t)r].push_back((uint32_t)k);
+        if (r == ctx->rank) {
+          beg.push_back((uint32_t)x);
+          end.push_back((uint32_t)std::min<int64_t>(x + CHUNK, e1));
+        }
+      }
+    }
+  }
+  c.sh_maxchunks = 1;
+  for (int r = 0; r < G; ++r) c.sh_maxchunks = std::max(c.sh_maxchunks, c.sh_chunk_row[(size_t)r].size());
+  const size_t mine = beg.size();
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 15, std::max<size_t>(1, 2 * mine), &c.d_sh_beg));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 7, c.sh_maxchunks * (size_t)G, &c.d_sh_partial));
+  if (mine) {
+    SDPSR_CUDA(cudaMemcpyAsync(c.d_sh_beg, beg.data(), mine * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SDPSR_CUDA(cudaMemcpyAsync(c.d_sh_beg + mine, end.data(), mine * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  c.sh_nranks = G;
+  c.sh_rank = ctx->rank;
+  return SDPSR_OK;
+}
+
+static int rowdots_sharded(sdpsr_ctx* ctx, const double* lut, std::vector<double>& out) {
+  ConstraintSet& c = ctx->cons;
+  SDPSR_TRY(rowdots_sharded_setup(ctx));
+  const int G = ctx->nranks;
+  const size_t mine = c.sh_chunk_row[(size_t)ctx->rank].size();
+  out.assign((size_t)c.m, 0.0);
+  if (mine) {
+    Timed tm(ctx, SDPSR_K_PROJECT, (double)c.nnz / G * 20.0);
+    rowdot_kernel<<<(unsigned)mine, 256, 0, ctx->stream>>>(c.d_col, c.d_val, c.d_sh_beg, c.d_sh_beg + mine, nullptr, lut,
+                                                           ctx->labels, c.d_sh_partial + c.sh_maxchunks * (size_t)ctx->rank);
+    count_launch(ctx);
+  }
+  SDPSR_CUDA(cudaGetLastError());
+  SDPSR_TRY(sdpsr_comm_allgather(ctx, c.d_sh_partial, c.sh_maxchunks * sizeof(double)));
+  std::vector<double> part(c.sh_maxchunks * (size_t)G);
+  SDPSR_CUDA(cudaMemcpyAsync(part.data(), c.d_sh_partial, part.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int r = 0; r < G; ++r)
+    for (size_t i = 0; i < c.sh_chunk_row[(size_t)r].size(); ++i)
+      out[c.sh_chunk_row[(size_t)r][i]] += part[c.sh_maxchunks * (size_t)r + i];      // fixed order: deterministic
+  return SDPSR_OK;
+}
+
 int sdpsr_rowdots(sdpsr_ctx* ctx, const double* x_array, const double* lut, std::vector<double>& out) {
   ConstraintSet& c = ctx->cons;
+  if (!x_array && sdpsr_shard_active(ctx) && !ctx->labels_full) return rowdots_sharded(ctx, lut, out);
   out.assign((size_t)c.m, 0.0);
   if (c.nchunks == 0) return SDPSR_OK;
   {
@@ -682,7 +750,7 @@ extern "C" int sdpsr_project_round_refine(sdpsr_ctx* ctx, double atol, int64_t* 
   long long isc;
   int qb;
   SDPSR_TRY(sdpsr_round_params(ctx, atol, &sc, &isc, &qb));
-  if (12 + qb + bits_for((uint64_t)ctx->tab[ctx->cur].cap) <= 64) {
+  if (12 + qb + sdpsr_label_bits(ctx) <= 64) {
     // The projected, rounded element stays as X (:163) -- but not as N^2 doubles: the keys of the pass carry
     // the rounded values, so X = fill(S_new, lut) with lut decoded from the new table (12 B/entry pass).
     sp.mode = KM_ROUND;
@@ -805,6 +873,7 @@ extern "C" int sdpsr_reduce_problem(sdpsr_ctx* ctx, const double* C, double* new
   SDPSR_REQUIRE(newA == nullptr || c.ready, SDPSR_E_STATE, "constraints not set (sdpsr_set_constraints_*)");
   const int64_t d = ctx->dim, m = c.m;
   if (d == 0) return SDPSR_OK;
+  SDPSR_TRY(sdpsr_shard_ensure_full_labels(ctx));
   KeyTable& t = ctx->tab[ctx->cur];
   const size_t smem = d <= RB_MAX ? (size_t)d * sizeof(double) : 0;
   double* dA = nullptr;

@@ -43,6 +43,7 @@ struct RefineArgs {
   const uint32_t* pid;
   uint32_t* lab_out;
   uint64_t total;
+  uint32_t idx0;        // padded linear index of the first entry of the range (sharded passes)
   double atol;
   double scale;
   long long iscale;
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(RT) refine_kernel(const RefineArgs a) {
 #pragma unroll
       for (int e = 0; e < EPT; ++e) {
         const uint64_t k = key[e];
-        const uint32_t idx = (uint32_t)(base + e);
+        const uint32_t idx = a.idx0 + (uint32_t)(base + e);
         const bool same = e > 0 && k == key[e - 1];      // run of equal keys: first one did the work
         const bool need = k != 0ull && !same;            // the zero class keeps id 0
         uint32_t g = same ? gid[e - 1] : 0u;
@@ -437,7 +438,7 @@ __global__ void __launch_bounds__(RT, 1) refine_fast_kernel(const RefineArgs a) 
             if (raw.x == klo[e] && raw.y == khi[e]) {
               g = raw.z;                                   // 0 while the publisher is in flight
               if (g != 0u && iter <= raw.w) {
-                const uint32_t idx = (uint32_t)(base + e);
+                const uint32_t idx = a.idx0 + (uint32_t)(base + e);
                 if (idx < ld_vol32(a.gmin + (g - 1))) atomicMin(a.gmin + (g - 1), idx);
               }
               break;
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(RT, 1) refine_fast_kernel(const RefineArgs a) 
         __syncwarp(wmask);       // lanes leave the probe loop at different times: reconverge here
         if (need && g == 0u)
           g = refine_miss(a.gkeys, a.gmin, a.gocc, a.gmeta, a.gmask, a.glimit, cache, &s_count,
-                          ((uint64_t)khi[e] << 32) | klo[e], (uint32_t)(base + e), free_slot, iter);
+                          ((uint64_t)khi[e] << 32) | klo[e], a.idx0 + (uint32_t)(base + e), free_slot, iter);
         __syncwarp(wmask);
         gid[e] = g;
       }
@@ -658,6 +659,11 @@ __global__ void __launch_bounds__(256) fill_kernel(const uint32_t* __restrict__ 
   }
 }
 
+__global__ void relabel_ids_kernel(uint32_t* __restrict__ ids, const uint32_t* __restrict__ rank, uint64_t total) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
+    ids[i] = rank[ids[i]];
+}
+
 // canonical labels, unpadded: out[i + n*j] = rank[labels[i + ld*j]]
 __global__ void canonical_kernel(const uint32_t* __restrict__ labels, const uint32_t* __restrict__ rank,
                                  uint32_t* __restrict__ out, int64_t n, int64_t ld) {
@@ -772,27 +778,36 @@ int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
     SDPSR_CUDA(cudaFuncSetAttribute(refine_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  KeyTable& told = ctx->tab[ctx->cur];
   KeyTable& tnew = spec.table_override ? *spec.table_override : ctx->tab[ctx->cur ^ 1];
 
+  // Sharded partition (shard.cu): the pass runs over this rank's column block only and is followed by the
+  // key-table merge.  Passes with an output / table override (pattern ids, the id pass of the two-step
+  // refine) are rank-local full-range passes.
+  const bool sharded = sdpsr_shard_active(ctx) && !spec.out_override && !spec.table_override;
+  uint64_t rb = 0, re = ctx->elems;
+  if (sharded) sdpsr_shard_block(ctx, ctx->rank, &rb, &re);
+  else if (sdpsr_shard_active(ctx) && !spec.ignore_labels) SDPSR_TRY(sdpsr_shard_ensure_full_labels(ctx));
   RefineArgs a;
   std::memset(&a, 0, sizeof(a));
-  a.lab_in = spec.ignore_labels ? nullptr : ctx->labels;
-  a.lab2 = spec.lab2;
-  a.vals = spec.vals;
-  a.vals_out = spec.vals_out;
+  a.lab_in = spec.ignore_labels ? nullptr : ctx->labels + rb;
+  a.lab2 = spec.lab2 ? spec.lab2 + rb : nullptr;
+  a.vals = spec.vals ? spec.vals + rb : nullptr;
+  a.vals_out = spec.vals_out ? spec.vals_out + rb : nullptr;
   a.lut = spec.lut;
   a.tpat = spec.tpat;
-  a.pid = spec.pid;
-  a.lab_out = spec.out_override ? spec.out_override : ctx->labels_alt;
-  a.total = ctx->elems;
+  a.pid = spec.pid ? spec.pid + rb : nullptr;
+  a.lab_out = (spec.out_override ? spec.out_override : ctx->labels_alt) + rb;
+  a.total = re - rb;
+  a.idx0 = (uint32_t)rb;
   a.atol = spec.atol;
   a.do_round = spec.do_round ? 1 : 0;
   a.fillproj = spec.fillproj ? 1 : 0;
   a.raw_bits = spec.raw_bits ? 1 : 0;
   // the per-CTA cache only pays while the classes fit it; the new dim is >= the current one
   a.use_cache = ((ctx->flags & SDPSR_F_NO_SMEM_CACHE) || (!spec.table_override && ctx->dim > SC_LIMIT)) ? 0 : 1;
-  a.lbits = spec.ignore_labels ? 1 : bits_for((uint64_t)told.cap);   // provisional ids are <= cap
+  // provisional ids are <= cap; sharded: canonical ids <= dim, and the key layout must not depend on a
+  // rank's table capacity (keys are compared across ranks)
+  a.lbits = spec.ignore_labels ? 1 : sdpsr_label_bits(ctx);
   if (spec.do_round && spec.mode != KM_PAIR) SDPSR_TRY(sdpsr_round_params(ctx, spec.atol, &a.scale, &a.iscale, &a.qbits));
   if (spec.mode == KM_ROUND) {
     SDPSR_REQUIRE(spec.do_round, SDPSR_E_INVALID, "KM_ROUND needs rounding");
@@ -802,8 +817,8 @@ int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
   size_t cap = tnew.cap ? tnew.cap : initial_cap(ctx);
   if (cap < initial_cap(ctx)) cap = initial_cap(ctx);
   const size_t cap_max = std::max<size_t>(64, next_pow2(2 * (uint64_t)ctx->elems));
-  const uint64_t ntiles = (ctx->elems + TILE - 1) / TILE;
-  const int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count);
+  const uint64_t ntiles = (a.total + TILE - 1) / TILE;
+  const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count));
   bool last_fast = false;
 
   for (;;) {
@@ -817,7 +832,7 @@ int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
     a.gmask = tnew.cap - 1;
     a.glimit = tnew.cap / 2;
     {
-      Timed tm(ctx, SDPSR_K_REFINE, (double)ctx->elems * 16.0);
+      Timed tm(ctx, SDPSR_K_REFINE, (double)a.total * 16.0);
       const bool wb = a.vals_out != nullptr;
       const bool fast = spec.mode == KM_ROUND && a.iscale == 10000000ll && a.lbits <= 28 &&
                         !(ctx->flags & SDPSR_F_NO_SMEM_CACHE);
@@ -855,7 +870,14 @@ int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
     SDPSR_REQUIRE(cap < cap_max, SDPSR_E_ALLOC, "key table overflow at maximum capacity");
     cap = std::min(cap * 4, cap_max);
   }
-  SDPSR_TRY(sdpsr_rank_table(ctx, tnew));
+  if (sharded) {
+    int64_t dg = 0;
+    SDPSR_TRY(sdpsr_shard_merge(ctx, tnew, ctx->labels_alt, &dg));
+    ctx->labels_full = false;
+    ctx->clabels_valid = false;
+  } else {
+    SDPSR_TRY(sdpsr_rank_table(ctx, tnew));
+  }
   if (!spec.out_override) {
     std::swap(ctx->labels, ctx->labels_alt);
     ctx->cur ^= 1;
@@ -869,6 +891,13 @@ int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
   }
   if (dim) *dim = tnew.count;
   return SDPSR_OK;
+}
+
+// Bits of the old-label field of a key.  Provisional ids are <= cap; in a sharded run the labels are canonical
+// (<= dim) and the layout must not depend on a rank's table capacity: keys are compared across ranks, and the
+// choice between the fused pass and the two-step refine (which contains collectives) must be the same everywhere.
+int sdpsr_label_bits(const sdpsr_ctx* ctx) {
+  return sdpsr_shard_active(ctx) ? bits_for((uint64_t)ctx->dim + 1) : bits_for((uint64_t)ctx->tab[ctx->cur].cap);
 }
 
 int sdpsr_ensure_tmp_labels(sdpsr_ctx* ctx) {
@@ -890,7 +919,7 @@ int sdpsr_generic_refine_values(sdpsr_ctx* ctx, const double* dvals, double atol
     long long isc;
     int qb;
     SDPSR_TRY(sdpsr_round_params(ctx, atol, &sc, &isc, &qb));
-    fused = 12 + qb + bits_for((uint64_t)ctx->tab[ctx->cur].cap) <= 64;
+    fused = 12 + qb + sdpsr_label_bits(ctx) <= 64;
   }
   RefineSpec sp;
   sp.vals = dvals;
@@ -915,6 +944,8 @@ int sdpsr_generic_refine_values(sdpsr_ctx* ctx, const double* dvals, double atol
   sp.table_override = &scratch;
   int64_t d2 = 0;
   int st = sdpsr_refine_pass(ctx, sp, &d2);
+  if (st == SDPSR_OK && sdpsr_shard_active(ctx))
+    st = sdpsr_relabel_by_rank(ctx, ctx->labels_tmp, scratch);   // ids that every rank agrees on
   if (st == SDPSR_OK) {
     RefineSpec pr;
     pr.mode = KM_PAIR;
@@ -924,6 +955,15 @@ int sdpsr_generic_refine_values(sdpsr_ctx* ctx, const double* dvals, double atol
     st = sdpsr_refine_pass(ctx, pr, dim);
   }
   return st;
+}
+
+// ids[i] = t.rank[ids[i]]: provisional slot ids (rank-dependent) -> canonical first-occurrence labels
+int sdpsr_relabel_by_rank(sdpsr_ctx* ctx, uint32_t* ids, KeyTable& t) {
+  const int grid = (int)std::min<uint64_t>((ctx->elems + 255) / 256, (uint64_t)ctx->sm_count * 16);
+  relabel_ids_kernel<<<grid, 256, 0, ctx->stream>>>(ids, t.rank, ctx->elems);
+  count_launch(ctx);
+  SDPSR_CUDA(cudaGetLastError());
+  return SDPSR_OK;
 }
 
 int sdpsr_upload_values(sdpsr_ctx* ctx, const double* values, int64_t len) {
@@ -1003,6 +1043,7 @@ int sdpsr_lut_stats(sdpsr_ctx* ctx, double* vmax, double* vmin_nz) {
 }
 
 int sdpsr_materialize_fill(sdpsr_ctx* ctx, double* dst) {
+  SDPSR_TRY(sdpsr_shard_ensure_full_labels(ctx));
   Timed tm(ctx, SDPSR_K_FILL, (double)ctx->elems * 12.0);
   const uint64_t per = 256 * 4;
   const int grid = (int)std::min<uint64_t>((ctx->elems + per - 1) / per, (uint64_t)ctx->sm_count * 8);
@@ -1013,6 +1054,7 @@ int sdpsr_materialize_fill(sdpsr_ctx* ctx, double* dst) {
 }
 
 int sdpsr_canonical_labels(sdpsr_ctx* ctx, uint32_t* dst_unpadded) {
+  SDPSR_TRY(sdpsr_shard_ensure_full_labels(ctx));
   KeyTable& t = ctx->tab[ctx->cur];
   dim3 grid((unsigned)std::min<int64_t>((ctx->n + 255) / 256, 64), (unsigned)ctx->n);
   canonical_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->labels, t.rank, dst_unpadded, ctx->n, ctx->ld);

@@ -68,6 +68,12 @@ struct ConstraintSet {
   std::vector<double> pat_val;
   std::vector<int64_t> pat_cnt;  // [npat+1]
   std::vector<uint32_t> chunk_row;   // host copy
+  // sharded row dots (C3): the chunks of every rank's column block; d_sh_* hold this rank's
+  int sh_nranks = 0, sh_rank = -1;
+  std::vector<std::vector<uint32_t>> sh_chunk_row;   // [rank][chunk] constraint row
+  size_t sh_maxchunks = 0;
+  uint32_t* d_sh_beg = nullptr;      // [2 * nchunks of this rank] begin | end
+  double* d_sh_partial = nullptr;    // [nranks * sh_maxchunks]
   std::vector<long double> gram_chol;   // m x m pivoted Cholesky factor (row-major) of A A'
   std::vector<int> gram_perm;           // pivot order: gram_perm[i] = constraint row eliminated i-th
   int gram_rank = 0;                    // numerical rank of A; rows gram_perm[rank..] are dependent (dropped)
@@ -103,6 +109,14 @@ struct sdpsr_ctx {
   uint32_t* labels_tmp = nullptr;   // lazily allocated third buffer (generic two-step refine, IO)
   KeyTable tab[2];
   KeyTable tab_scratch;             // reusable third table (two-step refine, pattern ids)
+  KeyTable tab_merge;               // sharded refine: the merged (key -> first index) table (shard.cu)
+  // Sharded partition (nranks > 1, shard.cu): this rank's column block of `labels` is always current; the
+  // other blocks only while labels_full.  clabels = all blocks as 1- / 2-byte canonical labels (gathered
+  // lazily, the INT8 square reads its digit slices through them).
+  bool labels_full = true;
+  uint8_t* clabels = nullptr;       // [elems * 2] bytes, lazily
+  int clabel_width = 0;             // 1, 2 (clabels) or 4 (labels gathered directly)
+  bool clabels_valid = false;
   int cur = 0;
   int64_t dim = 0;
 
@@ -253,6 +267,7 @@ int sdpsr_generic_refine_values(sdpsr_ctx* ctx, const double* dvals, double atol
 int sdpsr_table_alloc(sdpsr_ctx* ctx, KeyTable& t, size_t cap);
 void sdpsr_table_free(KeyTable& t);
 int sdpsr_rank_table(sdpsr_ctx* ctx, KeyTable& t);
+int sdpsr_relabel_by_rank(sdpsr_ctx* ctx, uint32_t* ids, KeyTable& t);
 int sdpsr_build_lut(sdpsr_ctx* ctx, const double* d_values, int64_t len);
 int sdpsr_materialize_fill(sdpsr_ctx* ctx, double* dst);
 int sdpsr_decode_lut(sdpsr_ctx* ctx, double atol);
@@ -260,13 +275,14 @@ int sdpsr_lut_stats(sdpsr_ctx* ctx, double* vmax, double* vmin_nz);
 int sdpsr_canonical_labels(sdpsr_ctx* ctx, uint32_t* dst_unpadded);
 int sdpsr_round_params(sdpsr_ctx* ctx, double atol, double* scale, long long* iscale, int* qbits);
 int sdpsr_ensure_tmp_labels(sdpsr_ctx* ctx);
+int sdpsr_label_bits(const sdpsr_ctx* ctx);
 int sdpsr_upload_values(sdpsr_ctx* ctx, const double* values, int64_t len);
 
 // gemm_f64.cu :  C[M x Nc] = A[M x K] * B[K x Nc], all column-major with the given lds
 int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t ldb,
                    double* C, int64_t ldc, int64_t M, int64_t Nc, int64_t K, bool symmetric_out,
                    bool shard = false, int accum = 0);
-int sdpsr_mirror_lower(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t n);
+int sdpsr_mirror_lower(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t n, int64_t col_begin = 0, int64_t col_end = -1);
 
 // gemm_i8.cu : C = X * X for bit-for-bit symmetric X on the tcgen05 INT8 tensor path
 int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int slices, int bits, bool shard, bool force_range,
@@ -293,6 +309,14 @@ void sdpsr_comm_free(sdpsr_ctx* ctx);
 int sdpsr_comm_exchange_tilecols(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t ncols, int tile_cols, int ntilecols);
 int sdpsr_comm_bcast(sdpsr_ctx* ctx, void* buf, size_t bytes, int root);
 int sdpsr_comm_allgather(sdpsr_ctx* ctx, void* recv, size_t bytes_per_rank);
+int sdpsr_comm_allgatherv(sdpsr_ctx* ctx, void* base, const size_t* offset, const size_t* bytes);
+
+// shard.cu
+void sdpsr_shard_block(const sdpsr_ctx* ctx, int r, uint64_t* begin, uint64_t* end);
+bool sdpsr_shard_active(const sdpsr_ctx* ctx);
+int sdpsr_shard_merge(sdpsr_ctx* ctx, KeyTable& tloc, uint32_t* lab, int64_t* dim);
+int sdpsr_shard_gather_compact(sdpsr_ctx* ctx);
+int sdpsr_shard_ensure_full_labels(sdpsr_ctx* ctx);
 int sdpsr_comm_agree_min(sdpsr_ctx* ctx, int* flag);
 int sdpsr_comm_barrier(sdpsr_ctx* ctx);
 double* const* sdpsr_comm_peer_table(sdpsr_ctx* ctx, const double* C);
