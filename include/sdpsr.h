@@ -196,23 +196,26 @@ int sdpsr_set_qhat(sdpsr_ctx* ctx, const double* qhat, const int64_t* blk_sizes,
  * with |entries| < atol clamped to 0.  out_len must be dim * sum(s_k^2).              */
 int sdpsr_basis_image(sdpsr_ctx* ctx, double atol, double* out, int64_t out_len);
 
-/* ------------------------------------------ blockDiagonalize, Krylov variant
+/* ------------------------------------------ blockDiagonalize, module variant
  * Same results as sdpsr_eig / sdpsr_block_norms / sdpsr_irreducible (i.e. as
- * src/eigen_decomposition.jl:236-348) for partitions whose generic element has FEW distinct
- * eigenvalues, at the cost of O(ne) label-matrix x vector products instead of an O(N^3) `eigen`:
- * Lanczos on A1 = fill(S, r1) breaks down after ne = #eigenspaces steps and its Ritz vectors are one
- * unit eigenvector per eigenspace -- all the reference ever uses (first column of the root
- * eigenspace, :311-314, and projections of A3 times it, :327-336).  Self-validating: every entry
- * point returns SDPSR_E_KRYLOV when a clean breakdown / integer multiplicities / matching Ritz
- * values are not observed; the caller then runs the dense entry points with the same r1, r2, r3.
+ * src/eigen_decomposition.jl:236-348) without the O(N^3) `eigen`: everything the reference takes from the
+ * eigendecomposition of the generic element A1 = fill(S, r1) -- one unit vector per eigenspace (first
+ * column of the root eigenspace, :311-314) and the projections of A3 times it (:327-336) -- lies in the
+ * module M generated by one unit vector per diagonal class, an invariant subspace of dimension
+ * D <= 2 dim(S).  The engine builds an orthonormal basis Q of M from columns of the label matrix (closing it
+ * under A1 when the partition is a Jordan configuration that is not coherent), and runs the reference's
+ * steps on the D x D matrices Q' A_t Q; Qhat = Q Z.  Cost: a few (N x N) x (N x D) products.
+ * Self-validating: every entry point returns SDPSR_E_KRYLOV when the module is larger than max_dim, a rank
+ * decision is ambiguous, the eigenspace dimensions are not integers adding up to N, or M is not invariant
+ * under A2 / A3; the caller then runs the dense entry points with the same r1, r2, r3.
  *
- * sdpsr_eig_krylov: vals[0..ne) = distinct eigenvalues of A1 ascending, mult[i] = dim E_i
- *   (sum = N); vals and mult need room for max_steps entries; tol = relative breakdown
- *   threshold (beta <= tol * ||A1||), 1e-10 recommended.  max_steps is capped at 48.
- * sdpsr_block_norms_krylov: norms (ne x ne, column-major) = ||P_j A2 y_i|| for eigenspaces of
- *   equal dimension, else 0 -- the stand-in for block_norms(Q'A2Q, Inf) (:177-204).
- * sdpsr_irreducible_krylov: as sdpsr_irreducible, with the eigenspaces of sdpsr_eig_krylov.      */
-int sdpsr_eig_krylov(sdpsr_ctx* ctx, const double* r1, int64_t len, int64_t max_steps, double tol,
+ * sdpsr_eig_krylov: vals[0..ne) = distinct eigenvalues of A1 ascending (clusters of the reference's rule:
+ *   a new eigenspace where the gap exceeds atol, :19-40), mult[i] = dim E_i (sum = N); vals and mult need
+ *   room for max_dim entries (the cap on D; at most 4096).
+ * sdpsr_block_norms_krylov: norms (ne x ne, column-major) = max |U_i' (Q' A2 Q) U_j| for eigenspaces of
+ *   equal dimension, else 0 -- block_norms(Q'A2Q, Inf) (:177-204) evaluated inside M.
+ * sdpsr_irreducible_krylov: as sdpsr_irreducible, with the eigenspaces of sdpsr_eig_krylov.          */
+int sdpsr_eig_krylov(sdpsr_ctx* ctx, const double* r1, int64_t len, int64_t max_dim, double atol,
                      double* vals, int64_t* mult, int64_t* ne);
 int sdpsr_block_norms_krylov(sdpsr_ctx* ctx, const double* r2, int64_t len, double* norms);
 int sdpsr_irreducible_krylov(sdpsr_ctx* ctx, const double* r3, int64_t len, const int64_t* kroot,

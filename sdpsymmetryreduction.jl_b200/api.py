@@ -403,10 +403,11 @@ def _isomorphism_classes(norms: np.ndarray, atol: float) -> np.ndarray:
 # ----------------------------------------------------------------------------
 # diagonalize / basis_image / blockDiagonalize
 # ----------------------------------------------------------------------------
-# Largest dim(P) for which ``eig="auto"`` tries the Krylov variant first (ne <= dim(P); a clean Lanczos
-# breakdown is only observed for about a dozen eigenspaces, and a failed attempt costs <= 48 label-matrix
-# x vector products -- a few ms at N = 16384 against seconds for syevd).
-KRYLOV_AUTO_MAX_DIM = 64
+# Largest dim(P) for which ``eig="auto"`` tries the module variant first (csrc/krylov.cu): its cost is a few
+# N x N x D products with D <= 2 dim(P), against an O(N^3) syevd, and a failed attempt falls back to the dense
+# path with the same coefficient vectors.
+KRYLOV_AUTO_MAX_DIM = 1024
+KRYLOV_MAX_MODULE_DIM = None        # cap on the module dimension (default 2 dim(P) + 16); tests lower it
 EIG_MODES = ("auto", "syevd", "krylov")
 
 
@@ -456,12 +457,11 @@ class _KrylovNotApplicable(Exception):
 
 
 def _diagonalize_krylov(P: Partition, ctx: B.Context, atol: float, rand: Callable):
-    """The same three steps on one vector per eigenspace (csrc/krylov.cu).  Raises
-    ``_KrylovNotApplicable`` when the device reports no clean Lanczos breakdown."""
+    """The same three steps inside the module generated by one unit vector per diagonal class
+    (csrc/krylov.cu).  Raises ``_KrylovNotApplicable`` when the device reports that it does not apply."""
     try:
-        vals, mult = ctx.eig_krylov(rand(P.nparts))                  # :242-254
-        if vals.size > 1 and np.min(np.diff(vals)) <= atol:          # the reference would merge these (:19-40)
-            raise _KrylovNotApplicable("distinct eigenvalues closer than atol")
+        vals, mult = ctx.eig_krylov(rand(P.nparts), atol,                              # :242-254, clusters :19-40
+                                    max_dim=KRYLOV_MAX_MODULE_DIM or 2 * P.nparts + 16)
         ptrs = np.concatenate([[0], np.cumsum(mult)]).astype(np.int64)
         norms = ctx.block_norms_krylov(rand(P.nparts), vals.size)    # :259, :203-204
         kroot = _isomorphism_classes(norms, atol)
@@ -511,7 +511,7 @@ def diagonalize(P: Partition, *, verbose: bool = False, atol: Optional[float] = 
                 raise _KrylovNotApplicable("block sizes do not add up to dim(P)")
             P._eig_mode = "krylov"
             if verbose:
-                log.info("Eigenspaces and algebra-isomorphism by Lanczos (%d eigenspaces)... %.3fs",
+                log.info("Eigenspaces and algebra-isomorphism inside the cyclic module (%d eigenspaces)... %.3fs",
                          ptrs.size - 1, time.perf_counter() - t)
         except _KrylovNotApplicable as e:
             if eig == "krylov":

@@ -343,14 +343,15 @@ class Context:
         return sizes[:nblk.value].copy()
 
     # -- Krylov variant (few distinct eigenvalues): raises SdpsrError(E_KRYLOV) when not applicable
-    def eig_krylov(self, r1, max_steps: int = 48, tol: float = 1e-10):
-        """Distinct eigenvalues (ascending) of fill(S, r1) and the dimensions of their eigenspaces."""
+    def eig_krylov(self, r1, atol: float, max_dim: int = 1024):
+        """Distinct eigenvalues (ascending, clustered with `atol`) of fill(S, r1) and the dimensions of their
+        eigenspaces, computed inside the module generated by one unit vector per diagonal class."""
         r1 = _f64(r1)
-        max_steps = int(max(1, min(max_steps, 48)))
-        vals = np.zeros(max_steps, dtype=np.float64)
-        mult = np.zeros(max_steps, dtype=np.int64)
+        max_dim = int(max(1, min(max_dim, 4096, self.n)))
+        vals = np.zeros(max_dim, dtype=np.float64)
+        mult = np.zeros(max_dim, dtype=np.int64)
         ne = _i64(0)
-        self._check(self.lib.sdpsr_eig_krylov(self._h, r1.ctypes.data, r1.size, max_steps, float(tol),
+        self._check(self.lib.sdpsr_eig_krylov(self._h, r1.ctypes.data, r1.size, max_dim, float(atol),
                                               vals.ctypes.data, mult.ctypes.data, C.byref(ne)))
         return vals[:ne.value].copy(), mult[:ne.value].copy()
 

@@ -373,10 +373,16 @@ int sdpsr_ensure_matrix(sdpsr_ctx* ctx, double** p) { return ensure_buffer(ctx, 
 
 namespace {
 
-// cuSOLVER is loaded with dlopen, the CUDA toolkit's copy first.  A host framework loaded into the same
-// process may bring an older libcusolver.so.11 under the same SONAME (PyTorch 2.11+cu128 bundles 11.7.3,
-// whose 64-bit Xsyevd_bufferSize rejects n = 32768 with INVALID_VALUE); binding by SONAME would silently
-// pick that one.  Order: $SDPSR_CUSOLVER_LIB, the toolkit path this library was built against, the SONAME.
+// cuSOLVER is loaded with dlopen.  Order:
+//   1. $SDPSR_CUSOLVER_LIB;
+//   2. a libcusolver.so.11 the process has ALREADY loaded (a host framework's copy: it matches the cuBLAS /
+//      cuSPARSE that framework brought, which is what its symbols bind to -- a second, newer cuSOLVER cannot be
+//      loaded next to an older cuBLAS under the same SONAME);
+//   3. the CUDA toolkit's copy, after its own dependencies (cuBLASLt, cuBLAS, cuSPARSE, nvJitLink) have been
+//      loaded from the same directory -- a bare box has no LD_LIBRARY_PATH entry for /usr/local/cuda/lib64;
+//   4. the SONAME through the default search path.
+// Known limit of case 2: PyTorch 2.11+cu128 bundles cuSOLVER 11.7.3, whose Xsyevd_bufferSize rejects
+// n >= 32767 (2 n^2 overflows an int); the toolkit's 11.7.5 accepts it.  The dense path reports that case.
 struct SolverApi {
   void* lib = nullptr;
   std::string path;
@@ -399,15 +405,31 @@ SolverApi& sapi() {
   tried = true;
   std::vector<std::string> names;
   if (const char* e = getenv("SDPSR_CUSOLVER_LIB")) names.push_back(e);
-  names.push_back("/usr/local/cuda/lib64/libcusolver.so.11");
+  names.push_back("@loaded");
+  names.push_back("@toolkit");
   names.push_back("libcusolver.so.11");
   names.push_back("libcusolver.so");
+  const char* tk = getenv("SDPSR_CUDA_LIB_DIR");
+  const std::string tkdir = tk ? tk : "/usr/local/cuda/lib64";
   for (const std::string& nme : names) {
-    void* h = dlopen(nme.c_str(), RTLD_NOW | RTLD_LOCAL);
+    void* h = nullptr;
+    std::string shown = nme;
+    if (nme == "@loaded") {
+      h = dlopen("libcusolver.so.11", RTLD_NOW | RTLD_NOLOAD);
+      shown = "libcusolver.so.11 (already loaded by the host process)";
+    } else if (nme == "@toolkit") {
+      if (dlopen("libcublas.so.12", RTLD_NOW | RTLD_NOLOAD)) continue;      // another cuBLAS is in: its cuSOLVER must follow
+      for (const char* dep : {"libnvJitLink.so.12", "libcublasLt.so.12", "libcublas.so.12", "libcusparse.so.12"})
+        dlopen((tkdir + "/" + dep).c_str(), RTLD_NOW | RTLD_GLOBAL);
+      shown = tkdir + "/libcusolver.so.11";
+      h = dlopen(shown.c_str(), RTLD_NOW | RTLD_LOCAL);
+    } else {
+      h = dlopen(nme.c_str(), RTLD_NOW | RTLD_LOCAL);
+    }
     if (!h) continue;
     SolverApi t;
     t.lib = h;
-    t.path = nme;
+    t.path = shown;
 #define SDPSR_SYM(field, sym) t.field = reinterpret_cast<decltype(t.field)>(dlsym(h, #sym))
     SDPSR_SYM(Create, cusolverDnCreate);
     SDPSR_SYM(Destroy, cusolverDnDestroy);
@@ -931,6 +953,43 @@ extern "C" int sdpsr_basis_image(sdpsr_ctx* ctx, double atol, double* out, int64
   SDPSR_TRY(status);
   SDPSR_CUDA(cudaMemcpy(out, result.data(), result.size() * 8, cudaMemcpyDefault));
   return finish(ctx);
+}
+
+
+// cuSOLVER Xsyevd of a small dense symmetric matrix held on the device (the module path of krylov.cu: D x D).
+// Eigenvectors overwrite dA; eigenvalues ascending in dvals (device).
+int sdpsr_small_syevd(sdpsr_ctx* ctx, double* dA, int64_t n, int64_t lda, double* dvals) {
+  if (!ctx->solver) {
+    Solver* s = new Solver();
+    ctx->solver = s;
+    SDPSR_REQUIRE(sapi().ok, SDPSR_E_CUSOLVER, "libcusolver.so.11 could not be loaded");
+    SDPSR_REQUIRE(sapi().Create(&s->h) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER, "cusolverDnCreate failed");
+    SDPSR_REQUIRE(sapi().SetStream(s->h, ctx->stream) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
+                  "cusolverDnSetStream failed");
+    SDPSR_REQUIRE(sapi().CreateParams(&s->params) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
+                  "cusolverDnCreateParams failed");
+    SDPSR_CUDA(cudaMalloc(&s->d_vals, (size_t)ctx->n * sizeof(double)));
+    SDPSR_CUDA(cudaMalloc(&ctx->solver_info, sizeof(int)));
+  }
+  Solver* s = reinterpret_cast<Solver*>(ctx->solver);
+  size_t wdev = 0, whost = 0;
+  cusolverStatus_t st = sapi().Xsyevd_bufferSize(s->h, s->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n,
+                                                 CUDA_R_64F, dA, lda, CUDA_R_64F, dvals, CUDA_R_64F, &wdev, &whost);
+  SDPSR_REQUIRE(st == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER, "cusolverDnXsyevd_bufferSize failed (small problem)");
+  void* work = nullptr;
+  SDPSR_TRY(sdpsr_scratch(ctx, 36, std::max<size_t>(wdev, 256), &work));
+  std::vector<unsigned char> hwork(std::max<size_t>(whost, 1));
+  {
+    Timed tm(ctx, SDPSR_K_EIG, 0.0);
+    st = sapi().Xsyevd(s->h, s->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F, dA, lda, CUDA_R_64F,
+                       dvals, CUDA_R_64F, work, wdev, hwork.data(), whost, ctx->solver_info);
+  }
+  SDPSR_REQUIRE(st == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER, "cusolverDnXsyevd failed (small problem)");
+  int* hinfo = reinterpret_cast<int*>(ctx->h_pinned) + 64;
+  SDPSR_CUDA(cudaMemcpyAsync(hinfo, ctx->solver_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  SDPSR_REQUIRE(*hinfo == 0, SDPSR_E_CUSOLVER, "syevd did not converge (small problem)");
+  return SDPSR_OK;
 }
 
 

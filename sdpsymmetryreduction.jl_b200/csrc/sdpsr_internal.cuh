@@ -205,7 +205,7 @@ struct sdpsr_ctx {
 
   // grow-only scratch buffers (slot -> device allocation): no cudaMalloc/cudaFree on the steady-state
   // path (allocation calls serialise across processes and jitter by up to seconds with IPC mappings)
-  static constexpr int SCRATCH_SLOTS = 32;
+  static constexpr int SCRATCH_SLOTS = 48;
   void* scratch_ptr[SCRATCH_SLOTS] = {};
   size_t scratch_bytes[SCRATCH_SLOTS] = {};
 

@@ -332,3 +332,53 @@ def synthetic_product_scheme(fields: int = 3, bits: int = 5, m: int = 64, seed: 
     return SDPProblem(name=f"synthetic-{fields}xH({bits},2)-m{m}", C=C, A=A, b=b, n=N,
                       expected_dim=norb, expected_blocks=[1] * norb, expected_mult=mult,
                       meta={"orbitals": orb_full})
+
+
+# ----------------------------------------------------------------------------
+# Jordan (not coherent) partitions: symmetrised regular representation of a non-abelian group
+# ----------------------------------------------------------------------------
+def symmetrized_group_partition(kind: str = "S3") -> np.ndarray:
+    """Label matrix (1-based classes, N x N, symmetric) of the partition  L[x, y] = class of {x^-1 y, y^-1 x}
+    for a small non-abelian group acting on itself.  Its span is the Jordan algebra of SYMMETRIC elements of
+    the regular representation: closed under squaring, but NOT under products (it is not a coherent
+    configuration), so the orbit of a unit vector under the basis is not an invariant subspace -- the case
+    that exercises the closure step of the module path (csrc/krylov.cu).  kinds: "S3", "S4", "D<n>" (dihedral
+    of order 2n), "Q8"."""
+    if kind == "S3" or kind == "S4":
+        k = int(kind[1])
+        elems = list(itertools.permutations(range(k)))
+        mul = lambda a, b: tuple(a[b[i]] for i in range(k))
+        inv = lambda a: tuple(sorted(range(k), key=lambda i: a[i]))
+    elif kind.startswith("D"):
+        n = int(kind[1:])
+        elems = [(r, s) for s in (0, 1) for r in range(n)]          # r^a s^b
+        mul = lambda a, b: ((a[0] + (b[0] if a[1] == 0 else -b[0])) % n, (a[1] + b[1]) % 2)
+        inv = lambda a: ((-a[0]) % n, 0) if a[1] == 0 else a
+    elif kind == "Q8":
+        # quaternion units as (sign, axis): axis 0 = 1, 1 = i, 2 = j, 3 = k
+        elems = [(s, a) for s in (1, -1) for a in range(4)]
+        tab = {(1, 2): (1, 3), (2, 3): (1, 1), (3, 1): (1, 2), (2, 1): (-1, 3), (3, 2): (-1, 1), (1, 3): (-1, 2)}
+
+        def mul(a, b):
+            if a[1] == 0:
+                return (a[0] * b[0], b[1])
+            if b[1] == 0:
+                return (a[0] * b[0], a[1])
+            if a[1] == b[1]:
+                return (-a[0] * b[0], 0)
+            s, ax = tab[(a[1], b[1])]
+            return (a[0] * b[0] * s, ax)
+        inv = lambda a: a if a[1] == 0 else (-a[0], a[1])
+    else:
+        raise ValueError(kind)
+    index = {g: i for i, g in enumerate(elems)}
+    N = len(elems)
+    cls = {}
+    L = np.zeros((N, N), dtype=np.int64)
+    for y in range(N):                      # column-major first occurrence: columns outer
+        for x in range(N):
+            g = mul(inv(elems[x]), elems[y])
+            key = min(index[g], index[inv(g)])
+            L[x, y] = cls.setdefault(key, len(cls) + 1)
+    assert np.array_equal(L, L.T)
+    return L

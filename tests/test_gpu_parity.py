@@ -288,7 +288,8 @@ def test_block_diagonalize_matches_oracle(prob, eig):
 
 
 KRYLOV_PROBLEMS = [pr.petersen(), pr.lovasz_er(3), pr.lovasz_er(5), pr.lovasz_er(7), pr.kneser(8, 3),
-                   pr.kneser(10, 4), pr.hamming(3, 8), pr.hamming(5, 4)]
+                   pr.kneser(10, 4), pr.hamming(3, 8), pr.hamming(5, 4), pr.qap_esc16j(os.path.join(GOLDEN, "esc16j.npz")),
+                   pr.synthetic_product_scheme(3, 2, 8), pr.synthetic_product_scheme(3, 3, 16)]
 
 
 @pytest.mark.parametrize("flags", [0, B.F_TINY_TABLE], ids=["single-pass-basis", "list-basis"])
@@ -320,23 +321,46 @@ def test_krylov_block_diagonalize_matches_oracle_and_dense(prob, flags):
     Pd.release()
 
 
+@pytest.mark.parametrize("kind", ["S3", "D4", "D5", "Q8", "D7", "S4", "D16"])
+def test_module_path_on_jordan_partitions_that_are_not_coherent(kind):
+    """Symmetrised regular representation of a non-abelian group: a Jordan algebra that is not closed under
+    products, so the orbit of a unit vector is not invariant and the module has to be closed under the generic
+    element (csrc/krylov.cu).  Same blocks as the oracle's dense restatement, same as the device's dense path."""
+    L = pr.symmetrized_group_partition(kind)
+    Po = O.Partition(int(L.max()), L.astype(np.uint32))
+    so, bo = O.blockDiagonalize(Po, Coeffs(52))
+    Pk = S.Partition(Po.nparts, Po.matrix.astype(np.uint32))
+    Pd = S.Partition(Po.nparts, Po.matrix.astype(np.uint32))
+    bk = S.blockDiagonalize(Pk, False, rand=Coeffs(52), eig="krylov")
+    bdn = S.blockDiagonalize(Pd, False, rand=Coeffs(52), eig="syevd")
+    assert list(bk.blkSizes) == list(bdn.blkSizes) == list(so)
+    assert np.array_equal(Pk._ptrs, Pd._ptrs) and np.array_equal(Pk._kroot, Pd._kroot)
+    for i in range(Po.nparts):
+        for k in range(len(so)):
+            tol = 1e-8 * max(1.0, np.abs(bo[i][k]).max())
+            assert np.abs(bk.blks[i][k] - bo[i][k]).max() < tol, (i, k)
+            assert np.abs(bk.blks[i][k] - bdn.blks[i][k]).max() < tol, (i, k)
+    Pk.release()
+    Pd.release()
+
+
 def test_krylov_not_applicable_falls_back_to_dense():
-    """esc16j has 45 eigenspaces: no clean Lanczos breakdown.  ``eig="krylov"`` reports it, ``auto``
-    (forced to try) lands on the dense path with the same coefficient vectors and the same blocks."""
+    """A module larger than the cap: ``eig="krylov"`` reports it, ``auto`` lands on the dense path with the
+    same coefficient vectors and the same blocks."""
+    import sdpsr_b200.api as api
     prob = pr.qap_esc16j(os.path.join(GOLDEN, "esc16j.npz"))
     Po = O.admissible_subspace(*prob, Coeffs(41))
     so, bo = O.blockDiagonalize(Po, Coeffs(42))
     P = S.Partition(Po.nparts, Po.matrix.astype(np.uint32))
-    with pytest.raises(S.NumericalInconsistency):
-        S.blockDiagonalize(P, False, rand=Coeffs(42), eig="krylov")
-    import sdpsr_b200.api as api
-    old = api.KRYLOV_AUTO_MAX_DIM
-    api.KRYLOV_AUTO_MAX_DIM = 1 << 20
+    old = api.KRYLOV_MAX_MODULE_DIM
+    api.KRYLOV_MAX_MODULE_DIM = 20          # the module of esc16j has dimension 45
     try:
+        with pytest.raises(S.NumericalInconsistency):
+            S.blockDiagonalize(P, False, rand=Coeffs(42), eig="krylov")
         cg = Coeffs(42)
         bd = S.blockDiagonalize(P, False, rand=cg, eig="auto")
     finally:
-        api.KRYLOV_AUTO_MAX_DIM = old
+        api.KRYLOV_MAX_MODULE_DIM = old
     assert P._eig_mode == "syevd" and cg.draws == [150] * 3
     assert list(bd.blkSizes) == list(so)
     for i in range(0, Po.nparts, 7):
