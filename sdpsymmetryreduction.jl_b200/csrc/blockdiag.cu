@@ -656,6 +656,7 @@ extern "C" int sdpsr_irreducible(sdpsr_ctx* ctx, const double* r3, int64_t len, 
   SDPSR_TRY(sdpsr_scratch_t(ctx, 16, (size_t)ld * (size_t)S, &ctx->Qhat));
   SDPSR_CUDA(cudaMemsetAsync(ctx->Qhat, 0, (size_t)ld * (size_t)S * 8, ctx->stream));
   ctx->qhat_cols = S;
+  sdpsr_module_invalidate_qhat(ctx);
   ctx->blk_sizes.clear();
   // first columns, and the list of (root, member) pairs that need work
   std::vector<int64_t> first_src, first_dst;     // Qhat[:, dst] = Q[:, src]
@@ -773,6 +774,7 @@ extern "C" int sdpsr_set_qhat(sdpsr_ctx* ctx, const double* qhat, const int64_t*
   SDPSR_CUDA(cudaMemcpy2DAsync(ctx->Qhat, (size_t)ctx->ld * 8, qhat, (size_t)ctx->n * 8, (size_t)ctx->n * 8, (size_t)S,
                                cudaMemcpyDefault, ctx->stream));
   ctx->qhat_cols = S;
+  sdpsr_module_invalidate_qhat(ctx);
   return finish(ctx);
 }
 
@@ -786,6 +788,8 @@ extern "C" int sdpsr_basis_image(sdpsr_ctx* ctx, double atol, double* out, int64
   SDPSR_REQUIRE(out_len == d * Sq, SDPSR_E_INVALID, "out_len must be dim * sum(s_k^2)");
   if (d == 0) return SDPSR_OK;
   SDPSR_TRY(sdpsr_shard_ensure_full_labels(ctx));
+  // Qhat built inside an orbit module (krylov.cu): basis_image is a counting pass
+  if (sdpsr_module_basis_available(ctx)) return sdpsr_module_basis_image(ctx, atol, out, out_len);
   KeyTable& t = ctx->tab[ctx->cur];
   if (d * Sq <= BS_MAX_BINS && Sq <= BS_MAX_PAIRS && !(ctx->flags & SDPSR_F_TINY_TABLE)) {
     // ---- few classes, small blocks: one pass over the labels (basis_small_kernel) -----------

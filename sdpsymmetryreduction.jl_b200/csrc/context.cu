@@ -250,6 +250,7 @@ extern "C" int sdpsr_partition_reset(sdpsr_ctx* ctx) {
   SDPSR_CUDA(cudaMemsetAsync(t.rank, 0, sizeof(uint32_t), ctx->stream));
   t.count = 0;
   ctx->dim = 0;
+  ctx->part_epoch += 1;
   ctx->x_is_fill = false;
   ctx->x_valid = false;
   ctx->key_decodable = false;

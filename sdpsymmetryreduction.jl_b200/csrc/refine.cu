@@ -882,6 +882,7 @@ int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
     std::swap(ctx->labels, ctx->labels_alt);
     ctx->cur ^= 1;
     ctx->dim = tnew.count;
+    ctx->part_epoch += 1;
     ctx->x_is_fill = false;
     // value-coded keys: the class values can be decoded from the table (sdpsr_decode_lut)
     ctx->key_decodable = spec.mode == KM_ROUND;

@@ -119,6 +119,7 @@ struct sdpsr_ctx {
   bool clabels_valid = false;
   int cur = 0;
   int64_t dim = 0;
+  uint64_t part_epoch = 0;          // bumped whenever the partition changes (derived state checks it)
 
   int i8_pair = -1;     // INT8 square on CTA pairs (cta_group::2): -1 = for N > 16384, 0 / 1 = SDPSR_I8_PAIR
   int i8_segblocks = 0; // test hook (SDPSR_I8_SEGBLOCKS): K segment length of the INT8 square in 128-byte blocks
@@ -303,6 +304,9 @@ void sdpsr_blockdiag_rebind(sdpsr_ctx* ctx);
 
 // krylov.cu
 void sdpsr_krylov_free(sdpsr_ctx* ctx);
+bool sdpsr_module_basis_available(const sdpsr_ctx* ctx);
+int sdpsr_module_basis_image(sdpsr_ctx* ctx, double atol, double* out, int64_t out_len);
+void sdpsr_module_invalidate_qhat(sdpsr_ctx* ctx);
 
 // comm.cu
 void sdpsr_comm_free(sdpsr_ctx* ctx);

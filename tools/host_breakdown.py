@@ -48,14 +48,14 @@ class Coeffs:
 
 which = sys.argv[1] if len(sys.argv) > 1 else "h74"
 t = time.perf_counter()
-prob = {"h74": lambda: pr.hamming(7, 4, sparse=True), "h48": lambda: pr.hamming(4, 8, sparse=True),
+prob = {"h74": lambda: pr.hamming(7, 4, sparse=True), "k205": lambda: pr.kneser(20, 5, sparse=True), "h48": lambda: pr.hamming(4, 8, sparse=True),
         "syn4096": lambda: pr.synthetic_product_scheme(3, 4, 32, keep_orbitals=False),
         "syn32768": lambda: pr.synthetic_product_scheme(3, 5, 64, keep_orbitals=False)}[which]()
 print(json.dumps({"build_s": time.perf_counter() - t}))
-for rep in range(2):
+for rep in range(3):
     acc.clear()
     t0 = time.perf_counter()
-    P = S.admissible_subspace(*prob, rand=Coeffs())
+    P = S.admissible_subspace(*prob, rand=Coeffs(), fetch_labels=False)
     t1 = time.perf_counter()
     bd = S.blockDiagonalize(P, False, rand=Coeffs(2))
     t2 = time.perf_counter()
