@@ -138,6 +138,11 @@ int sdpsr_partition_get_labels(sdpsr_ctx* ctx, void* labels, int elt_bytes);
 int sdpsr_partition_dim(sdpsr_ctx* ctx, int64_t* dim);
 /* number of entries with label 0 */
 int sdpsr_partition_zero_count(sdpsr_ctx* ctx, int64_t* count);
+/* _constraints(P) (src/diagonalize.jl:42-50; overridden per back-end, test/partitions_set.jl:92): for every
+ * class c = 1..dim the ascending column-major linear indices (plus index_base: 0 for C, 1 for Julia) of its
+ * entries, as one CSR: ptr[dim + 1], idx[idx_len] with idx_len = N^2 - sdpsr_partition_zero_count().
+ * The generic slow path of the AbstractPartition contract (the host does the counting sort).            */
+int sdpsr_partition_constraints(sdpsr_ctx* ctx, int64_t* ptr, uint32_t* idx, int64_t idx_len, int index_base);
 /* 1 iff labels[i,j] == labels[j,i] for all i,j */
 int sdpsr_partition_is_symmetric(sdpsr_ctx* ctx, int* is_symmetric);
 /* S = refine!(S, Partition(M)) with M a host/device N x N Float64 matrix

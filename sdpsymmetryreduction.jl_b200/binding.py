@@ -70,6 +70,7 @@ _SIGNATURES = {
     "sdpsr_square_round_refine": ([_p, C.c_double, C.POINTER(_i64)], C.c_int),
     "sdpsr_product_round_refine": ([_p, _p, _p, _i64, C.c_double, C.POINTER(_i64)], C.c_int),
     "sdpsr_eig": ([_p, _p, _i64, _p], C.c_int),
+    "sdpsr_partition_constraints": ([_p, _p, _p, _i64, C.c_int], C.c_int),
     "sdpsr_block_norms": ([_p, _p, _i64, _p, _i64, _p], C.c_int),
     "sdpsr_irreducible": ([_p, _p, _i64, _p, _i64, _p, C.c_double, _p, C.POINTER(_i64)], C.c_int),
     "sdpsr_eig_krylov": ([_p, _p, _i64, _i64, C.c_double, _p, _p, C.POINTER(_i64)], C.c_int),
@@ -341,6 +342,15 @@ class Context:
         self._check(self.lib.sdpsr_irreducible(self._h, r3.ctypes.data, r3.size, ptrs.ctypes.data, ptrs.size,
                                                kroot.ctypes.data, float(atol), sizes.ctypes.data, C.byref(nblk)))
         return sizes[:nblk.value].copy()
+
+    def partition_constraints(self, index_base: int = 0):
+        """``_constraints(P)`` (src/diagonalize.jl:42-50): list of ascending linear-index arrays, one per class."""
+        d = self.dim()
+        total = self.n * self.n - self.zero_count()
+        ptr = np.zeros(d + 1, dtype=np.int64)
+        idx = np.zeros(max(total, 1), dtype=np.uint32)
+        self._check(self.lib.sdpsr_partition_constraints(self._h, ptr.ctypes.data, idx.ctypes.data, total, index_base))
+        return [idx[ptr[i]:ptr[i + 1]] for i in range(d)]
 
     # -- Krylov variant (few distinct eigenvalues): raises SdpsrError(E_KRYLOV) when not applicable
     def eig_krylov(self, r1, atol: float, max_dim: int = 1024):

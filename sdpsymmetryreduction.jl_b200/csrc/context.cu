@@ -366,6 +366,38 @@ extern "C" int sdpsr_partition_zero_count(sdpsr_ctx* ctx, int64_t* count) {
   return SDPSR_OK;
 }
 
+// _constraints(P) (src/diagonalize.jl:42-50): for every class the ascending column-major linear indices of
+// its entries, as one CSR (ptr[dim + 1], idx[N^2 - #zeros]).  This is the generic slow path of the reference's
+// AbstractPartition contract, not a hot path: the canonical label matrix is brought to the host once and
+// the stable counting sort runs there.
+extern "C" int sdpsr_partition_constraints(sdpsr_ctx* ctx, int64_t* ptr, uint32_t* idx, int64_t idx_len, int index_base) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(ptr != nullptr && (idx != nullptr || idx_len == 0), SDPSR_E_INVALID, "ptr / idx is NULL");
+  SDPSR_REQUIRE(index_base == 0 || index_base == 1, SDPSR_E_INVALID, "index_base must be 0 or 1");
+  SDPSR_TRY(sdpsr_ensure_tmp_labels(ctx));
+  const int64_t nn = ctx->n * ctx->n, d = ctx->dim;
+  SDPSR_REQUIRE(nn + index_base <= 0xffffffffll, SDPSR_E_UNSUPPORTED, "linear indices do not fit UInt32");
+  SDPSR_TRY(sdpsr_canonical_labels(ctx, ctx->labels_tmp));
+  std::vector<uint32_t> lab((size_t)nn);
+  SDPSR_CUDA(cudaMemcpyAsync(lab.data(), ctx->labels_tmp, (size_t)nn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_TRY(finish(ctx));
+  std::vector<int64_t> cnt((size_t)d + 2, 0);
+  for (int64_t i = 0; i < nn; ++i) cnt[(size_t)lab[(size_t)i] + 1] += 1;       // cnt[c + 1] = |class c|
+  int64_t total = 0;
+  for (int64_t c = 1; c <= d; ++c) {
+    ptr[c - 1] = total;
+    total += cnt[(size_t)c + 1];
+  }
+  ptr[d] = total;
+  SDPSR_REQUIRE(idx_len == total, SDPSR_E_INVALID, "idx_len must be N^2 minus the number of zero labels");
+  std::vector<int64_t> cur(ptr, ptr + d);
+  for (int64_t i = 0; i < nn; ++i) {
+    const uint32_t c = lab[(size_t)i];
+    if (c) idx[cur[(size_t)c - 1]++] = (uint32_t)(i + index_base);
+  }
+  return SDPSR_OK;
+}
+
 extern "C" int sdpsr_partition_is_symmetric(sdpsr_ctx* ctx, int* is_symmetric) {
   CTX_ENTER();
   SDPSR_REQUIRE(is_symmetric != nullptr, SDPSR_E_INVALID, "is_symmetric is NULL");
@@ -499,7 +531,14 @@ extern "C" int sdpsr_square_round_refine(sdpsr_ctx* ctx, double atol, int64_t* d
   CTX_ENTER();
   SDPSR_REQUIRE(ctx->x_valid, SDPSR_E_STATE, "X is not defined yet (call sdpsr_fill first)");
   int sym = 0;
-  SDPSR_TRY(square_x(ctx, /*method=*/-1, ctx->i8_slices, 0, &sym));
+  if (sdpsr_shard_active(ctx)) {        // the refine below reads this rank's column block of X2 only
+    ctx->mirror_col0 = ctx->n * ctx->rank / ctx->nranks;
+    ctx->mirror_col1 = ctx->n * (ctx->rank + 1) / ctx->nranks;
+  }
+  const int sq_status = square_x(ctx, /*method=*/-1, ctx->i8_slices, 0, &sym);
+  ctx->mirror_col0 = 0;
+  ctx->mirror_col1 = -1;
+  SDPSR_TRY(sq_status);
   // X symmetric => X2 symmetric bit for bit (mirrored lower tiles): the refined partition stays symmetric
   SDPSR_TRY(sdpsr_generic_refine_values(ctx, ctx->X2, atol, true, nullptr, dim,
                                         /*keeps_symmetry=*/sym != 0 && !(ctx->flags & SDPSR_F_NO_SYRK)));

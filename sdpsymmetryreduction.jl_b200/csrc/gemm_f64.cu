@@ -362,7 +362,10 @@ int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B
       SDPSR_TRY(sdpsr_comm_exchange_tilecols(ctx, C, ldc, Nc, BN, tiles_n));
     }
   }
-  if (lower) SDPSR_TRY(sdpsr_mirror_lower(ctx, C, ldc, Nc));
+  if (lower) {
+    if (C == ctx->X2) SDPSR_TRY(sdpsr_mirror_lower(ctx, C, ldc, Nc, ctx->mirror_col0, ctx->mirror_col1));
+    else SDPSR_TRY(sdpsr_mirror_lower(ctx, C, ldc, Nc));
+  }
   return SDPSR_OK;
 }
 

@@ -1013,7 +1013,7 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits,
       SDPSR_TRY(sdpsr_comm_exchange_tilecols(ctx, C, ld, n, TN, (int)((n + TN - 1) / TN)));
     }
   }
-  SDPSR_TRY(sdpsr_mirror_lower(ctx, C, ld, n));
+  SDPSR_TRY(sdpsr_mirror_lower(ctx, C, ld, n, ctx->mirror_col0, ctx->mirror_col1));
   *done = 1;
   return SDPSR_OK;
 }

@@ -157,6 +157,33 @@ __global__ void __launch_bounds__(256) symmetrize_kernel(const double* __restric
   }
 }
 
+// out[i,j] = (f(i,j) + f(j,i)) / 2 for the columns j in [col0, col1), f = the elementwise step of init_elem_kernel
+// (mode 0: round(snap(src - t[pid])), mode 1: t[pid]) evaluated on the fly at both positions: the un-symmetrised
+// element is never written, and a rank of a sharded run produces its own column block only.  `out` must not
+// alias `src`.  32 x 32 tiles, the transposed operand goes through shared memory.
+__global__ void __launch_bounds__(256) init_sym_kernel(int mode, const double* __restrict__ src,
+                                                       const uint32_t* __restrict__ pid, const double* __restrict__ tpat,
+                                                       double* __restrict__ out, int64_t n, int64_t ld, int64_t col0,
+                                                       int64_t col1, double pw, int do_snap, double atol, double scale) {
+  __shared__ double t[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t bi = blockIdx.x;                       // row tile
+  const int64_t jb = col0 / 32 * 32 + (int64_t)blockIdx.y * 32;   // first column of the column tile
+  auto f = [&](int64_t i, int64_t j) -> double {
+    const double tp = tpat[pid[i + ld * j]];
+    return mode == 0 ? snap_round(__dsub_rn(src[i + ld * j], tp), pw, do_snap, atol, scale) : tp;
+  };
+  for (int r = ty; r < 32; r += 8) {   // transposed tile: rows jb.., columns bi*32..
+    const int64_t i = jb + tx, j = bi * 32 + r;
+    t[r][tx] = (i < n && j < n) ? f(i, j) : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = bi * 32 + tx, j = jb + r;
+    if (i < n && j >= col0 && j < col1) out[i + ld * j] = (f(i, j) + t[tx][r]) / 2;
+  }
+}
+
 __global__ void __launch_bounds__(256) symcheck_kernel(const uint32_t* __restrict__ lab, int64_t n, int64_t ld,
                                                        uint32_t* __restrict__ bad) {
   __shared__ uint32_t t[32][33];
@@ -435,7 +462,7 @@ static int rowdots_sharded_setup(sdpsr_ctx* ctx) {
   return SDPSR_OK;
 }
 
-static int rowdots_sharded(sdpsr_ctx* ctx, const double* lut, std::vector<double>& out) {
+static int rowdots_sharded(sdpsr_ctx* ctx, const double* x_array, const double* lut, std::vector<double>& out) {
   ConstraintSet& c = ctx->cons;
   SDPSR_TRY(rowdots_sharded_setup(ctx));
   const int G = ctx->nranks;
@@ -443,7 +470,7 @@ static int rowdots_sharded(sdpsr_ctx* ctx, const double* lut, std::vector<double
   out.assign((size_t)c.m, 0.0);
   if (mine) {
     Timed tm(ctx, SDPSR_K_PROJECT, (double)c.nnz / G * 20.0);
-    rowdot_kernel<<<(unsigned)mine, 256, 0, ctx->stream>>>(c.d_col, c.d_val, c.d_sh_beg, c.d_sh_beg + mine, nullptr, lut,
+    rowdot_kernel<<<(unsigned)mine, 256, 0, ctx->stream>>>(c.d_col, c.d_val, c.d_sh_beg, c.d_sh_beg + mine, x_array, lut,
                                                            ctx->labels, c.d_sh_partial + c.sh_maxchunks * (size_t)ctx->rank);
     count_launch(ctx);
   }
@@ -458,9 +485,10 @@ static int rowdots_sharded(sdpsr_ctx* ctx, const double* lut, std::vector<double
   return SDPSR_OK;
 }
 
-int sdpsr_rowdots(sdpsr_ctx* ctx, const double* x_array, const double* lut, std::vector<double>& out) {
+// x_own_block: x_array is current in this rank's column block only (sharded run)
+int sdpsr_rowdots(sdpsr_ctx* ctx, const double* x_array, const double* lut, std::vector<double>& out, bool x_own_block) {
   ConstraintSet& c = ctx->cons;
-  if (!x_array && sdpsr_shard_active(ctx) && !ctx->labels_full) return rowdots_sharded(ctx, lut, out);
+  if (sdpsr_shard_active(ctx) && (x_array ? x_own_block : !ctx->labels_full)) return rowdots_sharded(ctx, x_array, lut, out);
   out.assign((size_t)c.m, 0.0);
   if (c.nchunks == 0) return SDPSR_OK;
   {
@@ -766,7 +794,7 @@ extern "C" int sdpsr_project_round_refine(sdpsr_ctx* ctx, double atol, int64_t* 
     KeyTable& scratch = ctx->tab_scratch;   // reused across calls, freed with the context
     sp.mode = KM_RAW;
     sp.out_override = ctx->labels_tmp;
-    sp.table_override = &scratch;
+    sp.table_override = &scratch;      // (rank-local full-range pass: X must be complete on every rank)
     int st = sdpsr_refine_pass(ctx, sp, nullptr);
     if (st == SDPSR_OK) {
       RefineSpec pr;
@@ -802,39 +830,67 @@ extern "C" int sdpsr_init_partition(sdpsr_ctx* ctx, const double* C, const doubl
   const unsigned nb = (unsigned)((ctx->n + 31) / 32);
   std::vector<double> coef;
 
+  // This rank's column block (all columns in a single-rank run): the elementwise steps and both refine
+  // passes touch nothing else.
+  const bool shard = sdpsr_shard_active(ctx);
+  int64_t col0 = 0, col1 = ctx->n;
+  if (shard) {
+    col0 = ctx->n * ctx->rank / ctx->nranks;
+    col1 = ctx->n * (ctx->rank + 1) / ctx->nranks;
+  }
+  const uint64_t e0 = (uint64_t)col0 * (uint64_t)ctx->ld, e1 = (uint64_t)col1 * (uint64_t)ctx->ld;
+  const dim3 sgrid(nb, (unsigned)std::max<int64_t>(1, ((col1 + 31) / 32) - col0 / 32));
   // CL = symmetrize(round(C - proj(C)))                                   (:129-134)
   // C is read in place when it already lives on this device in the engine's own layout (ld == N);
-  // otherwise it is staged into X (the H2D upload of a host matrix, or the re-striding copy)
+  // otherwise it is staged into X (the H2D upload of a host matrix, or the re-striding copy).  With several
+  // ranks a HOST matrix is uploaded once in total: every rank copies its own column block over PCIe and the
+  // blocks are exchanged over NVLink.
   const double* Csrc = ctx->X;
   {
     cudaPointerAttributes pa;
     const bool on_device = cudaPointerGetAttributes(&pa, C) == cudaSuccess && pa.type == cudaMemoryTypeDevice &&
                            pa.device == ctx->device;
     cudaGetLastError();
+    int split = (!on_device && ctx->nranks > 1) ? 1 : 0;
+    if (ctx->nranks > 1) SDPSR_TRY(sdpsr_comm_agree_min(ctx, &split));     // a branch with a collective
     if (on_device && ctx->ld == ctx->n && ((uintptr_t)C % 16 == 0)) {
       Csrc = C;
     } else {
       if (ctx->ld != ctx->n) SDPSR_CUDA(cudaMemsetAsync(ctx->X, 0, ctx->elems * 8, ctx->stream));
       Timed tm(ctx, SDPSR_K_MISC, (double)ctx->elems * 16.0);              // staging copy (or the H2D upload)
-      SDPSR_CUDA(cudaMemcpy2DAsync(ctx->X, (size_t)ctx->ld * 8, C, (size_t)ctx->n * 8, (size_t)ctx->n * 8, (size_t)ctx->n,
-                                   cudaMemcpyDefault, ctx->stream));
+      if (split) {
+        const int64_t b0 = ctx->n * ctx->rank / ctx->nranks, b1 = ctx->n * (ctx->rank + 1) / ctx->nranks;
+        if (b1 > b0)
+          SDPSR_CUDA(cudaMemcpy2DAsync(ctx->X + b0 * ctx->ld, (size_t)ctx->ld * 8, C + b0 * ctx->n, (size_t)ctx->n * 8,
+                                       (size_t)ctx->n * 8, (size_t)(b1 - b0), cudaMemcpyDefault, ctx->stream));
+        size_t off[sdpsr_ctx::MAX_RANKS], len[sdpsr_ctx::MAX_RANKS];
+        for (int r = 0; r < ctx->nranks; ++r) {
+          const int64_t r0 = ctx->n * r / ctx->nranks, r1 = ctx->n * (r + 1) / ctx->nranks;
+          off[r] = (size_t)r0 * (size_t)ctx->ld * 8;
+          len[r] = (size_t)(r1 - r0) * (size_t)ctx->ld * 8;
+        }
+        SDPSR_TRY(sdpsr_comm_allgatherv(ctx, ctx->X, off, len));
+      } else {
+        SDPSR_CUDA(cudaMemcpy2DAsync(ctx->X, (size_t)ctx->ld * 8, C, (size_t)ctx->n * 8, (size_t)ctx->n * 8, (size_t)ctx->n,
+                                     cudaMemcpyDefault, ctx->stream));
+      }
     }
   }
   SDPSR_TRY(sdpsr_rowdots(ctx, Csrc, nullptr, coef));
   SDPSR_TRY(sdpsr_solve_gram(ctx, coef));
   SDPSR_TRY(sdpsr_upload_tpat(ctx, coef));
   {
-    Timed tm(ctx, SDPSR_K_MISC, (double)ctx->elems * (20.0 + 16.0));
-    init_elem_kernel<<<grid, 256, 0, ctx->stream>>>(0, Csrc, c.d_pid, c.d_tpat, ctx->X2, ctx->elems, pw, do_snap, atol, scale);
-    symmetrize_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(ctx->X2, ctx->X, ctx->n, ctx->ld);
-    count_launch(ctx, 2);
+    Timed tm(ctx, SDPSR_K_MISC, (double)(e1 - e0) * (24.0 + 8.0));
+    init_sym_kernel<<<sgrid, 256, 0, ctx->stream>>>(0, Csrc, c.d_pid, c.d_tpat, ctx->X2, ctx->n, ctx->ld, col0, col1, pw, do_snap,
+                                                    atol, scale);
+    count_launch(ctx);
   }
   SDPSR_CUDA(cudaGetLastError());
   SDPSR_TRY(sdpsr_partition_reset(ctx));
   {
     RefineSpec sp;                                                        // S = Part(CL)   (:145)
     sp.mode = KM_RAW;
-    sp.vals = ctx->X;
+    sp.vals = ctx->X2;
     sp.do_round = false;
     sp.ignore_labels = true;
     sp.keeps_symmetry = true;                                             // CL was symmetrised
@@ -845,17 +901,18 @@ extern "C" int sdpsr_init_partition(sdpsr_ctx* ctx, const double* C, const doubl
   SDPSR_TRY(sdpsr_solve_gram(ctx, coef));
   SDPSR_TRY(sdpsr_upload_tpat(ctx, coef));
   {
-    Timed tm(ctx, SDPSR_K_MISC, (double)ctx->elems * (12.0 + 16.0));
-    init_elem_kernel<<<grid, 256, 0, ctx->stream>>>(1, nullptr, c.d_pid, c.d_tpat, ctx->X2, ctx->elems, pw, do_snap, atol, scale);
-    symmetrize_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(ctx->X2, ctx->X, ctx->n, ctx->ld);
-    count_launch(ctx, 2);
+    Timed tm(ctx, SDPSR_K_MISC, (double)(e1 - e0) * (8.0 + 8.0));
+    init_sym_kernel<<<sgrid, 256, 0, ctx->stream>>>(1, nullptr, c.d_pid, c.d_tpat, ctx->X, ctx->n, ctx->ld, col0, col1, pw, do_snap,
+                                                    atol, scale);
+    count_launch(ctx);
   }
-  SDPSR_TRY(sdpsr_rowdots(ctx, ctx->X, nullptr, coef));
+  SDPSR_TRY(sdpsr_rowdots(ctx, ctx->X, nullptr, coef, /*x_own_block=*/true));
   SDPSR_TRY(sdpsr_solve_gram(ctx, coef));
   SDPSR_TRY(sdpsr_upload_tpat(ctx, coef));
-  {
-    Timed tm(ctx, SDPSR_K_MISC, (double)ctx->elems * 20.0);
-    init_elem_kernel<<<grid, 256, 0, ctx->stream>>>(2, nullptr, c.d_pid, c.d_tpat, ctx->X2, ctx->elems, pw, do_snap, atol, scale);
+  if (e1 > e0) {
+    Timed tm(ctx, SDPSR_K_MISC, (double)(e1 - e0) * 20.0);
+    const int g2 = (int)std::min<uint64_t>((e1 - e0 + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    init_elem_kernel<<<g2, 256, 0, ctx->stream>>>(2, nullptr, c.d_pid + e0, c.d_tpat, ctx->X2 + e0, e1 - e0, pw, do_snap, atol, scale);
     count_launch(ctx);
   }
   SDPSR_CUDA(cudaGetLastError());

@@ -659,11 +659,6 @@ __global__ void __launch_bounds__(256) fill_kernel(const uint32_t* __restrict__ 
   }
 }
 
-__global__ void relabel_ids_kernel(uint32_t* __restrict__ ids, const uint32_t* __restrict__ rank, uint64_t total) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
-    ids[i] = rank[ids[i]];
-}
-
 // canonical labels, unpadded: out[i + n*j] = rank[labels[i + ld*j]]
 __global__ void canonical_kernel(const uint32_t* __restrict__ labels, const uint32_t* __restrict__ rank,
                                  uint32_t* __restrict__ out, int64_t n, int64_t ld) {
@@ -783,7 +778,7 @@ int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
   // Sharded partition (shard.cu): the pass runs over this rank's column block only and is followed by the
   // key-table merge.  Passes with an output / table override (pattern ids, the id pass of the two-step
   // refine) are rank-local full-range passes.
-  const bool sharded = sdpsr_shard_active(ctx) && !spec.out_override && !spec.table_override;
+  const bool sharded = sdpsr_shard_active(ctx) && ((!spec.out_override && !spec.table_override) || spec.shard_block);
   uint64_t rb = 0, re = ctx->elems;
   if (sharded) sdpsr_shard_block(ctx, ctx->rank, &rb, &re);
   else if (sdpsr_shard_active(ctx) && !spec.ignore_labels) SDPSR_TRY(sdpsr_shard_ensure_full_labels(ctx));
@@ -872,9 +867,11 @@ int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
   }
   if (sharded) {
     int64_t dg = 0;
-    SDPSR_TRY(sdpsr_shard_merge(ctx, tnew, ctx->labels_alt, &dg));
-    ctx->labels_full = false;
-    ctx->clabels_valid = false;
+    SDPSR_TRY(sdpsr_shard_merge(ctx, tnew, spec.out_override ? spec.out_override : ctx->labels_alt, &dg));
+    if (!spec.out_override) {
+      ctx->labels_full = false;
+      ctx->clabels_valid = false;
+    }
   } else {
     SDPSR_TRY(sdpsr_rank_table(ctx, tnew));
   }
@@ -943,10 +940,9 @@ int sdpsr_generic_refine_values(sdpsr_ctx* ctx, const double* dvals, double atol
   sp.ignore_labels = true;
   sp.out_override = ctx->labels_tmp;
   sp.table_override = &scratch;
+  sp.shard_block = true;      // sharded run: ids of Part(M) on this rank's block, merged to canonical ids
   int64_t d2 = 0;
   int st = sdpsr_refine_pass(ctx, sp, &d2);
-  if (st == SDPSR_OK && sdpsr_shard_active(ctx))
-    st = sdpsr_relabel_by_rank(ctx, ctx->labels_tmp, scratch);   // ids that every rank agrees on
   if (st == SDPSR_OK) {
     RefineSpec pr;
     pr.mode = KM_PAIR;
@@ -956,15 +952,6 @@ int sdpsr_generic_refine_values(sdpsr_ctx* ctx, const double* dvals, double atol
     st = sdpsr_refine_pass(ctx, pr, dim);
   }
   return st;
-}
-
-// ids[i] = t.rank[ids[i]]: provisional slot ids (rank-dependent) -> canonical first-occurrence labels
-int sdpsr_relabel_by_rank(sdpsr_ctx* ctx, uint32_t* ids, KeyTable& t) {
-  const int grid = (int)std::min<uint64_t>((ctx->elems + 255) / 256, (uint64_t)ctx->sm_count * 16);
-  relabel_ids_kernel<<<grid, 256, 0, ctx->stream>>>(ids, t.rank, ctx->elems);
-  count_launch(ctx);
-  SDPSR_CUDA(cudaGetLastError());
-  return SDPSR_OK;
 }
 
 int sdpsr_upload_values(sdpsr_ctx* ctx, const double* values, int64_t len) {

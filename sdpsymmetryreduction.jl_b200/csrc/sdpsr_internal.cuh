@@ -121,6 +121,9 @@ struct sdpsr_ctx {
   int64_t dim = 0;
   uint64_t part_epoch = 0;          // bumped whenever the partition changes (derived state checks it)
 
+  // destination columns of the lower -> upper mirror after a symmetric product (sharded closure step: the
+  // refine pass that follows reads this rank's column block of X2 only); col1 < 0: all columns
+  int64_t mirror_col0 = 0, mirror_col1 = -1;
   int i8_pair = -1;     // INT8 square on CTA pairs (cta_group::2): -1 = for N > 16384, 0 / 1 = SDPSR_I8_PAIR
   int i8_segblocks = 0; // test hook (SDPSR_I8_SEGBLOCKS): K segment length of the INT8 square in 128-byte blocks
   int i8_slices = 0;    // int8 digits per entry of the INT8 square (gemm_i8.cu); 0 = 7 x 8-bit / 8 x 7-bit
@@ -260,6 +263,7 @@ struct RefineSpec {
   bool ignore_labels = false;       // treat the current labels as all-zero (fresh partition)
   bool keeps_symmetry = false;      // the refining values are symmetric by construction
   uint32_t* out_override = nullptr; // write provisional ids here instead of labels_alt (no swap)
+  bool shard_block = false;         // sharded run: a pass with overrides also runs on this rank's block + merge
   KeyTable* table_override = nullptr;
 };
 int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim);
@@ -268,7 +272,6 @@ int sdpsr_generic_refine_values(sdpsr_ctx* ctx, const double* dvals, double atol
 int sdpsr_table_alloc(sdpsr_ctx* ctx, KeyTable& t, size_t cap);
 void sdpsr_table_free(KeyTable& t);
 int sdpsr_rank_table(sdpsr_ctx* ctx, KeyTable& t);
-int sdpsr_relabel_by_rank(sdpsr_ctx* ctx, uint32_t* ids, KeyTable& t);
 int sdpsr_build_lut(sdpsr_ctx* ctx, const double* d_values, int64_t len);
 int sdpsr_materialize_fill(sdpsr_ctx* ctx, double* dst);
 int sdpsr_decode_lut(sdpsr_ctx* ctx, double atol);
@@ -292,7 +295,8 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int slices, int 
 // project.cu
 int sdpsr_constraints_finalize(sdpsr_ctx* ctx);
 void sdpsr_constraints_free(sdpsr_ctx* ctx);
-int sdpsr_rowdots(sdpsr_ctx* ctx, const double* x_array, const double* lut, std::vector<double>& out);
+int sdpsr_rowdots(sdpsr_ctx* ctx, const double* x_array, const double* lut, std::vector<double>& out,
+                  bool x_own_block = false);
 int sdpsr_solve_gram(sdpsr_ctx* ctx, std::vector<double>& rhs);
 int sdpsr_upload_tpat(sdpsr_ctx* ctx, const std::vector<double>& coef);
 int sdpsr_symmetric_check(sdpsr_ctx* ctx, int* is_sym);

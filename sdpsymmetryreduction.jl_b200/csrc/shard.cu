@@ -38,17 +38,24 @@ struct __align__(16) PackedKey {
   uint32_t pad;
 };
 
-// buf[i] = (key, first index) of the i-th occupied slot of the local table
+// buf[0] = (count, -) header, buf[1 + i] = (key, first index) of the i-th occupied slot of the local table (i < cap)
 __global__ void pack_kernel(const uint32_t* __restrict__ occ, const uint64_t* __restrict__ keys,
-                            const uint32_t* __restrict__ minidx, uint32_t count, PackedKey* __restrict__ buf) {
+                            const uint32_t* __restrict__ minidx, uint32_t count, uint32_t cap, PackedKey* __restrict__ buf) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
+  if (i == 0) {
+    PackedKey h;
+    h.key = count;
+    h.minidx = 0u;
+    h.pad = 0u;
+    buf[0] = h;
+  }
+  if (i >= count || i >= cap) return;
   const uint32_t s = occ[i];
   PackedKey p;
   p.key = keys[s];
   p.minidx = minidx[s];
   p.pad = 0u;
-  buf[i] = p;
+  buf[1 + i] = p;
 }
 
 // insert every gathered pair into the merge table: key -> min over the ranks of the first index
@@ -60,7 +67,7 @@ __global__ void merge_insert_kernel(const PackedKey* __restrict__ buf, const uin
   if (t >= (uint64_t)maxc * nranks) return;
   const uint32_t r = (uint32_t)(t / maxc), i = (uint32_t)(t % maxc);
   if (i >= counts[r]) return;
-  const PackedKey p = buf[t];
+  const PackedKey p = buf[(uint64_t)r * (maxc + 1) + 1 + i];       // (every rank's record starts with its header)
   uint32_t s = (uint32_t)(mix64s(p.key) >> 20) & mask;
   for (uint32_t probe = 0; probe <= mask; ++probe) {
     const unsigned long long old =
@@ -174,21 +181,38 @@ bool sdpsr_shard_active(const sdpsr_ctx* ctx) { return ctx->nranks > 1 && !(ctx-
 int sdpsr_shard_merge(sdpsr_ctx* ctx, KeyTable& tloc, uint32_t* lab, int64_t* dim) {
   const int G = ctx->nranks;
   Timed tm(ctx, SDPSR_K_RANK, 0.0);
-  // ---- C2: counts, then the packed (key, first index) pairs -------------------------------------
+  // ---- C2: the packed (count | key, first index ...) records of every rank, ONE all-gather -----------
+  // A record holds up to PK_CAP pairs (64 KB); only a pass that finds more classes than that on some rank
+  // pays a second, exactly sized exchange.
+  constexpr uint32_t PK_CAP = 4096;
   uint32_t* d_cnt = nullptr;
   SDPSR_TRY(sdpsr_scratch_t(ctx, 30, (size_t)sdpsr_ctx::MAX_RANKS, &d_cnt));
   uint32_t* h_cnt = reinterpret_cast<uint32_t*>(ctx->h_pinned) + 96;        // MAX_RANKS words
-  h_cnt[ctx->rank] = tloc.count;
-  SDPSR_CUDA(cudaMemcpyAsync(d_cnt + ctx->rank, h_cnt + ctx->rank, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  SDPSR_TRY(sdpsr_comm_allgather(ctx, d_cnt, sizeof(uint32_t)));
-  SDPSR_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(uint32_t) * (size_t)G, cudaMemcpyDeviceToHost, ctx->stream));
-  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
-  uint32_t maxc = 0;
-  uint64_t total = 0;
-  for (int r = 0; r < G; ++r) {
-    maxc = std::max(maxc, h_cnt[r]);
-    total += h_cnt[r];
+  PackedKey* h_hdr = reinterpret_cast<PackedKey*>(reinterpret_cast<unsigned char*>(ctx->h_pinned) + 2048);   // MAX_RANKS headers
+  PackedKey* buf = nullptr;
+  uint32_t maxc = PK_CAP;
+  for (int attempt = 0;; ++attempt) {
+    const size_t rec = (size_t)maxc + 1;
+    SDPSR_TRY(sdpsr_scratch_t(ctx, 31, rec * (size_t)G, &buf));
+    pack_kernel<<<(std::max<uint32_t>(1u, std::min(tloc.count, maxc)) + 255) / 256, 256, 0, ctx->stream>>>(
+        tloc.occ, tloc.keys, tloc.minidx, tloc.count, maxc, buf + rec * ctx->rank);
+    count_launch(ctx);
+    SDPSR_TRY(sdpsr_comm_allgather(ctx, buf, rec * sizeof(PackedKey)));
+    SDPSR_CUDA(cudaMemcpy2DAsync(h_hdr, sizeof(PackedKey), buf, rec * sizeof(PackedKey), sizeof(PackedKey), (size_t)G,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint32_t need = 0;
+    for (int r = 0; r < G; ++r) {
+      h_cnt[r] = (uint32_t)h_hdr[r].key;
+      need = std::max(need, h_cnt[r]);
+    }
+    if (need <= maxc) break;
+    SDPSR_REQUIRE(attempt == 0, SDPSR_E_CUDA, "internal: key-table exchange did not converge");
+    maxc = need;                                   // identical on every rank: all retry together
   }
+  uint64_t total = 0;
+  for (int r = 0; r < G; ++r) total += h_cnt[r];
+  SDPSR_CUDA(cudaMemcpyAsync(d_cnt, h_cnt, sizeof(uint32_t) * (size_t)G, cudaMemcpyHostToDevice, ctx->stream));
   KeyTable& tm_ = ctx->tab_merge;
   if (total == 0) {       // the all-zero matrix: the empty partition
     SDPSR_CUDA(cudaMemsetAsync(tloc.meta, 0, 4 * sizeof(uint32_t), ctx->stream));
@@ -197,14 +221,6 @@ int sdpsr_shard_merge(sdpsr_ctx* ctx, KeyTable& tloc, uint32_t* lab, int64_t* di
     if (dim) *dim = 0;
     return SDPSR_OK;
   }
-  PackedKey* buf = nullptr;
-  SDPSR_TRY(sdpsr_scratch_t(ctx, 31, (size_t)maxc * (size_t)G, &buf));
-  if (tloc.count) {
-    pack_kernel<<<(tloc.count + 255) / 256, 256, 0, ctx->stream>>>(tloc.occ, tloc.keys, tloc.minidx, tloc.count,
-                                                                    buf + (size_t)maxc * ctx->rank);
-    count_launch(ctx);
-  }
-  SDPSR_TRY(sdpsr_comm_allgather(ctx, buf, (size_t)maxc * sizeof(PackedKey)));
   // ---- identical merge on every rank ---------------------------------------------------------------
   const size_t mcap = std::max<size_t>(64, next_pow2(2 * total));
   SDPSR_TRY(sdpsr_table_alloc(ctx, tm_, mcap));
@@ -237,7 +253,7 @@ int sdpsr_shard_merge(sdpsr_ctx* ctx, KeyTable& tloc, uint32_t* lab, int64_t* di
   // ---- tloc becomes the identity table of the merged partition -------------------------------------
   const uint32_t dimg = tm_.count;
   const size_t need = std::max<size_t>(tloc.cap, next_pow2(2 * (uint64_t)dimg));
-  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));           // l2g was built from tloc: done before it is rewritten
+  // (l2g was built from tloc by kernels earlier on this stream; a reallocation synchronises by itself)
   SDPSR_TRY(sdpsr_table_alloc(ctx, tloc, need));
   SDPSR_CUDA(cudaMemsetAsync(tloc.keys, 0xff, (size_t)tloc.cap * 12, ctx->stream));
   identity_table_kernel<<<(dimg + 255) / 256, 256, 0, ctx->stream>>>(tm_.occ, tm_.keys, tm_.minidx, tm_.rank, dimg, tloc.keys,
