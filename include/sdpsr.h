@@ -108,12 +108,16 @@ int sdpsr_device_count(int* count);
  * `qr(A')` (src/partitions.jl:124) in project_colspace! (src/utils.jl:62-66).
  *   dense: A is m x N^2 column-major (a Julia Matrix{Float64}), ld = m.
  *   csr  : row k holds entries rowptr[k]..rowptr[k+1]-1; this is the CSC storage of
- *          A' (N^2 x m), i.e. `SparseMatrixCSC(transpose(A))` in Julia.
+ *          A' (N^2 x m), i.e. `SparseMatrixCSC(transpose(A))` in Julia.  The arrays are uploaded as they
+ *          are and validated / re-indexed by one kernel (no host pass over the stored entries).
  *   csc  : the SparseMatrixCSC storage of A itself (colptr has N^2+1 entries).
  * index_base is 0 (C / numpy) or 1 (Julia).                                           */
 int sdpsr_set_constraints_dense(sdpsr_ctx* ctx, int64_t m, const double* A);
 int sdpsr_set_constraints_csr(sdpsr_ctx* ctx, int64_t m, const int64_t* rowptr,
                               const int64_t* colidx, const double* vals, int index_base);
+/* the same with 32-bit column indices (scipy.sparse's default index type): no widening copy on the host */
+int sdpsr_set_constraints_csr_i32(sdpsr_ctx* ctx, int64_t m, const int64_t* rowptr,
+                                  const int32_t* colidx, const double* vals, int index_base);
 int sdpsr_set_constraints_csc(sdpsr_ctx* ctx, int64_t m, const int64_t* colptr,
                               const int64_t* rowval, const double* nzval, int index_base);
 /* number of distinct non-empty constraint column patterns found */

@@ -53,6 +53,7 @@ _SIGNATURES = {
     "sdpsr_device_count": ([C.POINTER(C.c_int)], C.c_int),
     "sdpsr_set_constraints_dense": ([_p, _i64, _p], C.c_int),
     "sdpsr_set_constraints_csr": ([_p, _i64, _p, _p, _p, C.c_int], C.c_int),
+    "sdpsr_set_constraints_csr_i32": ([_p, _i64, _p, _p, _p, C.c_int], C.c_int),
     "sdpsr_set_constraints_csc": ([_p, _i64, _p, _p, _p, C.c_int], C.c_int),
     "sdpsr_constraint_patterns": ([_p, C.POINTER(_i64)], C.c_int),
     "sdpsr_constraint_rank": ([_p, C.POINTER(_i64)], C.c_int),
@@ -195,10 +196,15 @@ class Context:
             m = A.shape[0]
             assert A.shape[1] == self.n * self.n
             rp = np.ascontiguousarray(A.indptr, dtype=np.int64)
-            ci = np.ascontiguousarray(A.indices, dtype=np.int64)
             vv = _f64(A.data)
-            self._check(self.lib.sdpsr_set_constraints_csr(self._h, m, rp.ctypes.data, ci.ctypes.data,
-                                                           vv.ctypes.data, 0))
+            if A.indices.dtype == np.int32:          # scipy's default: passed as it is (no 8-byte copy of 46 M indices)
+                ci = np.ascontiguousarray(A.indices)
+                self._check(self.lib.sdpsr_set_constraints_csr_i32(self._h, m, rp.ctypes.data, ci.ctypes.data,
+                                                                   vv.ctypes.data, 0))
+            else:
+                ci = np.ascontiguousarray(A.indices, dtype=np.int64)
+                self._check(self.lib.sdpsr_set_constraints_csr(self._h, m, rp.ctypes.data, ci.ctypes.data,
+                                                               vv.ctypes.data, 0))
         else:
             A = np.asarray(A, dtype=np.float64)
             m = A.shape[0]

@@ -110,6 +110,65 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const uint32_t* __restrict_
   }
 }
 
+// CSR ingestion on the device: the caller's column indices (int32 / int64, 0- or 1-based, unpadded linear index)
+// become padded u32 indices; range, strict ascent inside a row and explicit zeros are flagged
+// (flags[0]: out of range, flags[1]: not ascending, flags[2]: explicit zero present).
+template <typename IT>
+__global__ void __launch_bounds__(256) csr_ingest_kernel(const IT* __restrict__ colin, const double* __restrict__ val,
+                                                         const uint32_t* __restrict__ chunk_row,
+                                                         const uint32_t* __restrict__ chunk_beg,
+                                                         const uint32_t* __restrict__ chunk_end,
+                                                         const int64_t* __restrict__ rowptr, int64_t base, int64_t n,
+                                                         int64_t ld, uint32_t* __restrict__ colout,
+                                                         uint32_t* __restrict__ flags) {
+  const uint32_t c = blockIdx.x;
+  const int64_t rstart = rowptr[chunk_row[c]];
+  for (uint32_t i = chunk_beg[c] + threadIdx.x; i < chunk_end[c]; i += blockDim.x) {
+    const int64_t idx = (int64_t)colin[i] - base;
+    if (idx < 0 || idx >= n * n) {
+      flags[0] = 1u;
+      colout[i] = 0u;
+      continue;
+    }
+    if ((int64_t)i > rstart && (int64_t)colin[i - 1] - base >= idx) flags[1] = 1u;
+    if (val[i] == 0.0) flags[2] = 1u;
+    colout[i] = (uint32_t)((idx % n) + ld * (idx / n));
+  }
+}
+
+// out[p * m + k] = A[k, rep[p]] (0 when the entry is not stored): binary search of the padded index in row k
+__global__ void pattern_rows_kernel(const uint32_t* __restrict__ col, const double* __restrict__ val,
+                                    const int64_t* __restrict__ rowptr, int64_t m, const uint32_t* __restrict__ rep,
+                                    int64_t npat, double* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npat * m) return;
+  const int64_t p = t / m, k = t % m;
+  const uint32_t want = rep[p];
+  int64_t lo = rowptr[k], hi = rowptr[k + 1];
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (col[mid] < want) lo = mid + 1;
+    else hi = mid;
+  }
+  out[t] = (lo < rowptr[k + 1] && col[lo] == want) ? val[lo] : 0.0;
+}
+
+// out[b * m + k] = first stored entry of row k whose padded index is >= bound[b]
+__global__ void row_bounds_kernel(const uint32_t* __restrict__ col, const int64_t* __restrict__ rowptr, int64_t m,
+                                  const unsigned long long* __restrict__ bound, int nb, int64_t* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)nb * m) return;
+  const int64_t b = t / m, k = t % m;
+  const unsigned long long want = bound[b];
+  int64_t lo = rowptr[k], hi = rowptr[k + 1];
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((unsigned long long)col[mid] < want) lo = mid + 1;
+    else hi = mid;
+  }
+  out[t] = lo;
+}
+
 __device__ __forceinline__ double snap_round(double c, double pw, int do_snap, double atol, double scale) {
   if (do_snap) c = __ddiv_rn(rint(__dmul_rn(c, pw)), pw);      // numpy.round(c, decimals)
   if (fabs(c) < atol) return 0.0;                                // _clamp_round!, src/utils.jl:34-53
@@ -430,14 +489,22 @@ static int rowdots_sharded_setup(sdpsr_ctx* ctx) {
   const int64_t n = ctx->n;
   c.sh_chunk_row.assign((size_t)G, {});
   std::vector<uint32_t> beg, end;
+  // first stored entry of every row at or behind each block boundary (padded linear index c0 * ld)
+  std::vector<unsigned long long> hb((size_t)G + 1);
+  for (int r = 0; r <= G; ++r) hb[(size_t)r] = (unsigned long long)(n * r / G) * (unsigned long long)ctx->ld;
+  unsigned long long* d_b = nullptr;
+  int64_t* d_o = nullptr;
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 0, (size_t)G + 1, &d_b));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 1, (size_t)(G + 1) * (size_t)c.m, &d_o));
+  SDPSR_CUDA(cudaMemcpyAsync(d_b, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  row_bounds_kernel<<<(unsigned)(((int64_t)(G + 1) * c.m + 255) / 256), 256, 0, ctx->stream>>>(c.d_col, c.d_rowptr, c.m, d_b, G + 1, d_o);
+  count_launch(ctx);
+  std::vector<int64_t> ho((size_t)(G + 1) * (size_t)c.m);
+  SDPSR_CUDA(cudaMemcpyAsync(ho.data(), d_o, ho.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int r = 0; r < G; ++r) {
-    const int64_t c0 = n * r / G, c1 = n * (r + 1) / G;          // columns of rank r
-    const int64_t lo = c0 * n, hi = c1 * n;                       // unpadded linear index range
     for (int64_t k = 0; k < c.m; ++k) {
-      const int64_t* b = c.h_col.data() + c.h_rowptr[k];
-      const int64_t* e = c.h_col.data() + c.h_rowptr[k + 1];
-      const int64_t e0 = std::lower_bound(b, e, lo) - c.h_col.data();
-      const int64_t e1 = std::lower_bound(b, e, hi) - c.h_col.data();
+      const int64_t e0 = ho[(size_t)r * (size_t)c.m + (size_t)k], e1 = ho[(size_t)(r + 1) * (size_t)c.m + (size_t)k];
       for (int64_t x = e0; x < e1; x += CHUNK) {
         c.sh_chunk_row[(size_t)r].push_back((uint32_t)k);
         if (r == ctx->rank) {
@@ -506,26 +573,13 @@ int sdpsr_rowdots(sdpsr_ctx* ctx, const double* x_array, const double* lut, std:
   return SDPSR_OK;
 }
 
-// Build everything derived from the host CSR copy in ctx->cons (h_rowptr / h_col / h_val).
-int sdpsr_constraints_finalize(sdpsr_ctx* ctx) {
+// Reduction chunks of the CSR rows (host rowptr only) + the device buffers of the constraint set.
+static int constraints_layout(sdpsr_ctx* ctx, std::vector<uint32_t>& cbeg, std::vector<uint32_t>& cend) {
   ConstraintSet& c = ctx->cons;
-  const int64_t m = c.m, n = ctx->n, ld = ctx->ld;
+  const int64_t m = c.m;
   const int64_t nnz = c.h_rowptr[m];
   c.nnz = nnz;
   SDPSR_REQUIRE(nnz < 0xffffffffll, SDPSR_E_UNSUPPORTED, "more than 2^32-1 stored constraint entries");
-  // ---- device CSR with padded column indices, reduction chunks ----------------------
-  std::vector<uint32_t> col((size_t)nnz);
-  for (int64_t k = 0; k < m; ++k) {
-    int64_t prev = -1;
-    for (int64_t e = c.h_rowptr[k]; e < c.h_rowptr[k + 1]; ++e) {
-      const int64_t idx = c.h_col[e];
-      SDPSR_REQUIRE(idx >= 0 && idx < n * n, SDPSR_E_INVALID, "constraint column index out of range");
-      SDPSR_REQUIRE(idx > prev, SDPSR_E_INVALID, "constraint rows must have strictly increasing column indices");
-      prev = idx;
-      col[(size_t)e] = (uint32_t)((idx % n) + ld * (idx / n));
-    }
-  }
-  std::vector<uint32_t> cbeg, cend;
   c.chunk_row.clear();
   for (int64_t k = 0; k < m; ++k)
     for (int64_t e = c.h_rowptr[k]; e < c.h_rowptr[k + 1]; e += CHUNK) {
@@ -541,13 +595,91 @@ int sdpsr_constraints_finalize(sdpsr_ctx* ctx) {
   SDPSR_TRY(sdpsr_scratch_t(ctx, 11, 2 * ch_alloc, &c.d_chunk_beg));
   SDPSR_TRY(sdpsr_scratch_t(ctx, 12, ch_alloc, &c.d_partial));
   SDPSR_TRY(sdpsr_scratch_t(ctx, 13, ctx->elems, &c.d_pid));
-  if (nnz) {
-    SDPSR_CUDA(cudaMemcpyAsync(c.d_col, col.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
-    SDPSR_CUDA(cudaMemcpyAsync(c.d_val, c.h_val.data(), (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 39, (size_t)m + 1, &c.d_rowptr));
+  SDPSR_CUDA(cudaMemcpyAsync(c.d_rowptr, c.h_rowptr.data(), ((size_t)m + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (c.nchunks) {
     SDPSR_CUDA(cudaMemcpyAsync(c.d_chunk_row, c.chunk_row.data(), (size_t)c.nchunks * 4, cudaMemcpyHostToDevice, ctx->stream));
     SDPSR_CUDA(cudaMemcpyAsync(c.d_chunk_beg, cbeg.data(), (size_t)c.nchunks * 4, cudaMemcpyHostToDevice, ctx->stream));
     SDPSR_CUDA(cudaMemcpyAsync(c.d_chunk_beg + c.nchunks, cend.data(), (size_t)c.nchunks * 4, cudaMemcpyHostToDevice, ctx->stream));
   }
+  return SDPSR_OK;
+}
+
+// Host ingestion (dense / CSC input, or a CSR with explicit zeros): h_rowptr is set, hcol holds unpadded linear
+// indices.  Validates, pads and uploads.
+static int constraints_from_host(sdpsr_ctx* ctx, const std::vector<int64_t>& hcol, const std::vector<double>& hval) {
+  ConstraintSet& c = ctx->cons;
+  const int64_t m = c.m, n = ctx->n, ld = ctx->ld;
+  std::vector<uint32_t> cbeg, cend;
+  SDPSR_TRY(constraints_layout(ctx, cbeg, cend));
+  const int64_t nnz = c.nnz;
+  std::vector<uint32_t> col((size_t)nnz);
+  for (int64_t k = 0; k < m; ++k) {
+    int64_t prev = -1;
+    for (int64_t e = c.h_rowptr[k]; e < c.h_rowptr[k + 1]; ++e) {
+      const int64_t idx = hcol[(size_t)e];
+      SDPSR_REQUIRE(idx >= 0 && idx < n * n, SDPSR_E_INVALID, "constraint column index out of range");
+      SDPSR_REQUIRE(idx > prev, SDPSR_E_INVALID, "constraint rows must have strictly increasing column indices");
+      prev = idx;
+      col[(size_t)e] = (uint32_t)((idx % n) + ld * (idx / n));
+    }
+  }
+  if (nnz) {
+    SDPSR_CUDA(cudaMemcpyAsync(c.d_col, col.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SDPSR_CUDA(cudaMemcpyAsync(c.d_val, hval.data(), (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));   // the host vectors die with the caller
+  return sdpsr_constraints_finalize(ctx);
+}
+
+// Device ingestion of a caller-owned CSR (the large-problem path: 46 M stored entries for K(20,5)): the raw
+// arrays are uploaded as they are and converted by one kernel; no host copy, no host pass over the non-zeros.
+// *fallback = 1 when the matrix holds explicit zeros (the host path filters them).
+template <typename IT>
+static int constraints_from_csr(sdpsr_ctx* ctx, const int64_t* rowptr, const IT* colidx, const double* vals, int index_base,
+                                int* fallback) {
+  ConstraintSet& c = ctx->cons;
+  const int64_t m = c.m;
+  *fallback = 0;
+  c.h_rowptr.assign((size_t)m + 1, 0);
+  for (int64_t k = 0; k < m; ++k) {
+    SDPSR_REQUIRE(rowptr[k + 1] >= rowptr[k], SDPSR_E_INVALID, "rowptr must be non-decreasing");
+    c.h_rowptr[(size_t)k + 1] = rowptr[k + 1] - rowptr[0];
+  }
+  std::vector<uint32_t> cbeg, cend;
+  SDPSR_TRY(constraints_layout(ctx, cbeg, cend));
+  const int64_t nnz = c.nnz;
+  if (nnz) {
+    IT* raw = nullptr;
+    SDPSR_TRY(sdpsr_scratch_t(ctx, 40, (size_t)nnz, &raw));
+    uint32_t* flags = ctx->d_scalars + 12;
+    SDPSR_CUDA(cudaMemsetAsync(flags, 0, 3 * sizeof(uint32_t), ctx->stream));
+    SDPSR_CUDA(cudaMemcpyAsync(raw, colidx, (size_t)nnz * sizeof(IT), cudaMemcpyDefault, ctx->stream));
+    SDPSR_CUDA(cudaMemcpyAsync(c.d_val, vals, (size_t)nnz * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    csr_ingest_kernel<IT><<<(unsigned)c.nchunks, 256, 0, ctx->stream>>>(raw, c.d_val, c.d_chunk_row, c.d_chunk_beg,
+                                                                        c.d_chunk_beg + c.nchunks, c.d_rowptr, index_base,
+                                                                        ctx->n, ctx->ld, c.d_col, flags);
+    count_launch(ctx);
+    SDPSR_CUDA(cudaGetLastError());
+    uint32_t* hf = reinterpret_cast<uint32_t*>(ctx->h_pinned) + 112;
+    SDPSR_CUDA(cudaMemcpyAsync(hf, flags, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+    SDPSR_REQUIRE(hf[0] == 0u, SDPSR_E_INVALID, "constraint column index out of range");
+    SDPSR_REQUIRE(hf[1] == 0u, SDPSR_E_INVALID, "constraint rows must have strictly increasing column indices");
+    if (hf[2]) {
+      *fallback = 1;
+      return SDPSR_OK;
+    }
+  }
+  return sdpsr_constraints_finalize(ctx);
+}
+
+// Everything derived from the device CSR (d_col / d_val / d_rowptr + the chunk lists): pattern ids, the pattern
+// table, the Gram factorisation.
+int sdpsr_constraints_finalize(sdpsr_ctx* ctx) {
+  ConstraintSet& c = ctx->cons;
+  const int64_t m = c.m, n = ctx->n, ld = ctx->ld;
+  const int64_t nnz = c.nnz;
   // ---- pattern ids: hash every column, first-occurrence rank of the hashes ------------
   unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->X2);
   SDPSR_CUDA(cudaMemsetAsync(h, 0, ctx->elems * 8, ctx->stream));
@@ -595,29 +727,36 @@ int sdpsr_constraints_finalize(sdpsr_ctx* ctx) {
   std::vector<unsigned long long> cnt((size_t)npat + 1);
   SDPSR_CUDA(cudaMemcpyAsync(cnt.data(), dcnt, cnt.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
   SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
-  std::vector<int64_t> rep((size_t)npat + 1, -1);
+  std::vector<uint32_t> rep((size_t)npat + 1, 0xffffffffu);      // padded linear index of the representative
   for (int64_t i = 0; i < npat; ++i) {
     const uint32_t slot = occ[(size_t)i];
-    const uint32_t r = rk[(size_t)slot + 1];
-    const uint32_t pidx = allmin[slot];
-    rep[r] = (int64_t)(pidx % ld) + n * (int64_t)(pidx / ld);
+    rep[rk[(size_t)slot + 1]] = allmin[slot];
   }
   c.pat_cnt.assign(cnt.begin(), cnt.end());
-  // ---- pattern table: column of A at each representative entry -------------------------
+  // ---- pattern table: column of A at each representative entry (binary searches on the device) ----------
   c.pat_ptr.assign((size_t)npat + 2, 0);
   c.pat_row.clear();
   c.pat_val.clear();
+  std::vector<double> prow((size_t)npat * (size_t)m);
+  if (npat) {
+    uint32_t* d_rep = nullptr;
+    double* d_prow = nullptr;
+    SDPSR_TRY(sdpsr_scratch_t(ctx, 1, (size_t)npat, &d_rep));
+    SDPSR_TRY(sdpsr_scratch_t(ctx, 2, (size_t)npat * (size_t)m, &d_prow));
+    for (int64_t p = 1; p <= npat; ++p) SDPSR_REQUIRE(rep[(size_t)p] != 0xffffffffu, SDPSR_E_CUDA, "internal: pattern without representative");
+    SDPSR_CUDA(cudaMemcpyAsync(d_rep, rep.data() + 1, (size_t)npat * 4, cudaMemcpyHostToDevice, ctx->stream));
+    pattern_rows_kernel<<<(unsigned)((npat * m + 255) / 256), 256, 0, ctx->stream>>>(c.d_col, c.d_val, c.d_rowptr, m, d_rep, npat, d_prow);
+    count_launch(ctx);
+    SDPSR_CUDA(cudaMemcpyAsync(prow.data(), d_prow, prow.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   for (int64_t p = 1; p <= npat; ++p) {
     c.pat_ptr[(size_t)p] = (int64_t)c.pat_row.size();
-    const int64_t idx = rep[(size_t)p];
-    SDPSR_REQUIRE(idx >= 0, SDPSR_E_CUDA, "internal: pattern without representative");
     for (int64_t k = 0; k < m; ++k) {
-      const int64_t* b = c.h_col.data() + c.h_rowptr[k];
-      const int64_t* e = c.h_col.data() + c.h_rowptr[k + 1];
-      const int64_t* it = std::lower_bound(b, e, idx);
-      if (it != e && *it == idx) {
+      const double v = prow[(size_t)(p - 1) * (size_t)m + (size_t)k];
+      if (v != 0.0) {
         c.pat_row.push_back((int32_t)k);
-        c.pat_val.push_back(c.h_val[(size_t)(it - c.h_col.data())]);
+        c.pat_val.push_back(v);
       }
     }
   }
@@ -658,27 +797,46 @@ static int finish(sdpsr_ctx* ctx) {
   return SDPSR_OK;
 }
 
-extern "C" int sdpsr_set_constraints_csr(sdpsr_ctx* ctx, int64_t m, const int64_t* rowptr, const int64_t* colidx,
-                                         const double* vals, int index_base) {
-  CTX_ENTER();
+template <typename IT>
+static int set_constraints_csr_impl(sdpsr_ctx* ctx, int64_t m, const int64_t* rowptr, const IT* colidx, const double* vals,
+                                    int index_base) {
   SDPSR_REQUIRE(m >= 1 && rowptr && (index_base == 0 || index_base == 1), SDPSR_E_INVALID, "bad CSR arguments");
   sdpsr_constraints_free(ctx);
   ConstraintSet& c = ctx->cons;
   c.m = m;
-  c.h_rowptr.assign((size_t)m + 1, 0);
   const int64_t nnz_in = rowptr[m] - rowptr[0];
   SDPSR_REQUIRE(nnz_in >= 0 && (nnz_in == 0 || (colidx && vals)), SDPSR_E_INVALID, "bad CSR arguments");
-  c.h_col.reserve((size_t)nnz_in);
-  c.h_val.reserve((size_t)nnz_in);
+  int fallback = 0;
+  SDPSR_TRY(constraints_from_csr<IT>(ctx, rowptr, colidx + rowptr[0], vals + rowptr[0], index_base, &fallback));
+  if (!fallback) return SDPSR_OK;
+  // explicit zeros carry no constraint: filter them on the host
+  c.h_rowptr.assign((size_t)m + 1, 0);
+  std::vector<int64_t> hcol;
+  std::vector<double> hval;
+  hcol.reserve((size_t)nnz_in);
+  hval.reserve((size_t)nnz_in);
   for (int64_t k = 0; k < m; ++k) {
-    for (int64_t e = rowptr[k] - rowptr[0]; e < rowptr[k + 1] - rowptr[0]; ++e) {
-      if (vals[e] == 0.0) continue;   // explicit zeros carry no constraint
-      c.h_col.push_back(colidx[e] - index_base);
-      c.h_val.push_back(vals[e]);
+    for (int64_t e = rowptr[k]; e < rowptr[k + 1]; ++e) {
+      if (vals[e] == 0.0) continue;
+      hcol.push_back((int64_t)colidx[e] - index_base);
+      hval.push_back(vals[e]);
     }
-    c.h_rowptr[(size_t)k + 1] = (int64_t)c.h_col.size();
+    c.h_rowptr[(size_t)k + 1] = (int64_t)hcol.size();
   }
-  SDPSR_TRY(sdpsr_constraints_finalize(ctx));
+  return constraints_from_host(ctx, hcol, hval);
+}
+
+extern "C" int sdpsr_set_constraints_csr(sdpsr_ctx* ctx, int64_t m, const int64_t* rowptr, const int64_t* colidx,
+                                         const double* vals, int index_base) {
+  CTX_ENTER();
+  SDPSR_TRY(set_constraints_csr_impl<int64_t>(ctx, m, rowptr, colidx, vals, index_base));
+  return finish(ctx);
+}
+
+extern "C" int sdpsr_set_constraints_csr_i32(sdpsr_ctx* ctx, int64_t m, const int64_t* rowptr, const int32_t* colidx,
+                                             const double* vals, int index_base) {
+  CTX_ENTER();
+  SDPSR_TRY(set_constraints_csr_impl<int32_t>(ctx, m, rowptr, colidx, vals, index_base));
   return finish(ctx);
 }
 
@@ -695,18 +853,18 @@ extern "C" int sdpsr_set_constraints_dense(sdpsr_ctx* ctx, int64_t m, const doub
       if (A[k + m * idx] != 0.0) ++cntk[(size_t)k];
   c.h_rowptr.assign((size_t)m + 1, 0);
   for (int64_t k = 0; k < m; ++k) c.h_rowptr[(size_t)k + 1] = c.h_rowptr[(size_t)k] + cntk[(size_t)k];
-  c.h_col.resize((size_t)c.h_rowptr[m]);
-  c.h_val.resize((size_t)c.h_rowptr[m]);
+  std::vector<int64_t> hcol((size_t)c.h_rowptr[m]);
+  std::vector<double> hval((size_t)c.h_rowptr[m]);
   std::vector<int64_t> pos(c.h_rowptr.begin(), c.h_rowptr.end() - 1);
   for (int64_t idx = 0; idx < nn; ++idx)
     for (int64_t k = 0; k < m; ++k) {
       const double v = A[k + m * idx];
       if (v != 0.0) {
-        c.h_col[(size_t)pos[k]] = idx;
-        c.h_val[(size_t)pos[k]++] = v;
+        hcol[(size_t)pos[k]] = idx;
+        hval[(size_t)pos[k]++] = v;
       }
     }
-  SDPSR_TRY(sdpsr_constraints_finalize(ctx));
+  SDPSR_TRY(constraints_from_host(ctx, hcol, hval));
   return finish(ctx);
 }
 
@@ -727,17 +885,17 @@ extern "C" int sdpsr_set_constraints_csc(sdpsr_ctx* ctx, int64_t m, const int64_
   }
   c.h_rowptr.assign((size_t)m + 1, 0);
   for (int64_t k = 0; k < m; ++k) c.h_rowptr[(size_t)k + 1] = c.h_rowptr[(size_t)k] + cntk[(size_t)k];
-  c.h_col.resize((size_t)c.h_rowptr[m]);
-  c.h_val.resize((size_t)c.h_rowptr[m]);
+  std::vector<int64_t> hcol((size_t)c.h_rowptr[m]);
+  std::vector<double> hval((size_t)c.h_rowptr[m]);
   std::vector<int64_t> pos(c.h_rowptr.begin(), c.h_rowptr.end() - 1);
   for (int64_t idx = 0; idx < nn; ++idx)
     for (int64_t e = colptr[idx] - off; e < colptr[idx + 1] - off; ++e) {
       if (nzval[e] == 0.0) continue;
       const int64_t k = rowval[e] - index_base;
-      c.h_col[(size_t)pos[k]] = idx;
-      c.h_val[(size_t)pos[k]++] = nzval[e];
+      hcol[(size_t)pos[k]] = idx;
+      hval[(size_t)pos[k]++] = nzval[e];
     }
-  SDPSR_TRY(sdpsr_constraints_finalize(ctx));
+  SDPSR_TRY(constraints_from_host(ctx, hcol, hval));
   return finish(ctx);
 }
 

@@ -80,10 +80,8 @@ struct ConstraintSet {
   double* d_tpat = nullptr;      // [npat+1]
   int pid_sym = -1;              // pattern ids transpose-invariant? (checked once; decides whether the
                                  // projection keeps a symmetric partition symmetric)
-  // host CSR copy (needed to read pattern columns)
-  std::vector<int64_t> h_rowptr;
-  std::vector<int64_t> h_col;    // unpadded linear index
-  std::vector<double> h_val;
+  std::vector<int64_t> h_rowptr; // host copy of the row pointers (the stored entries live on the device only)
+  int64_t* d_rowptr = nullptr;   // [m + 1]
   bool ready = false;
 };
 
