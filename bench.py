@@ -180,25 +180,27 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------
 # the job
 # ----------------------------------------------------------------------------------
-def job_resident(S, ctx, prob, C_dev, seed, eig="auto"):
-    """Whole job with C already in HBM and the partition left on the device."""
+def job_resident(S, ctx, prob, C_dev, seed, eig="auto", A_dev=None):
+    """Whole job with the inputs (C and the stored entries of A) already in HBM and the partition left on the
+    device."""
     rand = Coeffs(seed)
     tr = {}
-    P = S.admissible_subspace(C_dev, prob.A, prob.b, rand=rand, ctx=ctx, fetch_labels=False, trace=tr)
+    P = S.admissible_subspace(C_dev, A_dev if A_dev is not None else prob.A, prob.b, rand=rand, ctx=ctx,
+                              fetch_labels=False, trace=tr)
     bd = S.blockDiagonalize(P, False, rand=rand, eig=eig)
     tr["eig_mode"] = P._eig_mode
     return P, bd, tr
 
 
-def job_e2e(S, prob, C_pinned, labels_pinned, seed, ctx=None, eig="auto", fetch=True):
+def job_e2e(S, prob, C_pinned, labels_pinned, seed, ctx=None, eig="auto", fetch=True, A_pin=None):
     """The public API with host buffers: the call a user makes.  With several GPUs the caller
     owns a context that carries the communicator and passes it in; the host matrix C is then uploaded ONCE in
     total (every rank copies its own column block, the blocks travel over NVLink) and the label matrix is
     fetched by rank 0 only (`fetch`), the rank that hands the result to the user."""
     rand = Coeffs(seed)
     # UInt16 labels: what the reference's admissible_subspace(C, A, b) returns (src/partitions.jl:84)
-    P = S.admissible_subspace(C_pinned, prob.A, prob.b, rand=rand, labels_out=labels_pinned, ctx=ctx,
-                              label_dtype=labels_pinned.dtype, fetch_labels=fetch)
+    P = S.admissible_subspace(C_pinned, A_pin if A_pin is not None else prob.A, prob.b, rand=rand,
+                              labels_out=labels_pinned, ctx=ctx, label_dtype=labels_pinned.dtype, fetch_labels=fetch)
     bd = S.blockDiagonalize(P, False, rand=rand, eig=eig)
     if ctx is None:
         P.release()
@@ -458,6 +460,15 @@ def main():
     labels_pinned_t = torch.empty(N * N, dtype=torch.int16).pin_memory()
     labels_pinned = labels_pinned_t.numpy().view(np.uint16).reshape(N, N, order="F")
     C_dev = C_pinned_t.cuda(non_blocking=False)
+    # the constraint matrix: stored entries resident in HBM for the `value` arm, in pinned host memory for e2e
+    Acsr = prob.A.tocsr()
+    Acsr.sort_indices()
+    a_idx_pin = torch.from_numpy(np.ascontiguousarray(Acsr.indices)).pin_memory()
+    a_val_pin = torch.from_numpy(np.ascontiguousarray(Acsr.data, dtype=np.float64)).pin_memory()
+    a_idx_dev, a_val_dev = a_idx_pin.cuda(), a_val_pin.cuda()
+    ib = a_idx_pin.element_size()
+    A_dev = B.DeviceCSR(Acsr.shape, Acsr.indptr, a_idx_dev.data_ptr(), a_val_dev.data_ptr(), ib, keep=(a_idx_dev, a_val_dev))
+    A_pin = B.DeviceCSR(Acsr.shape, Acsr.indptr, a_idx_pin.data_ptr(), a_val_pin.data_ptr(), ib, keep=(a_idx_pin, a_val_pin))
     torch.cuda.synchronize()
 
     ctx = B.Context(N, local, B.F_TIMING | int(os.environ.get("SDPSR_BENCH_FLAGS", "0")))
@@ -508,7 +519,7 @@ def main():
     clocks = ClockSampler(local)
     clocks.start()
     for w in range(args.warmup):
-        P, bd, tr = job_resident(S, ctx, prob, C_dev, SEED0 + 1000 + w, eig=args.eig)
+        P, bd, tr = job_resident(S, ctx, prob, C_dev, SEED0 + 1000 + w, eig=args.eig, A_dev=A_dev)
     barrier()
     ctx.timing_reset()
     l0 = ctx.launch_count()
@@ -518,7 +529,7 @@ def main():
     for k in range(args.steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
-        P, bd, tr = job_resident(S, ctx, prob, C_dev, SEED0 + k, eig=args.eig)
+        P, bd, tr = job_resident(S, ctx, prob, C_dev, SEED0 + k, eig=args.eig, A_dev=A_dev)
         b.record(stream)
         evs.append((a, b))
         modes.append(tr["eig_mode"])
@@ -536,14 +547,14 @@ def main():
     other, tim_dense = None, None
     if not args.no_extras and args.eig == "auto":
         ko = 2
-        job_resident(S, ctx, prob, C_dev, SEED0 + args.steps - 1, eig="syevd")
+        job_resident(S, ctx, prob, C_dev, SEED0 + args.steps - 1, eig="syevd", A_dev=A_dev)
         barrier()
         ctx.timing_reset()
         evo = []
         for _ in range(ko):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
-            P_o, bd_o, tr_o = job_resident(S, ctx, prob, C_dev, SEED0 + args.steps - 1, eig="syevd")
+            P_o, bd_o, tr_o = job_resident(S, ctx, prob, C_dev, SEED0 + args.steps - 1, eig="syevd", A_dev=A_dev)
             b.record(stream)
             evo.append((a, b))
         barrier()
@@ -562,11 +573,11 @@ def main():
         sweep = {}
         for sl in (6, 5, 4):
             ctx.set_square_slices(sl)
-            job_resident(S, ctx, prob, C_dev, SEED0, eig=args.eig)
+            job_resident(S, ctx, prob, C_dev, SEED0, eig=args.eig, A_dev=A_dev)
             barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
-            P_s, bd_s, _ = job_resident(S, ctx, prob, C_dev, SEED0, eig=args.eig)
+            P_s, bd_s, _ = job_resident(S, ctx, prob, C_dev, SEED0, eig=args.eig, A_dev=A_dev)
             b.record(stream)
             barrier()
             assert P_s.nparts == dim and [int(s) for s in bd_s.blkSizes] == sizes
@@ -577,13 +588,13 @@ def main():
     e2e_ctx = ctx if world > 1 else None
     fetch = rank == 0
     for _ in range(min(args.warmup, 1)):
-        job_e2e(S, prob, C_pinned, labels_pinned, SEED0 + 2000, ctx=e2e_ctx, eig=args.eig, fetch=fetch)
+        job_e2e(S, prob, C_pinned, labels_pinned, SEED0 + 2000, ctx=e2e_ctx, eig=args.eig, fetch=fetch, A_pin=A_pin)
     barrier()
     evs = []
     for k in range(args.steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
-        P_e, bd_e = job_e2e(S, prob, C_pinned, labels_pinned, SEED0 + k, ctx=e2e_ctx, eig=args.eig, fetch=fetch)
+        P_e, bd_e = job_e2e(S, prob, C_pinned, labels_pinned, SEED0 + k, ctx=e2e_ctx, eig=args.eig, fetch=fetch, A_pin=A_pin)
         b.record(stream)
         evs.append((a, b))
     barrier()
@@ -640,7 +651,7 @@ def main():
     # (per GPU: each rank computes 1/world of the tiles of every square)
     fp64_equiv = (2.0 * tiles_half * 128 * 128 * N * sq_launches / world / gi["ms"] / 1e9) if (gi["ms"] and tiles_half) else None
     ref_gbs = rf["work"] / rf["ms"] / 1e6 if rf["ms"] else None
-    h2d = N * N * 8 + world * int(prob.A.data.nbytes + prob.A.indices.astype(np.int64).nbytes + prob.A.indptr.nbytes)
+    h2d = N * N * 8 + world * int(a_val_pin.numel() * 8 + a_idx_pin.numel() * ib + (Acsr.shape[0] + 1) * 8)
     d2h = N * N * labels_pinned.dtype.itemsize + N * 8 + dim * len(sizes) * 8
     cfg.update({"dim": dim, "blocks": sizes if len(sizes) <= 16 else "%d x [1]" % len(sizes),
                 "iterations": iters_seen[-1], "eig": max(set(modes), key=modes.count),

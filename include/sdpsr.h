@@ -135,8 +135,9 @@ int sdpsr_partition_reset(sdpsr_ctx* ctx);
  * (src/partitions.jl:37-60).  labels: N x N integers of elt_bytes in {1,2,4,8}.     */
 int sdpsr_partition_set_labels(sdpsr_ctx* ctx, const void* labels, int elt_bytes,
                                int64_t* dim);
-/* P.matrix in canonical first-occurrence numbering.  SDPSR_E_LABEL_OVERFLOW when a
- * label does not fit elt_bytes (the reference's InexactError for UInt16).             */
+/* P.matrix in canonical first-occurrence numbering.  SDPSR_E_LABEL_OVERFLOW when dim(P) does not
+ * fit elt_bytes (InexactError in the reference; the reference may throw earlier, for an intermediate
+ * p1 + p2*(dim+1) of refine! that the engine never forms, src/partitions.jl:62-66).   */
 int sdpsr_partition_get_labels(sdpsr_ctx* ctx, void* labels, int elt_bytes);
 /* dim(P) (src/partitions.jl:13) */
 int sdpsr_partition_dim(sdpsr_ctx* ctx, int64_t* dim);

@@ -7,7 +7,7 @@ The compute lives in ``csrc/`` (hand-written sm_100a CUDA behind the C ABI of
 host-side mirror of the reference's Julia API for that path; it has no CPU
 fallback and raises ``LibraryNotBuilt`` when the shared library is missing.
 """
-from . import problems  # noqa: F401
+from . import compat, problems  # noqa: F401
 from .api import (  # noqa: F401
     DimensionMismatch,
     InvalidDecompositionField,

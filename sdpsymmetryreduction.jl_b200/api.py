@@ -223,8 +223,10 @@ def admissible_subspace(C, A, b, *, verbose: bool = False, atol: float = RTOL_DE
     ``init_elements=(CL, X0)`` lets a host that owns the reference's own ``qr`` and
     ``Krylov.craig`` (the Julia wrapper) supply the two initial elements
     (:129-142); otherwise they are computed on the device.  ``label_dtype=np.uint16``
-    reproduces the reference's default ``Partition{UInt16}`` including its overflow
-    error (:84).
+    returns the reference's default ``Partition{UInt16}`` and raises ``OverflowError`` (InexactError) when the
+    FINAL dim does not fit; the reference can also throw mid-loop, when an intermediate
+    ``p1 + p2*(dim(P1)+1)`` of ``refine!`` exceeds 65535 (:62-66) -- the engine has no such intermediate, so
+    runs that error there for that reason alone succeed here.
     """
     rand = rand or _default_rand()
     Cv = C

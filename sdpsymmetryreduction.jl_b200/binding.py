@@ -28,6 +28,18 @@ K_REFINE, K_GEMM, K_FILL, K_PROJECT, K_RANK, K_EIG, K_BASIS, K_MISC, K_KRYLOV, K
 K_NAMES = ["refine", "gemm", "fill", "project", "rank", "eig", "basis", "misc", "krylov", "gemm_i8"]
 
 
+class DeviceCSR:
+    """A constraint matrix A (m x N^2, CSR) whose column indices and values already live in device memory (or in
+    pinned host memory): `rowptr` is a host int64 array, `indices_ptr` / `data_ptr` are raw pointers to `nnz`
+    int32 or int64 indices and `nnz` doubles.  `keep` holds whatever owns that memory (e.g. torch tensors)."""
+
+    def __init__(self, shape, rowptr, indices_ptr: int, data_ptr: int, index_bytes: int, keep=None):
+        self.shape = tuple(shape)
+        self.rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+        self.indices_ptr, self.data_ptr, self.index_bytes, self.keep = int(indices_ptr), int(data_ptr), int(index_bytes), keep
+        assert index_bytes in (4, 8)
+
+
 class LibraryNotBuilt(RuntimeError):
     pass
 
@@ -189,7 +201,12 @@ class Context:
     def set_constraints(self, A):
         """A: (m, N^2) ndarray or scipy.sparse matrix (src/partitions.jl:112)."""
         import scipy.sparse as sp
-        if sp.issparse(A):
+        if isinstance(A, DeviceCSR):
+            m = A.shape[0]
+            assert A.shape[1] == self.n * self.n
+            fn = self.lib.sdpsr_set_constraints_csr_i32 if A.index_bytes == 4 else self.lib.sdpsr_set_constraints_csr
+            self._check(fn(self._h, m, A.rowptr.ctypes.data, A.indices_ptr, A.data_ptr, 0))
+        elif sp.issparse(A):
             A = A.tocsr()
             A.sum_duplicates()
             A.sort_indices()

@@ -16,9 +16,12 @@
 //   3. fold:   X2 = sum_c 2^(2e-12-bc) * P_c, added from the smallest weight up in FP64.
 //
 // The truncated terms (s+t >= S) are below 2^-bS relative, the level of dgemm's own rounding error, and
-// because the integer sums are exact the result does not depend on the summation order: two entries
-// whose products are the same multiset (= entries of one class of the coherent closure) get
-// bit-identical values, which a floating-point GEMM cannot guarantee.
+// because the integer sums are exact the result does not depend on the summation order WITHIN a K segment:
+// with a single segment (N <= 16384 with 8-bit digits, N <= 32768 with 7-bit digits) two entries whose
+// products are the same multiset (= entries of one class of the coherent closure) get bit-identical values,
+// which a floating-point GEMM cannot guarantee.  With several segments every segment is folded into C by a
+// rounded FP64 read-modify-write, so the value then depends on how the k terms fall into the segments (like
+// dgemm's blocking; still identical for entries whose terms are distributed alike).
 //
 // Kernel structure (one persistent CTA per SM, 128 x 256 output tiles of the lower triangle):
 //   warp 0   TMA producer: cp.async.bulk.tensor.3d (k, row, slice) into a ring of SWIZZLE_128B tiles

@@ -809,6 +809,12 @@ static int set_constraints_csr_impl(sdpsr_ctx* ctx, int64_t m, const int64_t* ro
   int fallback = 0;
   SDPSR_TRY(constraints_from_csr<IT>(ctx, rowptr, colidx + rowptr[0], vals + rowptr[0], index_base, &fallback));
   if (!fallback) return SDPSR_OK;
+  {
+    cudaPointerAttributes pa;
+    const bool on_device = cudaPointerGetAttributes(&pa, vals) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    SDPSR_REQUIRE(!on_device, SDPSR_E_INVALID, "a device-resident CSR must not hold explicit zeros");
+  }
   // explicit zeros carry no constraint: filter them on the host
   c.h_rowptr.assign((size_t)m + 1, 0);
   std::vector<int64_t> hcol;
