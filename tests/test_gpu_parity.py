@@ -123,6 +123,24 @@ def test_round_refine_other_tolerances(atol):
             assert np.array_equal(ctx.get_labels(), P.matrix)
 
 
+@pytest.mark.parametrize("flags", [0, B.F_TINY_TABLE], ids=["default", "tiny-table"])
+def test_round_refine_chain_with_many_classes(flags):
+    """dim > 4096: the per-CTA key cache is bypassed and the batched global-table probes of refine_fast_kernel
+    run (four probes of a thread issued together); labels stay bit-identical to the oracle."""
+    rng = np.random.default_rng(17)
+    n = 160
+    with B.Context(n, 0, flags) as ctx:
+        P = None
+        for step in range(4):
+            M = rng.integers(0, 3000, size=(n, n)) * 0.37 + 0.11
+            M[rng.random((n, n)) < 0.05] = 0.0
+            d = ctx.refine_values(M, ATOL, do_round=True)
+            P = oracle_refine_values(P, M, True)
+            assert d == P.nparts, (step, d, P.nparts)
+            assert np.array_equal(ctx.get_labels(), P.matrix), f"labels differ at step {step}"
+        assert P.nparts > 4096
+
+
 def test_negative_zero_and_raw_bits():
     M = np.array([[0.0, -0.0, 1.0], [1.0, 0.0, -0.0], [2.0, 2.0, 0.0]])
     want = O.partition_from_values(M)
