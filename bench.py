@@ -89,16 +89,21 @@ class Coeffs:
 
 
 def workload_config(name):
-    """The `config` keys both arms print (same_config)."""
+    """The `config` dict BOTH arms print, key for key (same_config): it names the workload only; what a run
+    observed (dim, blocks, iterations, path taken, parallelisation) goes under `run`."""
     fam, par = WORKLOADS[name]
     if fam == "hamming":
         d, q = par
-        return {"workload": name, "N": q ** d, "m": 2, "atol": ATOL}
-    if fam == "kneser":
+        n, m = q ** d, 2
+    elif fam == "kneser":
         from math import comb
-        return {"workload": name, "N": comb(*par), "m": 2, "atol": ATOL}
-    f, bits, m = par
-    return {"workload": name, "N": 1 << (f * bits), "m": m, "atol": ATOL}
+        n, m = comb(*par), 2
+    else:
+        f, bits, m = par
+        n = 1 << (f * bits)
+    return {"workload": name, "N": n, "m": m, "atol": ATOL,
+            "job": "admissible_subspace(C, A, b) + blockDiagonalize(P), a new coefficient seed every step",
+            "l2": "inputs larger than L2 (C and X are %.2f GB each)" % (n * n * 8 / 1e9)}
 
 
 def build_workload(name):
@@ -653,11 +658,11 @@ def main():
     ref_gbs = rf["work"] / rf["ms"] / 1e6 if rf["ms"] else None
     h2d = N * N * 8 + world * int(a_val_pin.numel() * 8 + a_idx_pin.numel() * ib + (Acsr.shape[0] + 1) * 8)
     d2h = N * N * labels_pinned.dtype.itemsize + N * 8 + dim * len(sizes) * 8
-    cfg.update({"dim": dim, "blocks": sizes if len(sizes) <= 16 else "%d x [1]" % len(sizes),
+    run = {}
+    run.update({"dim": dim, "blocks": sizes if len(sizes) <= 16 else "%d x [1]" % len(sizes),
                 "iterations": iters_seen[-1], "eig": max(set(modes), key=modes.count),
                 "eig_modes_per_step": {m: modes.count(m) for m in sorted(set(modes))},
                 "seeds": "default_rng(%d + step): a new coefficient draw every step" % SEED0,
-                "l2": "inputs larger than L2 (X is %.1f GB)" % (N * N * 8 / 1e9),
                 "parallelism": ("%d ranks: the partition is sharded by column blocks (per-rank refine passes + key-table "
                                 "merge, compact labels all-gathered once per square), GEMM tile-columns dealt "
                                 "round-robin with tiles exchanged from the epilogue over NVLink peer memory; e2e: C "
@@ -671,6 +676,7 @@ def main():
                       "s8 x s8 -> s32 products of its digit slices (54 magnitude bits by default) folded in f64, "
                       "an FP64-grade product (DESIGN.md 5b); every other product is f64 DMMA",
         "config": cfg,
+        "run": run,
         "parity": {"ok": bool(ok.item()), "checked": "labels+blocks ok" if bool(ok.item()) else "FAILED",
                    "labels": "canonical labels == closed-form partition (device compare, every rank; e2e host copy too)",
                    "blocks": "sizes, multiplicities, trace identities" + (", eigenmatrix columns" if eigmat is not None else ""),
