@@ -296,6 +296,11 @@ int sdpsr_comm_info(sdpsr_ctx* ctx, int* nranks, int* rank);
 int sdpsr_comm_local_group(void** group, int nranks);
 int sdpsr_comm_init_local(sdpsr_ctx* ctx, void* group, int rank);
 
+/* Test hook (host-only, needs no device): the tile deal of the sharded products exactly as the kernels use it.
+ * kind 0: FP64 GEMM (all 128 x 128 tiles), 1: FP64 GEMM lower triangle, 2: INT8 square (128 x 256 tiles),
+ * 3: INT8 square on CTA pairs (256 x 256).  out (may be NULL) receives *count (tm, tn) pairs.                  */
+int sdpsr_debug_tile_deal(int kind, int64_t n, int nranks, int rank, int32_t* out, int64_t cap, int64_t* count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,16 @@ class DeviceCSR:
         assert index_bytes in (4, 8)
 
 
+def tile_deal(kind: int, n: int, nranks: int, rank: int):
+    """The (tm, tn) tiles `rank` of `nranks` computes, straight from the library (host-only test hook)."""
+    lib = load_library()
+    cnt = _i64(0)
+    assert lib.sdpsr_debug_tile_deal(kind, n, nranks, rank, None, 0, C.byref(cnt)) == OK
+    out = np.zeros((max(cnt.value, 1), 2), dtype=np.int32)
+    assert lib.sdpsr_debug_tile_deal(kind, n, nranks, rank, out.ctypes.data, cnt.value, C.byref(cnt)) == OK
+    return [tuple(int(x) for x in row) for row in out[:cnt.value]]
+
+
 class LibraryNotBuilt(RuntimeError):
     pass
 
@@ -83,6 +93,7 @@ _SIGNATURES = {
     "sdpsr_square_round_refine": ([_p, C.c_double, C.POINTER(_i64)], C.c_int),
     "sdpsr_product_round_refine": ([_p, _p, _p, _i64, C.c_double, C.POINTER(_i64)], C.c_int),
     "sdpsr_eig": ([_p, _p, _i64, _p], C.c_int),
+    "sdpsr_debug_tile_deal": ([C.c_int, _i64, C.c_int, C.c_int, _p, _i64, C.POINTER(_i64)], C.c_int),
     "sdpsr_partition_constraints": ([_p, _p, _p, _i64, C.c_int], C.c_int),
     "sdpsr_block_norms": ([_p, _p, _i64, _p, _i64, _p], C.c_int),
     "sdpsr_irreducible": ([_p, _p, _i64, _p, _i64, _p, C.c_double, _p, C.POINTER(_i64)], C.c_int),

@@ -295,6 +295,31 @@ static void owned_tiles(int tiles_m, int tiles_n, bool lower, int nranks, int ra
     for (int tm = lower ? tn : 0; tm < tiles_m; ++tm) out.push_back(make_int2(tm, tn));
 }
 
+int sdpsr_tile_deal_i8(int64_t n, int nranks, int rank, int pair, std::vector<int2>& out);
+
+/* The tile deal of the sharded products as the kernels use it, for `rank` of `nranks` (host-only: works without a
+ * device).  kind 0: FP64 GEMM, all 128 x 128 tiles; 1: FP64 GEMM, lower triangle; 2: INT8 square (128 x 256 tiles);
+ * 3: INT8 square on CTA pairs (256 x 256 tiles).  out receives (tm, tn) pairs, *count their number.            */
+extern "C" int sdpsr_debug_tile_deal(int kind, int64_t n, int nranks, int rank, int32_t* out, int64_t cap, int64_t* count) {
+  if (n < 1 || nranks < 1 || rank < 0 || rank >= nranks || kind < 0 || kind > 3 || !count) return SDPSR_E_INVALID;
+  std::vector<int2> tiles;
+  if (kind <= 1) {
+    const int t = (int)((n + BM - 1) / BM);
+    owned_tiles(t, t, kind == 1, nranks, rank, tiles);
+  } else {
+    sdpsr_tile_deal_i8(n, nranks, rank, kind == 3, tiles);
+  }
+  *count = (int64_t)tiles.size();
+  if (out) {
+    if (cap < (int64_t)tiles.size()) return SDPSR_E_INVALID;
+    for (size_t i = 0; i < tiles.size(); ++i) {
+      out[2 * i] = tiles[i].x;
+      out[2 * i + 1] = tiles[i].y;
+    }
+  }
+  return SDPSR_OK;
+}
+
 int sdpsr_gemm_f64(sdpsr_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                    int64_t ldc, int64_t M, int64_t Nc, int64_t K, bool symmetric_out, bool shard, int accum) {
   SDPSR_REQUIRE(M > 0 && Nc > 0 && K > 0, SDPSR_E_INVALID, "empty GEMM");

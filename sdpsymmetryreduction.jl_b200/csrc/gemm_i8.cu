@@ -816,6 +816,14 @@ void launch_slices(const double* X, size_t elems, int8_t* slices, double scale, 
 }  // namespace
 
 
+// Host-only view of the tile deal (no device needed): what tests/test_sharding_gloo.py holds the Python model of
+// the deal against, so that a change here cannot go unnoticed.
+int sdpsr_tile_deal_i8(int64_t n, int nranks, int rank, int pair, std::vector<int2>& out) {
+  if (pair) build_tiles_2cta((int)n, nranks, rank, out);
+  else build_tiles((int)n, nranks, rank, out);
+  return 0;
+}
+
 // X2 = X * X for bit-for-bit symmetric X (checked by the caller).  *done = 0 when the values are out of
 // the range the slicing handles (Inf/NaN, extreme exponents, or -- unless force_range -- rows whose
 // largest entry is more than 2^8 below the global maximum): the caller then uses the DMMA path.

@@ -1,14 +1,11 @@
-"""Multi-GPU sharding of the path: pure host logic, mirrored by
-``owned_tiles`` in csrc/gemm_f64.cu and CPU-tested with gloo (tests/test_sharding_gloo.py).
+"""A host-side MODEL of the tile deal of the sharded products, used by the CPU tests only.
 
-Only the GEMMs shard (they are >98 % of the kernel time): the 128-column TILE-COLUMNS of a
-product C = A*B are dealt round-robin to the ranks (``tn % nranks == rank``).  For a symmetric
-product only tiles on or below the diagonal are computed; the round-robin deal balances the
-triangle.  Each owned tile-column is one contiguous slab of the column-major matrix, so the
-exchange is one grouped set of broadcasts, one per tile-column, rooted at its owner; the upper
-triangle is then mirrored locally.  The cheap streaming passes (fill, projection, refine) are
-replicated on every rank: they see bit-identical X / X^2, so every observable (dims, canonical
-labels, X) is identical on all ranks with no further communication.
+The deal itself is compiled into libsdpsr_cuda.so (``owned_tiles`` in csrc/gemm_f64.cu, ``build_tiles`` in
+csrc/gemm_i8.cu) and exported host-side as ``sdpsr_debug_tile_deal``; tests/test_sharding_gloo.py holds this model
+against it tile for tile, then proves coverage and balance on the model.  Tile-COLUMNS of a product are dealt
+round-robin to the ranks (``tn % nranks == rank``); for a symmetric product only tiles on or below the diagonal
+are computed and the round-robin deal balances the triangle.  Nothing in the product imports this module; the
+sharding of the partition itself (column blocks + key-table merge) lives in csrc/shard.cu.
 """
 from __future__ import annotations
 

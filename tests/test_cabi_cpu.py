@@ -66,6 +66,39 @@ def test_host_scalar_logic_matches_oracle():
     assert np.array_equal(api.eigen_clusters(v, 1e-3), O.eigen_clusters(v, 1e-3))
 
 
+def test_host_scalar_logic_known_answers():
+    """The same scalar steps against answers worked out by hand from the reference's definitions
+    (src/eigen_decomposition.jl:19-40 clusters, :83-139 log-histogram + Otsu, DataStructures' union by rank) -- the
+    comparison with the oracle above is between two restatements by the same author and proves little."""
+    from sdpsr_b200 import api
+    # clusters: a new eigenspace exactly where the gap exceeds atol
+    v = np.array([-1.0, -1.0 + 5e-9, 0.0, 1e-8, 2e-8 + 1e-12, 1.0])
+    assert api.eigen_clusters(v, 1e-8).tolist() == [0, 2, 4, 5, 6]
+    assert api.eigen_clusters(np.array([3.0]), 1e-8).tolist() == [0, 1]
+    # Otsu on a clearly bimodal set: 16 log-spaced bins between lo = atol and hi = 1; "noise" sits in the first
+    # bins, "signal" in the last ones -> the threshold is a bin edge strictly between the two groups
+    atol = 1e-8
+    X = np.array([1e-16, 3e-12, 2e-9, 5e-9, 0.2, 0.5, 0.9, 1.0])
+    thr = api.otsu_threshold(X, atol)
+    assert 5e-9 < thr < 0.2
+    edges = np.exp(np.linspace(np.log(atol), np.log(1.0), 17))
+    assert np.isclose(edges, thr).any()                       # an edge of the 16-bin log histogram (:94-101)
+    # all values in one bin: the variance is NaN everywhere but ... the first candidate wins (Julia's argmax on NaN)
+    assert api.otsu_threshold(np.array([0.5, 0.5, 0.5]), atol) == api.otsu_threshold(np.array([0.5, 0.5]), atol)
+    # union-find: union by rank, ties keep the FIRST argument's root; path compression must not change roots
+    K = api._DisjointSets(6)
+    K.union(1, 0)            # tie -> root 1
+    assert K.find(0) == 1
+    K.union(2, 3)            # tie -> root 2
+    K.union(3, 0)            # ranks equal (1, 1): roots are 2 and 1, tie -> first argument's root = 2
+    assert [K.find(i) for i in range(6)] == [2, 2, 2, 2, 4, 5]
+    K.union(4, 2)            # rank 0 vs rank 2 -> the deeper tree's root 2 survives
+    assert K.find(4) == 2
+    # the consistency rule (:163-167): a class whose root is not its smallest member is rejected
+    norms = np.array([[1.0, 0.0, 1.0], [0.0, 1.0, 0.0], [1.0, 0.0, 1.0]])
+    assert api._isomorphism_classes(norms, 1e-8).tolist() == [0, 1, 0]
+
+
 def test_problem_generators():
     p = S.problems.lovasz_er(3)
     assert p.n == 13 and p.A.shape == (2, 169) and p.A[0].sum() == 13 * 4 - 4   # 4 absolute points

@@ -10,7 +10,29 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+from sdpsr_b200 import binding as B
 from sdpsr_b200 import sharding as sh
+
+
+@pytest.mark.parametrize("n", [1, 100, 257, 4096, 15504, 16384, 32768])
+@pytest.mark.parametrize("nranks", [1, 2, 3, 8])
+def test_python_model_equals_the_library_deal(n, nranks):
+    """sharding.py is only a MODEL; the deal the kernels use is compiled into libsdpsr_cuda.so and exported
+    host-side (sdpsr_debug_tile_deal).  Both must agree tile for tile, in order -- so the coverage / balance
+    properties asserted on the model below are properties of the product code."""
+    t = sh.num_tiles(n)
+    for r in range(nranks):
+        assert B.tile_deal(0, n, nranks, r) == sh.owned_tiles(t, t, False, nranks, r)
+        assert B.tile_deal(1, n, nranks, r) == sh.owned_tiles(t, t, True, nranks, r)
+        assert B.tile_deal(2, n, nranks, r) == sh.owned_tiles_i8(n, nranks, r)
+    # CTA-pair deal (256 x 256 tiles): every lower-triangle tile exactly once
+    t2 = -(-n // 256)
+    seen = set()
+    for r in range(nranks):
+        for tm, tn in B.tile_deal(3, n, nranks, r):
+            assert (tm, tn) not in seen and tn % nranks == r and tm >= tn
+            seen.add((tm, tn))
+    assert len(seen) == t2 * (t2 + 1) // 2
 
 
 @pytest.mark.parametrize("n", [100, 128, 1000, 4096, 16384, 15504])
@@ -122,6 +144,68 @@ def test_exchange_protocol_gloo_world2(lower):
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, 150, 32, lower, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) == 1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the sharded partition (csrc/shard.cu): local pass + key-table merge, over gloo with two ranks
+# ---------------------------------------------------------------------------------------------------------
+def _merge_worker(rank, world, port, n, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(3)
+    old = rng.integers(0, 4, size=(n, n))                    # current labels (canonical ids, replicated)
+    val = rng.integers(0, 5, size=(n, n))                    # rounded-value codes of the refining matrix
+    key = (val.astype(np.int64) << 8) | old                  # the pass's 64-bit key (0 = the zero class)
+    flat = key.reshape(-1, order="F")
+    # 1. local pass over this rank's column block: key -> first (column-major) index inside the block
+    c0, c1 = n * rank // world, n * (rank + 1) // world
+    local = {}
+    for idx in range(c0 * n, c1 * n):
+        k = int(flat[idx])
+        if k and k not in local:
+            local[k] = idx
+    # 2. all-gather of the (key, first index) pairs, identical merge on every rank
+    gathered = [None] * world
+    dist.all_gather_object(gathered, sorted(local.items()))
+    merged = {}
+    for pairs in gathered:
+        for k, idx in pairs:
+            merged[k] = min(idx, merged.get(k, idx))
+    order = sorted(merged, key=lambda k: merged[k])          # canonical numbering = rank of the first indices
+    canon = {k: i + 1 for i, k in enumerate(order)}
+    # 3. local relabel of the block
+    mine = np.array([canon.get(int(k), 0) for k in flat[c0 * n:c1 * n]], dtype=np.int64)
+    # 4. lazy gather of the blocks (only to check the result here)
+    blocks = [None] * world
+    dist.all_gather_object(blocks, mine)
+    got = np.concatenate(blocks)
+    # the reference: Partition(M) numbering by first occurrence over the WHOLE matrix (src/partitions.jl:24-35)
+    want, seen = np.zeros(n * n, dtype=np.int64), {}
+    for idx, k in enumerate(flat):
+        if k:
+            want[idx] = seen.setdefault(int(k), len(seen) + 1)
+    flag = torch.tensor([1 if np.array_equal(got, want) and len(order) == len(seen) else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(int(flag.item()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [7, 24])
+def test_sharded_refine_merge_protocol_gloo_world2(n):
+    """C1/C2 of SURVEY.md 8(e): per-rank key tables over column blocks, merged by smallest first index, give the
+    reference's first-occurrence numbering on every rank (n = 7: ragged blocks)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_merge_worker, args=(r, 2, port, n, q)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
