@@ -150,6 +150,28 @@ __device__ __forceinline__ uint32_t elect_one() {
 }
 __device__ __forceinline__ double pow2(int e) { return __longlong_as_double((long long)(e + 1023) << 52); }
 
+// Grid-wide pacing of the TMA producers.  The persistent CTAs (clusters) of a launch are all co-resident and each
+// walks the same schedule (tile wave, accumulator pair, k-block) over different tiles; the tiles of a wave share
+// their operand panels through L2 only while the CTAs stay within a few k-blocks of each other.  Nothing keeps
+// them there: over 112 waves of 2 ms tiles (N = 32768) the drift exceeds what L2 holds, every CTA streams its
+// own panels from HBM (ncu: L2 hit rate 34 %, 1.8 TB of DRAM reads per launch, 4.7 TB/s) and the power that costs
+// drops the SM clock to 1.15 GHz.  An epoch = (wave, accumulator pair); a producer enters an epoch only after
+// every CTA that works in the PREVIOUS epoch has issued its last load of it.  Counters live in global memory,
+// zeroed by the host before the launch; they order nothing but time (no data depends on them).
+__device__ __forceinline__ void pace_arrive(unsigned int* sync, int epoch) {
+  if (sync) atomicAdd(sync + epoch, 1u);
+}
+__device__ __forceinline__ void pace_wait(const unsigned int* sync, int epoch, unsigned int expect) {
+  if (!sync || epoch < 0) return;
+  const volatile unsigned int* p = sync + epoch;
+  if (*p >= expect) return;
+  const long long t0 = clock64();
+  while (*p < expect) {
+    __nanosleep(200);
+    if (clock64() - t0 > WAIT_LIMIT) __trap();
+  }
+}
+
 // --------------------------------------------------------------------------------------------
 // out[0] = max |x| over the matrix, out[1] = the smallest non-zero column maximum (positive doubles
 // order like their bit patterns).  One warp per column.  The slices share ONE scale, so a row / column
@@ -320,7 +342,7 @@ __global__ void __launch_bounds__(256) colmax_labels_kernel(const uint32_t* __re
 __global__ void __launch_bounds__(THREADS, 1)
 square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, double* __restrict__ C,
                  int64_t ldc, int n, int S, int bits, int segblocks, const int2* __restrict__ tiles, int ntiles, int wexp,
-                 double* const* __restrict__ peers, int npeers) {
+                 double* const* __restrict__ peers, int npeers, unsigned int* __restrict__ pace, int pace_kb) {
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const uint32_t bar_full = base + NPAIR * PAIR_BYTES;
@@ -364,12 +386,22 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
       uint32_t t = 0;
-      for (int w = blockIdx.x; w < ntiles; w += gridDim.x) {
+      const int npair = (S + 1) / 2, nsub = (KB + pace_kb - 1) / pace_kb;
+      int wave = 0;
+      for (int w = blockIdx.x; w < ntiles; w += gridDim.x, ++wave) {
         const int2 tile = tiles[w];
         const int m0 = tile.x * TM, n0 = tile.y * TN;
-        for (int c0 = S - 2; c0 >= -1; c0 -= 2) {
+        int pidx = 0;
+        for (int c0 = S - 2; c0 >= -1; c0 -= 2, ++pidx) {
           const int nch = c0 + 2;
           for (int kb = 0; kb < KB; ++kb) {      // (segments are contiguous: the producer just streams on)
+            if (kb % pace_kb == 0) {   // pacing: everyone who works in the previous epoch has issued its loads
+              const int epoch = (wave * npair + pidx) * nsub + kb / pace_kb;
+              if (epoch > 0) {
+                const int pw = (epoch - 1) / (npair * nsub);
+                pace_wait(pace, epoch - 1, (unsigned int)min((int)gridDim.x, ntiles - pw * (int)gridDim.x));
+              }
+            }
             for (int i = 0; i < nch; ++i) {
               {   // T_{2i} = B_{c0+1-i}
                 const uint32_t slot = t % NSLOT, ph = (t / NSLOT) & 1u;
@@ -386,6 +418,7 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 ++t;
               }
             }
+            if ((kb + 1) % pace_kb == 0 || kb == KB - 1) pace_arrive(pace, (wave * npair + pidx) * nsub + kb / pace_kb);
           }
         }
       }
@@ -561,7 +594,7 @@ __device__ __forceinline__ void mma_i8_2sm(uint32_t tmem_d, uint64_t adesc, uint
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 square_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmT, double* __restrict__ C, int64_t ldc, int n, int S, int bits,
                       int segblocks, const int2* __restrict__ tiles, int ntiles, int wexp,
-                      double* const* __restrict__ peers, int npeers) {
+                      double* const* __restrict__ peers, int npeers, unsigned int* __restrict__ pace, int pace_kb) {
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const uint32_t bar_full = base + NSLOT2 * T2_BYTES;
@@ -601,13 +634,23 @@ square_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmT, double* __restric
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmT) : "memory");
       uint32_t t = 0;
-      for (int w = cluster_id; w < ntiles; w += nclusters) {
+      const int npair = (S + 1) / 2, nsub = (KB + pace_kb - 1) / pace_kb;
+      int wave = 0;
+      for (int w = cluster_id; w < ntiles; w += nclusters, ++wave) {
         const int2 tile = tiles[w];
         const int m0 = tile.x * 256 + (int)crank * 128;       // this CTA's rows of A
         const int n0 = tile.y * TN + (int)crank * 128;        // this CTA's half of the B columns
-        for (int c0 = S - 2; c0 >= -1; c0 -= 2) {
+        int pidx = 0;
+        for (int c0 = S - 2; c0 >= -1; c0 -= 2, ++pidx) {
           const int nch = c0 + 2;
           for (int kb = 0; kb < KB; ++kb) {
+            if (kb % pace_kb == 0) {   // pacing (both CTAs of a pair wait; the leader signals)
+              const int epoch = (wave * npair + pidx) * nsub + kb / pace_kb;
+              if (epoch > 0) {
+                const int pw = (epoch - 1) / (npair * nsub);
+                pace_wait(pace, epoch - 1, (unsigned int)min(nclusters, ntiles - pw * nclusters));
+              }
+            }
             for (int i = 0; i < 2 * nch; ++i) {               // even i: B_{c0+1-i/2}, odd i: A_{i/2}
               const uint32_t slot = t % NSLOT2, ph = (t / NSLOT2) & 1u;
               mbar_wait(bar_empty + 8 * slot, ph ^ 1u);
@@ -619,6 +662,8 @@ square_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmT, double* __restric
                 tma_load_3d_2sm(base + slot * T2_BYTES, &tmT, lead_full, kb * TK, n0, c0 + 1 - (i >> 1));
               ++t;
             }
+            if (crank == 0 && ((kb + 1) % pace_kb == 0 || kb == KB - 1))
+              pace_arrive(pace, (wave * npair + pidx) * nsub + kb / pace_kb);
           }
         }
       }
@@ -986,6 +1031,25 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits,
   double* const* peers = sharded ? sdpsr_comm_peer_table(ctx, C) : nullptr;
   // nobody may still be reading the previous contents of C on any rank when remote stores begin
   if (peers) SDPSR_TRY(sdpsr_comm_barrier(ctx));
+  // pacing counters (one per (wave, accumulator pair)); SDPSR_I8_PACE=0 disables the pacing (A/B switch)
+  unsigned int* d_pace = nullptr;
+  static int pace_kb = 0;                 // k-blocks (of 128 bytes) per pacing epoch
+  if (!pace_kb) {
+    const char* pk = getenv("SDPSR_I8_PACE_KB");
+    pace_kb = pk && atoi(pk) > 0 ? atoi(pk) : 64;
+  }
+  {
+    static int pace_env = -1;
+    if (pace_env < 0) {
+      const char* pe = getenv("SDPSR_I8_PACE");
+      pace_env = pe ? (atoi(pe) != 0 ? 1 : 0) : 1;
+    }
+    if (pace_env && ntiles > 0) {
+      const size_t epochs = (size_t)ntiles * (size_t)((S + 1) / 2) * (size_t)(((n + TK - 1) / TK + pace_kb - 1) / pace_kb) + 8;
+      SDPSR_TRY(sdpsr_scratch_t(ctx, 41, epochs, &d_pace));
+      SDPSR_CUDA(cudaMemsetAsync(d_pace, 0, epochs * sizeof(unsigned int), ctx->stream));
+    }
+  }
   {
     // work = int8 operations issued: S(S+1)/2 products of (tile rows x 256 x K) per tile
     const double kpad = (double)((n + TK - 1) / TK * TK);
@@ -1008,11 +1072,11 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits,
       }
       const int nclusters = std::max(1, std::min(max_pairs, ntiles));
       square_i8_2cta_kernel<<<2 * nclusters, THREADS, SMEM2_BYTES, ctx->stream>>>(tmA, C, ld, (int)n, S, bits, segblocks, d_tiles,
-                                                                                 ntiles, 2 * e - 12, peers, ctx->nranks);
+                                                                                 ntiles, 2 * e - 12, peers, ctx->nranks, d_pace, pace_kb);
     } else {
       const int grid = std::max(1, std::min(ctx->sm_count, ntiles));
       square_i8_kernel<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, C, ld, (int)n, S, bits, segblocks, d_tiles, ntiles,
-                                                                   2 * e - 12, peers, ctx->nranks);
+                                                                   2 * e - 12, peers, ctx->nranks, d_pace, pace_kb);
     }
     count_launch(ctx);
   }

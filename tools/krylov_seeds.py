@@ -1,5 +1,5 @@
-"""Diagnostic (GPU): how often is the Krylov block-diagonalisation applicable, and why not?
-   python tools/krylov_seeds.py [h54|h74|h48] [nseeds]"""
+"""Diagnostic (GPU): over how many coefficient draws does the module path of blockDiagonalize apply, and why not?
+   python tools/krylov_seeds.py [h54|h74|h48|k104|k205|syn32768] [nseeds]"""
 import json
 import sys
 
@@ -21,8 +21,10 @@ class Coeffs:
 which = sys.argv[1] if len(sys.argv) > 1 else "h54"
 nseeds = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 prob = {"h54": lambda: pr.hamming(5, 4, sparse=True), "h74": lambda: pr.hamming(7, 4, sparse=True),
-        "h48": lambda: pr.hamming(4, 8, sparse=True), "k104": lambda: pr.kneser(10, 4)}[which]()
-P = S.admissible_subspace(*prob, rand=Coeffs(1))
+        "h48": lambda: pr.hamming(4, 8, sparse=True), "k104": lambda: pr.kneser(10, 4),
+        "k205": lambda: pr.kneser(20, 5, sparse=True),
+        "syn32768": lambda: pr.synthetic_product_scheme(3, 5, 64, keep_orbitals=False)}[which]()
+P = S.admissible_subspace(*prob, rand=Coeffs(1), fetch_labels=False)
 out = []
 for seed in range(nseeds):
     try:
