@@ -235,6 +235,16 @@ int sdpsr_comm_agree_min(sdpsr_ctx* ctx, int* flag) {
   return SDPSR_OK;
 }
 
+// true when another rank of the in-process transport computes on the same device: its persistent kernels then
+// compete with this rank's for the SMs, so "every CTA of the launch is co-resident" does not hold
+bool sdpsr_comm_shares_device(const sdpsr_ctx* ctx) {
+  if (!ctx->local_group) return false;
+  LocalGroup* g = (LocalGroup*)ctx->local_group;
+  for (int r = 0; r < g->nranks; ++r)
+    if (g->ctxs[r] && g->ctxs[r] != ctx && g->ctxs[r]->device == ctx->device) return true;
+  return false;
+}
+
 int sdpsr_comm_barrier(sdpsr_ctx* ctx) {
   if (ctx->nranks <= 1) return SDPSR_OK;
   if (ctx->local_group) return local_barrier(ctx);

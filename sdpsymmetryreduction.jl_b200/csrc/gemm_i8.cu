@@ -1044,7 +1044,9 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits,
       const char* pe = getenv("SDPSR_I8_PACE");
       pace_env = pe ? (atoi(pe) != 0 ? 1 : 0) : 1;
     }
-    if (pace_env && ntiles > 0) {
+    // (the spin-wait needs every CTA of the launch co-resident: not guaranteed when another in-process rank runs
+    //  its own persistent kernel on the same device)
+    if (pace_env && ntiles > 0 && !sdpsr_comm_shares_device(ctx)) {
       const size_t epochs = (size_t)ntiles * (size_t)((S + 1) / 2) * (size_t)(((n + TK - 1) / TK + pace_kb - 1) / pace_kb) + 8;
       SDPSR_TRY(sdpsr_scratch_t(ctx, 41, epochs, &d_pace));
       SDPSR_CUDA(cudaMemsetAsync(d_pace, 0, epochs * sizeof(unsigned int), ctx->stream));

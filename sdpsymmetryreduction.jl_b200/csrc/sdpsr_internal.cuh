@@ -325,6 +325,7 @@ int sdpsr_shard_gather_compact(sdpsr_ctx* ctx);
 int sdpsr_shard_ensure_full_labels(sdpsr_ctx* ctx);
 int sdpsr_comm_agree_min(sdpsr_ctx* ctx, int* flag);
 int sdpsr_comm_barrier(sdpsr_ctx* ctx);
+bool sdpsr_comm_shares_device(const sdpsr_ctx* ctx);
 double* const* sdpsr_comm_peer_table(sdpsr_ctx* ctx, const double* C);
 int sdpsr_ensure_matrix(sdpsr_ctx* ctx, double** p);
 

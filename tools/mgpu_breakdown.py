@@ -1,4 +1,5 @@
-"""Diagnostic (multi-GPU, torchrun): wall time per C-ABI call of one sharded job."""
+"""Diagnostic (multi-GPU, torchrun): wall time per C-ABI call of one sharded job.
+   torchrun ... tools/mgpu_breakdown.py d q [e2e]     (e2e: host-resident C from pinned memory, labels fetched by rank 0)"""
 import json
 import os
 import sys
@@ -41,8 +42,15 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 d, q = (int(x) for x in (sys.argv[1:3] if len(sys.argv) > 2 else (6, 4)))
+e2e = len(sys.argv) > 3 and sys.argv[3] == "e2e"
 prob = pr.hamming(d, q, sparse=True)
-for flags in (0, B.F_NCCL_EXCHANGE):
+labels_pinned = None
+if e2e:
+    Cp = torch.from_numpy(np.ascontiguousarray(prob.C)).pin_memory()
+    prob.C = Cp.numpy()
+    lp = torch.empty(prob.n * prob.n, dtype=torch.int16).pin_memory()
+    labels_pinned = lp.numpy().view(np.uint16).reshape(prob.n, prob.n, order="F")
+for flags in ((0,) if e2e else (0, B.F_NCCL_EXCHANGE)):
     ctx = B.Context(prob.n, local, B.F_TIMING | flags)
     box = [B.Context.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
@@ -53,11 +61,18 @@ for flags in (0, B.F_NCCL_EXCHANGE):
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        P = S.admissible_subspace(*prob, rand=Coeffs(), ctx=ctx, fetch_labels=False)
+        if e2e:
+            P = S.admissible_subspace(prob.C, prob.A, prob.b, rand=Coeffs(), ctx=ctx, labels_out=labels_pinned,
+                                      label_dtype=np.uint16, fetch_labels=rank == 0)
+        else:
+            P = S.admissible_subspace(*prob, rand=Coeffs(), ctx=ctx, fetch_labels=False)
+        t1 = time.perf_counter()
         bd = S.blockDiagonalize(P, False, rand=Coeffs(2))
+        torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        if rank == 0 and rep:
-            print(json.dumps({"flags": flags, "rep": rep, "wall_s": round(wall, 4),
+        if rep and (rank == 0 or (e2e and rank == world - 1)):
+            print(json.dumps({"rank": rank, "e2e": e2e, "flags": flags, "rep": rep, "wall_s": round(wall, 4),
+                              "admissible_s": round(t1 - t0, 4),
                               "calls": {k: [v[0], round(v[1], 4)] for k, v in acc.items()},
                               "kernels_ms": {k: round(v["ms"], 2) for k, v in ctx.timing().items() if v["launches"]}}),
                   flush=True)
