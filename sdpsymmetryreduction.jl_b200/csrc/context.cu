@@ -245,7 +245,7 @@ extern "C" int sdpsr_partition_reset(sdpsr_ctx* ctx) {
   SDPSR_CUDA(cudaMemsetAsync(ctx->labels, 0, ctx->elems * sizeof(uint32_t), ctx->stream));
   KeyTable& t = ctx->tab[ctx->cur];
   SDPSR_TRY(sdpsr_table_alloc(ctx, t, 64));
-  SDPSR_CUDA(cudaMemsetAsync(t.keys, 0xff, (size_t)t.cap * 12, ctx->stream));
+  SDPSR_CUDA(cudaMemsetAsync(t.slots, 0xff, (size_t)t.cap * sizeof(KeySlot), ctx->stream));
   SDPSR_CUDA(cudaMemsetAsync(t.meta, 0, 4 * sizeof(uint32_t), ctx->stream));
   SDPSR_CUDA(cudaMemsetAsync(t.rank, 0, sizeof(uint32_t), ctx->stream));
   t.count = 0;

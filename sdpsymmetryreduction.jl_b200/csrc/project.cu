@@ -716,8 +716,8 @@ int sdpsr_constraints_finalize(sdpsr_ctx* ctx) {
     SDPSR_CUDA(cudaMemcpyAsync(occ.data(), scratch.occ, (size_t)npat * 4, cudaMemcpyDeviceToHost, ctx->stream));
     SDPSR_CUDA(cudaMemcpyAsync(rk.data(), scratch.rank, rk.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
   }
-  std::vector<uint32_t> allmin((size_t)scratch.cap);
-  SDPSR_CUDA(cudaMemcpyAsync(allmin.data(), scratch.minidx, allmin.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<KeySlot> allslots((size_t)scratch.cap);
+  SDPSR_CUDA(cudaMemcpyAsync(allslots.data(), scratch.slots, allslots.size() * sizeof(KeySlot), cudaMemcpyDeviceToHost, ctx->stream));
   unsigned long long* dcnt = nullptr;
   SDPSR_TRY(sdpsr_scratch_t(ctx, 0, (size_t)npat + 1, &dcnt));
   SDPSR_CUDA(cudaMemsetAsync(dcnt, 0, ((size_t)npat + 1) * 8, ctx->stream));
@@ -730,7 +730,7 @@ int sdpsr_constraints_finalize(sdpsr_ctx* ctx) {
   std::vector<uint32_t> rep((size_t)npat + 1, 0xffffffffu);      // padded linear index of the representative
   for (int64_t i = 0; i < npat; ++i) {
     const uint32_t slot = occ[(size_t)i];
-    rep[rk[(size_t)slot + 1]] = allmin[slot];
+    rep[rk[(size_t)slot + 1]] = allslots[slot].minidx;
   }
   c.pat_cnt.assign(cnt.begin(), cnt.end());
   // ---- pattern table: column of A at each representative entry (binary searches on the device) ----------

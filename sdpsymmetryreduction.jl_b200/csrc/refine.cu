@@ -18,6 +18,7 @@
 // HBM traffic of a pass: 8 B value + 4 B old id + 4 B new id = 16 B / entry.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "sdpsr_internal.cuh"
@@ -29,6 +30,11 @@ constexpr int EPT = 4;            // consecutive entries per thread per tile
 constexpr int TILE = RT * EPT;    // entries per tile
 constexpr int SC = 8192;          // slots of the per-CTA key cache (128 KB)
 constexpr int SC_LIMIT = SC / 2;      // keys cached per CTA; the rest always go to the global table
+// current dim above which a pass skips the cache altogether: with 16-byte table slots (one L2 sector per lookup) the
+// global path holds 2.3-2.5 TB/s from ~2000 classes up, the cache falls below that at ~2300 (probe chains at load
+// factors > 0.28 cost more warp-level iterations than the L2 round trip; sweep in DESIGN.md section 4)
+constexpr int CACHE_DIM_LIMIT = 2304;
+constexpr int JOINT_MIN_DIM = 1500;    // classes above which refine_fast_kernel probes its four entries jointly
 constexpr int CACHE_PROBES = 8;       // linear-probe window of the cache (lookups and inserts)
 constexpr uint32_t PROBE_LIMIT = 4096;
 constexpr int RANK_BRUTE_MAX = 16384;
@@ -53,8 +59,7 @@ struct RefineArgs {
   int fillproj;
   int use_cache;
   int raw_bits;
-  uint64_t* gkeys;
-  uint32_t* gmin;
+  KeySlot* gslots;
   uint32_t* gocc;
   uint32_t* gmeta;
   uint32_t gmask;
@@ -75,6 +80,11 @@ __device__ __forceinline__ uint64_t ld_vol64(const uint64_t* p) {
 }
 __device__ __forceinline__ uint32_t ld_vol32(const uint32_t* p) {
   return *reinterpret_cast<const volatile uint32_t*>(p);
+}
+__device__ __forceinline__ uint4 ld_vol128(const void* p) {
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
 }
 
 // _clamp_round! of one value (src/utils.jl:34-53) as an integer code:
@@ -122,11 +132,11 @@ __device__ __forceinline__ uint64_t raw_code(double v) {
 __device__ __forceinline__ uint32_t global_insert(const RefineArgs& a, uint64_t k, uint64_t h) {
   uint32_t s = (uint32_t)(h >> 20) & a.gmask;
   for (uint32_t probe = 0; probe < PROBE_LIMIT; ++probe) {
-    const uint64_t kk = ld_vol64(a.gkeys + s);
+    const uint64_t kk = ld_vol64(&a.gslots[s].key);
     if (kk == k) return s + 1;
     if (kk == KEY_EMPTY) {
       const unsigned long long old =
-          atomicCAS(reinterpret_cast<unsigned long long*>(a.gkeys + s), KEY_EMPTY, (unsigned long long)k);
+          atomicCAS(reinterpret_cast<unsigned long long*>(&a.gslots[s].key), KEY_EMPTY, (unsigned long long)k);
       if (old == KEY_EMPTY) {
         const uint32_t pos = atomicAdd(a.gmeta, 1u);
         if (pos < a.glimit)
@@ -174,15 +184,14 @@ __device__ __forceinline__ void load_entries(const RefineArgs& a, uint64_t base,
 // Keep the first occurrence: the table entry only ever decreases, so a stale (larger) read
 // merely costs one redundant atomic.
 __device__ __forceinline__ void note_first(const RefineArgs& a, uint32_t g, uint32_t idx) {
-  if (idx < ld_vol32(a.gmin + (g - 1))) atomicMin(a.gmin + (g - 1), idx);
+  if (idx < ld_vol32(&a.gslots[g - 1].minidx)) atomicMin(&a.gslots[g - 1].minidx, idx);
 }
 
-__device__ __noinline__ uint32_t refine_miss(uint64_t* gkeys, uint32_t* gmin, uint32_t* gocc, uint32_t* gmeta,
+__device__ __noinline__ uint32_t refine_miss(KeySlot* gslots, uint32_t* gocc, uint32_t* gmeta,
                                              uint32_t gmask, uint32_t glimit, CacheSlot* cache, uint32_t* s_count,
                                              uint64_t k, uint32_t idx, int free_slot, uint32_t mytile) {
   RefineArgs a;                      // only the table fields are read below
-  a.gkeys = gkeys;
-  a.gmin = gmin;
+  a.gslots = gslots;
   a.gocc = gocc;
   a.gmeta = gmeta;
   a.gmask = gmask;
@@ -299,7 +308,7 @@ __global__ void __launch_bounds__(RT) refine_kernel(const RefineArgs a) {
         }
         __syncwarp(wmask);      // reconverge (see refine_fast_kernel)
         if (need && g == 0u)
-          g = refine_miss(a.gkeys, a.gmin, a.gocc, a.gmeta, a.gmask, a.glimit, cache, &s_count, k, idx, free_slot,
+          g = refine_miss(a.gslots, a.gocc, a.gmeta, a.gmask, a.glimit, cache, &s_count, k, idx, free_slot,
                           mytile);
         __syncwarp(wmask);
         gid[e] = g;
@@ -319,7 +328,7 @@ __global__ void __launch_bounds__(RT) refine_kernel(const RefineArgs a) {
 // multiplies and compared word-wise.  Same protocol as refine_kernel otherwise; the cold
 // miss path is out of line.
 // ---------------------------------------------------------------------------
-template <bool WRITEBACK, bool FILLPROJ>
+template <bool WRITEBACK, bool FILLPROJ, bool JOINT>
 __global__ void __launch_bounds__(RT, 1) refine_fast_kernel(const RefineArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CacheSlot* cache = reinterpret_cast<CacheSlot*>(smem_raw);
@@ -419,76 +428,142 @@ __global__ void __launch_bounds__(RT, 1) refine_fast_kernel(const RefineArgs a) 
         __stcs(reinterpret_cast<double2*>(vals_out + base), make_double2(r[0], r[1]));
         __stcs(reinterpret_cast<double2*>(vals_out + base + 2), make_double2(r[2], r[3]));
       }
-      // The four entries of a thread are resolved TOGETHER: every probe round issues the (predicated) 16-byte
-      // shared loads of all entries that are still searching before any of them is compared, so the rounds of
-      // a warp cost max-over-lanes iterations ONCE instead of once per entry, with four independent loads in
-      // flight (the sequential version was bound by branch resolution and fixed-latency waits at ~3000 classes:
-      // 730 warp instructions per 128 entries against 295 at 8 classes).
-      bool same[EPT], need[EPT], pend[EPT];
-      uint32_t g[EPT], slot[EPT];
-      int free_slot[EPT];
-      bool any = false;
+      if (!JOINT) {
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        same[e] = e > 0 && khi[e] == khi[e - 1] && klo[e] == klo[e - 1];
-        need[e] = (khi[e] | klo[e]) != 0u && !same[e];
-        g[e] = 0u;
-        free_slot[e] = -1;
-        slot[e] = (((klo[e] * 0x9e3779b1u) ^ (khi[e] * 0x85ebca77u)) >> 19) & (SC - 1);
-        pend[e] = need[e] && use_cache;
-        any |= pend[e];
-      }
+        for (int e = 0; e < EPT; ++e) {
+          // Lanes need different probe counts; without the explicit __syncwarp below each lane
+          // would walk the rest of the tile alone (measured: 3.4 active lanes per instruction).
+          const bool same = e > 0 && khi[e] == khi[e - 1] && klo[e] == klo[e - 1];
+          const bool need = (khi[e] | klo[e]) != 0u && !same;
+          uint32_t g = same ? gid[e - 1] : 0u;
+          uint32_t s = (((klo[e] * 0x9e3779b1u) ^ (khi[e] * 0x85ebca77u)) >> 19) & (SC - 1);
+          int free_slot = -1;
+          if (need && use_cache) {
 #pragma unroll 1
-      for (int probe = 0; probe < CACHE_PROBES && __any_sync(wmask, any); ++probe) {
-        uint4 raw[EPT];
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-          raw[e] = make_uint4(0u, 0u, 0u, 0u);
-          asm volatile(
-              "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t"
-              "@p ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
-              : "+r"(raw[e].x), "+r"(raw[e].y), "+r"(raw[e].z), "+r"(raw[e].w)
-              : "r"(cache_base + slot[e] * 16u), "r"((uint32_t)pend[e]));
-        }
-        any = false;
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-          if (pend[e]) {
-            if (raw[e].x == klo[e] && raw[e].y == khi[e]) {
-              g[e] = raw[e].z;                             // 0 while the publisher is in flight
-              if (g[e] != 0u && iter <= raw[e].w) {
-                const uint32_t idx = a.idx0 + (uint32_t)(base + e);
-                if (idx < ld_vol32(a.gmin + (g[e] - 1))) atomicMin(a.gmin + (g[e] - 1), idx);
+            for (int probe = 0; probe < CACHE_PROBES; ++probe) {
+              uint4 raw;
+              asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w)
+                           : "r"(cache_base + s * 16u));
+              if (raw.x == klo[e] && raw.y == khi[e]) {
+                g = raw.z;                                   // 0 while the publisher is in flight
+                if (g != 0u && iter <= raw.w) {
+                  const uint32_t idx = a.idx0 + (uint32_t)(base + e);
+                  if (idx < ld_vol32(&a.gslots[g - 1].minidx)) atomicMin(&a.gslots[g - 1].minidx, idx);
+                }
+                break;
               }
-              pend[e] = false;
-            } else if ((raw[e].x & raw[e].y) == 0xffffffffu) {
-              free_slot[e] = (int)slot[e];
-              pend[e] = false;
-            } else {
-              slot[e] = (slot[e] + 1) & (SC - 1);
-              any = true;
+              if ((raw.x & raw.y) == 0xffffffffu) {
+                free_slot = (int)s;
+                break;
+              }
+              s = (s + 1) & (SC - 1);
+            }
+          }
+          __syncwarp(wmask);       // lanes leave the probe loop at different times: reconverge here
+          if (need && g == 0u)
+            g = refine_miss(a.gslots, a.gocc, a.gmeta, a.gmask, a.glimit, cache, &s_count,
+                            ((uint64_t)khi[e] << 32) | klo[e], a.idx0 + (uint32_t)(base + e), free_slot, iter);
+          __syncwarp(wmask);
+          gid[e] = g;
+        }
+      } else {
+        // The four entries of a thread are resolved TOGETHER: every probe round issues the (predicated) 16-byte
+        // shared loads of all entries that are still searching before any of them is compared, so the rounds of
+        // a warp cost max-over-lanes iterations ONCE instead of once per entry, with four independent loads in
+        // flight (the sequential version was bound by branch resolution and fixed-latency waits at ~3000 classes:
+        // 730 warp instructions per 128 entries against 295 at 8 classes).
+        bool same[EPT], need[EPT], pend[EPT];
+        uint32_t g[EPT], slot[EPT];
+        int free_slot[EPT];
+        bool any = false;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          same[e] = e > 0 && khi[e] == khi[e - 1] && klo[e] == klo[e - 1];
+          need[e] = (khi[e] | klo[e]) != 0u && !same[e];
+          g[e] = 0u;
+          free_slot[e] = -1;
+          slot[e] = (((klo[e] * 0x9e3779b1u) ^ (khi[e] * 0x85ebca77u)) >> 19) & (SC - 1);
+          pend[e] = need[e] && use_cache;
+          any |= pend[e];
+        }
+#pragma unroll 1
+        for (int probe = 0; probe < CACHE_PROBES && __any_sync(wmask, any); ++probe) {
+          uint4 raw[EPT];
+#pragma unroll
+          for (int e = 0; e < EPT; ++e) {
+            raw[e] = make_uint4(0u, 0u, 0u, 0u);
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t"
+                "@p ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+                : "+r"(raw[e].x), "+r"(raw[e].y), "+r"(raw[e].z), "+r"(raw[e].w)
+                : "r"(cache_base + slot[e] * 16u), "r"((uint32_t)pend[e]));
+          }
+          any = false;
+#pragma unroll
+          for (int e = 0; e < EPT; ++e) {
+            if (pend[e]) {
+              if (raw[e].x == klo[e] && raw[e].y == khi[e]) {
+                g[e] = raw[e].z;                             // 0 while the publisher is in flight
+                if (g[e] != 0u && iter <= raw[e].w) {
+                  const uint32_t idx = a.idx0 + (uint32_t)(base + e);
+                  if (idx < ld_vol32(&a.gslots[g[e] - 1].minidx)) atomicMin(&a.gslots[g[e] - 1].minidx, idx);
+                }
+                pend[e] = false;
+              } else if ((raw[e].x & raw[e].y) == 0xffffffffu) {
+                free_slot[e] = (int)slot[e];
+                pend[e] = false;
+              } else {
+                slot[e] = (slot[e] + 1) & (SC - 1);
+                any = true;
+              }
             }
           }
         }
-      }
-      __syncwarp(wmask);
-      // misses (first sight of a key in this CTA, or a publisher still in flight): in entry order, because an
-      // entry equal to its predecessor takes the predecessor's id
-      bool miss = false;
+        __syncwarp(wmask);
+        if (!use_cache) {
+          // More classes than the CTA cache holds: every entry goes to the global table.  The first probe and the
+          // first-index check of the four entries are issued together (two dependent L2 round trips per tile
+          // instead of eight); whatever is not settled by the first probe takes the out-of-line path below.
+          uint4 sl[EPT];
+          uint32_t gs[EPT];
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) miss |= need[e] && g[e] == 0u;
-      if (__any_sync(wmask, miss)) {
+          for (int e = 0; e < EPT; ++e) {
+            const uint64_t k = ((uint64_t)khi[e] << 32) | klo[e];
+            gs[e] = (uint32_t)(mix64(k) >> 20) & a.gmask;
+            sl[e] = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
+            if (need[e]) sl[e] = ld_vol128(a.gslots + gs[e]);   // {key lo, key hi, minidx, -}
+          }
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-          if (need[e] && g[e] == 0u)
-            g[e] = refine_miss(a.gkeys, a.gmin, a.gocc, a.gmeta, a.gmask, a.glimit, cache, &s_count,
-                               ((uint64_t)khi[e] << 32) | klo[e], a.idx0 + (uint32_t)(base + e), free_slot[e], iter);
+          for (int e = 0; e < EPT; ++e) {
+            if (need[e] && sl[e].x == klo[e] && sl[e].y == khi[e]) {
+              g[e] = gs[e] + 1u;
+              // (a 16-byte load need not be single-copy atomic: a stale or torn first index can only be LARGER
+              //  than the true one, which costs a redundant atomicMin, never a missed one)
+              const uint32_t idx = a.idx0 + (uint32_t)(base + e);
+              if (idx < sl[e].z) atomicMin(&a.gslots[gs[e]].minidx, idx);
+            }
+          }
           __syncwarp(wmask);
         }
-      }
-      gid[0] = g[0];
+        // misses (first sight of a key in this CTA, or a publisher still in flight): in entry order, because an
+        // entry equal to its predecessor takes the predecessor's id
+        bool miss = false;
 #pragma unroll
-      for (int e = 1; e < EPT; ++e) gid[e] = same[e] ? gid[e - 1] : g[e];
+        for (int e = 0; e < EPT; ++e) miss |= need[e] && g[e] == 0u;
+        if (__any_sync(wmask, miss)) {
+#pragma unroll
+          for (int e = 0; e < EPT; ++e) {
+            if (need[e] && g[e] == 0u)
+              g[e] = refine_miss(a.gslots, a.gocc, a.gmeta, a.gmask, a.glimit, cache, &s_count,
+                                 ((uint64_t)khi[e] << 32) | klo[e], a.idx0 + (uint32_t)(base + e), free_slot[e], iter);
+            __syncwarp(wmask);
+          }
+        }
+        gid[0] = g[0];
+#pragma unroll
+        for (int e = 1; e < EPT; ++e) gid[e] = same[e] ? gid[e - 1] : g[e];
+      }
       __stcs(reinterpret_cast<uint4*>(lab_out + base), make_uint4(gid[0], gid[1], gid[2], gid[3]));
     }
     cur = nx1;
@@ -499,10 +574,10 @@ __global__ void __launch_bounds__(RT, 1) refine_fast_kernel(const RefineArgs a) 
 // ---------------------------------------------------------------------------
 // canonical ranking of a table: rank[slot+1] = 1 + #{keys whose first index is smaller}
 // ---------------------------------------------------------------------------
-__global__ void gather_minidx_kernel(const uint32_t* __restrict__ occ, const uint32_t* __restrict__ gmin,
+__global__ void gather_minidx_kernel(const uint32_t* __restrict__ occ, const KeySlot* __restrict__ gslots,
                                      uint32_t* __restrict__ mi, uint32_t count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < count) mi[i] = gmin[occ[i]];
+  if (i < count) mi[i] = gslots[occ[i]].minidx;
 }
 
 __global__ void __launch_bounds__(256) rank_brute_kernel(const uint32_t* __restrict__ occ,
@@ -522,11 +597,11 @@ __global__ void __launch_bounds__(256) rank_brute_kernel(const uint32_t* __restr
   if (i < count) rank[occ[i] + 1] = r + 1;
 }
 
-__global__ void bitmap_set_kernel(const uint32_t* __restrict__ occ, const uint32_t* __restrict__ gmin,
+__global__ void bitmap_set_kernel(const uint32_t* __restrict__ occ, const KeySlot* __restrict__ gslots,
                                   uint32_t* __restrict__ bitmap, uint32_t count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) {
-    const uint32_t idx = gmin[occ[i]];
+    const uint32_t idx = gslots[occ[i]].minidx;
     atomicOr(bitmap + (idx >> 5), 1u << (idx & 31u));
   }
 }
@@ -598,14 +673,14 @@ __global__ void __launch_bounds__(1024) blocksum_scan_kernel(uint32_t* __restric
   }
 }
 
-__global__ void bitmap_rank_kernel(const uint32_t* __restrict__ occ, const uint32_t* __restrict__ gmin,
+__global__ void bitmap_rank_kernel(const uint32_t* __restrict__ occ, const KeySlot* __restrict__ gslots,
                                    const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ wordpre,
                                    const uint32_t* __restrict__ blocksum, uint32_t* __restrict__ rank,
                                    uint32_t count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) {
     const uint32_t s = occ[i];
-    const uint32_t idx = gmin[s];
+    const uint32_t idx = gslots[s].minidx;
     const uint32_t w = idx >> 5;
     const uint32_t below = __popc(bitmap[w] & ((1u << (idx & 31u)) - 1u));
     rank[s + 1] = blocksum[w >> 10] + wordpre[w] + below + 1u;
@@ -630,13 +705,13 @@ __global__ void build_lut_kernel(const uint32_t* __restrict__ occ, const uint32_
 // to be written to HBM (src/partitions.jl:160-164: "X stays the projected, rounded element").
 //   fast layout   hi = sign | e11 | q>>4,  lo = (q & 15) << 28 | old id          (refine_fast_kernel)
 //   generic       key = (sign | e11 | q) << lbits | old id                        (refine_kernel<KM_ROUND>)
-__global__ void decode_lut_kernel(const uint32_t* __restrict__ occ, const uint64_t* __restrict__ keys, uint32_t count,
+__global__ void decode_lut_kernel(const uint32_t* __restrict__ occ, const KeySlot* __restrict__ slots, uint32_t count,
                                   int fast, int lbits, int qbits, double scale, double* __restrict__ lut) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) lut[0] = 0.0;
   if (i >= count) return;
   const uint32_t s = occ[i];
-  const uint64_t k = keys[s];
+  const uint64_t k = slots[s].key;
   uint64_t aq, e11, sign;
   if (fast) {
     const uint32_t hi = (uint32_t)(k >> 32), lo = (uint32_t)k;
@@ -705,7 +780,7 @@ __global__ void canonical_kernel(const uint32_t* __restrict__ labels, const uint
 // host side
 // ---------------------------------------------------------------------------
 void sdpsr_table_free(KeyTable& t) {
-  cudaFree(t.keys);   // minidx lives in the same allocation
+  cudaFree(t.slots);
   cudaFree(t.rank);
   cudaFree(t.occ);
   cudaFree(t.meta);
@@ -713,15 +788,13 @@ void sdpsr_table_free(KeyTable& t) {
 }
 
 int sdpsr_table_alloc(sdpsr_ctx* ctx, KeyTable& t, size_t cap) {
-  if (t.alloc >= cap && t.keys) {
+  if (t.alloc >= cap && t.slots) {
     t.cap = (uint32_t)cap;
-    t.minidx = reinterpret_cast<uint32_t*>(t.keys + t.cap);
     return SDPSR_OK;
   }
   sdpsr_table_free(t);
-  // keys and minidx share one allocation so that a single memset(0xff) clears both
-  SDPSR_CUDA(cudaMalloc(&t.keys, cap * 12));
-  t.minidx = reinterpret_cast<uint32_t*>(t.keys + cap);
+  // a single memset(0xff) clears a slot: key = KEY_EMPTY, first index = 2^32 - 1
+  SDPSR_CUDA(cudaMalloc(&t.slots, cap * sizeof(KeySlot)));
   SDPSR_CUDA(cudaMalloc(&t.rank, (cap + 1) * sizeof(uint32_t)));
   SDPSR_CUDA(cudaMalloc(&t.occ, cap * sizeof(uint32_t)));
   SDPSR_CUDA(cudaMalloc(&t.meta, 4 * sizeof(uint32_t)));
@@ -754,7 +827,7 @@ int sdpsr_rank_table(sdpsr_ctx* ctx, KeyTable& t) {
   Timed tm(ctx, SDPSR_K_RANK, (double)count * 8.0);
   SDPSR_CUDA(cudaMemsetAsync(t.rank, 0, sizeof(uint32_t), ctx->stream));
   if (count == 0) return SDPSR_OK;
-  const uint32_t* gmin = t.minidx;
+  const KeySlot* gmin = t.slots;
   const int blocks = (int)((count + 255) / 256);
   const bool brute = count <= (uint32_t)RANK_BRUTE_MAX && !(ctx->flags & SDPSR_F_FORCE_BITMAP_RANK);
   if (brute) {
@@ -799,10 +872,14 @@ int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
     SDPSR_CUDA(cudaFuncSetAttribute(refine_kernel<KM_RAW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SDPSR_CUDA(cudaFuncSetAttribute(refine_kernel<KM_RAW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SDPSR_CUDA(cudaFuncSetAttribute(refine_kernel<KM_PAIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SDPSR_CUDA(cudaFuncSetAttribute(refine_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SDPSR_CUDA(cudaFuncSetAttribute(refine_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SDPSR_CUDA(cudaFuncSetAttribute(refine_fast_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SDPSR_CUDA(cudaFuncSetAttribute(refine_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDPSR_CUDA(cudaFuncSetAttribute(refine_fast_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDPSR_CUDA(cudaFuncSetAttribute(refine_fast_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDPSR_CUDA(cudaFuncSetAttribute(refine_fast_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDPSR_CUDA(cudaFuncSetAttribute(refine_fast_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDPSR_CUDA(cudaFuncSetAttribute(refine_fast_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDPSR_CUDA(cudaFuncSetAttribute(refine_fast_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDPSR_CUDA(cudaFuncSetAttribute(refine_fast_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDPSR_CUDA(cudaFuncSetAttribute(refine_fast_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   KeyTable& tnew = spec.table_override ? *spec.table_override : ctx->tab[ctx->cur ^ 1];
@@ -831,7 +908,16 @@ int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
   a.fillproj = spec.fillproj ? 1 : 0;
   a.raw_bits = spec.raw_bits ? 1 : 0;
   // the per-CTA cache only pays while the classes fit it; the new dim is >= the current one
-  a.use_cache = ((ctx->flags & SDPSR_F_NO_SMEM_CACHE) || (!spec.table_override && ctx->dim > SC_LIMIT)) ? 0 : 1;
+  // (SDPSR_REFINE_CACHE_LIMIT / SDPSR_REFINE_JOINT_MIN: experiment knobs of tools/refine_bench.py)
+  static const int64_t cache_limit = [] {
+    const char* e = getenv("SDPSR_REFINE_CACHE_LIMIT");
+    return e ? std::min<int64_t>(atoll(e), SC_LIMIT) : (int64_t)CACHE_DIM_LIMIT;
+  }();
+  static const int64_t joint_min = [] {
+    const char* e = getenv("SDPSR_REFINE_JOINT_MIN");
+    return e ? (int64_t)atoll(e) : (int64_t)JOINT_MIN_DIM;
+  }();
+  a.use_cache = ((ctx->flags & SDPSR_F_NO_SMEM_CACHE) || (!spec.table_override && ctx->dim > cache_limit)) ? 0 : 1;
   // provisional ids are <= cap; sharded: canonical ids <= dim, and the key layout must not depend on a
   // rank's table capacity (keys are compared across ranks)
   a.lbits = spec.ignore_labels ? 1 : sdpsr_label_bits(ctx);
@@ -850,10 +936,9 @@ int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
 
   for (;;) {
     SDPSR_TRY(sdpsr_table_alloc(ctx, tnew, cap));
-    SDPSR_CUDA(cudaMemsetAsync(tnew.keys, 0xff, (size_t)tnew.cap * 12, ctx->stream));
+    SDPSR_CUDA(cudaMemsetAsync(tnew.slots, 0xff, (size_t)tnew.cap * sizeof(KeySlot), ctx->stream));
     SDPSR_CUDA(cudaMemsetAsync(tnew.meta, 0, 4 * sizeof(uint32_t), ctx->stream));
-    a.gkeys = tnew.keys;
-    a.gmin = tnew.minidx;
+    a.gslots = tnew.slots;
     a.gocc = tnew.occ;
     a.gmeta = tnew.meta;
     a.gmask = tnew.cap - 1;
@@ -865,13 +950,23 @@ int sdpsr_refine_pass(sdpsr_ctx* ctx, const RefineSpec& spec, int64_t* dim) {
                         !(ctx->flags & SDPSR_F_NO_SMEM_CACHE);
       last_fast = fast;
       if (fast) {
+        // few classes: nearly every lane hits on its first probe and the entry-by-entry loop is the shorter code;
+        // many classes: the joint probe rounds win (sweep at N = 16384: 216 classes 4.72 vs 4.44 TB/s,
+        // 3000 classes 1.79 vs 1.93 TB/s)
+        const bool joint = ctx->dim > joint_min;
+#define SDPSR_LAUNCH_FAST(WB, FP)                                                      \
+  do {                                                                                 \
+    if (joint) refine_fast_kernel<WB, FP, true><<<grid, RT, smem, ctx->stream>>>(a);   \
+    else refine_fast_kernel<WB, FP, false><<<grid, RT, smem, ctx->stream>>>(a);        \
+  } while (0)
         if (a.fillproj) {
-          if (wb) refine_fast_kernel<true, true><<<grid, RT, smem, ctx->stream>>>(a);
-          else refine_fast_kernel<false, true><<<grid, RT, smem, ctx->stream>>>(a);
+          if (wb) SDPSR_LAUNCH_FAST(true, true);
+          else SDPSR_LAUNCH_FAST(false, true);
         } else {
-          if (wb) refine_fast_kernel<true, false><<<grid, RT, smem, ctx->stream>>>(a);
-          else refine_fast_kernel<false, false><<<grid, RT, smem, ctx->stream>>>(a);
+          if (wb) SDPSR_LAUNCH_FAST(true, false);
+          else SDPSR_LAUNCH_FAST(false, false);
         }
+#undef SDPSR_LAUNCH_FAST
       } else
       switch (spec.mode) {
         case KM_ROUND:
@@ -1032,7 +1127,7 @@ int sdpsr_decode_lut(sdpsr_ctx* ctx, double atol) {
   int qbits;
   SDPSR_TRY(sdpsr_round_params(ctx, atol, &scale, &iscale, &qbits));
   const int blocks = (int)std::max<uint32_t>(1, (t.count + 255) / 256);
-  decode_lut_kernel<<<blocks, 256, 0, ctx->stream>>>(t.occ, t.keys, t.count, ctx->key_fast ? 1 : 0, ctx->key_lbits, qbits,
+  decode_lut_kernel<<<blocks, 256, 0, ctx->stream>>>(t.occ, t.slots, t.count, ctx->key_fast ? 1 : 0, ctx->key_lbits, qbits,
                                                       scale, ctx->lut);
   count_launch(ctx);
   SDPSR_CUDA(cudaGetLastError());

@@ -39,9 +39,17 @@
 // --------------------------------------------------------------------------
 constexpr uint64_t KEY_EMPTY = ~0ull;
 
+// One slot of the table: the key and the first index of its class share a 16-byte slot, i.e. one 32-byte L2
+// sector serves the lookup AND the first-occurrence check of an entry (round 1 kept them in two arrays: two
+// sectors per entry, which is what bounded the pass once the classes no longer fit the per-CTA cache).
+struct __align__(16) KeySlot {
+  uint64_t key;      // KEY_EMPTY when free
+  uint32_t minidx;   // smallest padded linear index holding the key
+  uint32_t pad;
+};
+
 struct KeyTable {
-  uint64_t* keys = nullptr;    // [cap]      KEY_EMPTY when free
-  uint32_t* minidx = nullptr;  // [cap]      smallest padded linear index holding the key
+  KeySlot* slots = nullptr;    // [cap]
   uint32_t* rank = nullptr;    // [cap + 1]  canonical label of provisional id (rank[0] = 0)
   uint32_t* occ = nullptr;     // [cap]      list of occupied slots, in claim order
   uint32_t* meta = nullptr;    // [4]        {count, overflow, -, -}

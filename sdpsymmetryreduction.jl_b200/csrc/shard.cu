@@ -39,8 +39,8 @@ struct __align__(16) PackedKey {
 };
 
 // buf[0] = (count, -) header, buf[1 + i] = (key, first index) of the i-th occupied slot of the local table (i < cap)
-__global__ void pack_kernel(const uint32_t* __restrict__ occ, const uint64_t* __restrict__ keys,
-                            const uint32_t* __restrict__ minidx, uint32_t count, uint32_t cap, PackedKey* __restrict__ buf) {
+__global__ void pack_kernel(const uint32_t* __restrict__ occ, const KeySlot* __restrict__ slots, uint32_t count, uint32_t cap,
+                            PackedKey* __restrict__ buf) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {
     PackedKey h;
@@ -52,15 +52,15 @@ __global__ void pack_kernel(const uint32_t* __restrict__ occ, const uint64_t* __
   if (i >= count || i >= cap) return;
   const uint32_t s = occ[i];
   PackedKey p;
-  p.key = keys[s];
-  p.minidx = minidx[s];
+  p.key = slots[s].key;
+  p.minidx = slots[s].minidx;
   p.pad = 0u;
   buf[1 + i] = p;
 }
 
 // insert every gathered pair into the merge table: key -> min over the ranks of the first index
 __global__ void merge_insert_kernel(const PackedKey* __restrict__ buf, const uint32_t* __restrict__ counts, uint32_t maxc,
-                                    int nranks, uint64_t* __restrict__ mkeys, uint32_t* __restrict__ mmin,
+                                    int nranks, KeySlot* __restrict__ mslots,
                                     uint32_t* __restrict__ mocc, uint32_t* __restrict__ mmeta, uint32_t mask,
                                     uint32_t limit) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -71,7 +71,7 @@ __global__ void merge_insert_kernel(const PackedKey* __restrict__ buf, const uin
   uint32_t s = (uint32_t)(mix64s(p.key) >> 20) & mask;
   for (uint32_t probe = 0; probe <= mask; ++probe) {
     const unsigned long long old =
-        atomicCAS(reinterpret_cast<unsigned long long*>(mkeys + s), (unsigned long long)KEY_EMPTY, (unsigned long long)p.key);
+        atomicCAS(reinterpret_cast<unsigned long long*>(&mslots[s].key), (unsigned long long)KEY_EMPTY, (unsigned long long)p.key);
     if (old == KEY_EMPTY) {
       const uint32_t pos = atomicAdd(mmeta, 1u);
       if (pos < limit)
@@ -80,7 +80,7 @@ __global__ void merge_insert_kernel(const PackedKey* __restrict__ buf, const uin
         mmeta[1] = 1u;
     }
     if (old == KEY_EMPTY || old == p.key) {
-      atomicMin(mmin + s, p.minidx);
+      atomicMin(&mslots[s].minidx, p.minidx);
       return;
     }
     s = (s + 1) & mask;
@@ -88,30 +88,29 @@ __global__ void merge_insert_kernel(const PackedKey* __restrict__ buf, const uin
   mmeta[1] = 1u;
 }
 
-__device__ __forceinline__ uint32_t merged_find(const uint64_t* __restrict__ mkeys, uint32_t mask, uint64_t key) {
+__device__ __forceinline__ uint32_t merged_find(const KeySlot* __restrict__ mslots, uint32_t mask, uint64_t key) {
   uint32_t s = (uint32_t)(mix64s(key) >> 20) & mask;
   for (uint32_t probe = 0; probe <= mask; ++probe) {
-    if (mkeys[s] == key) return s;
+    if (mslots[s].key == key) return s;
     s = (s + 1) & mask;
   }
   return 0u;   // unreachable: every local key was inserted
 }
 
 // l2g[local slot + 1] = canonical label of the local key
-__global__ void local_to_global_kernel(const uint32_t* __restrict__ occ, const uint64_t* __restrict__ keys, uint32_t count,
-                                       const uint64_t* __restrict__ mkeys, const uint32_t* __restrict__ mrank,
+__global__ void local_to_global_kernel(const uint32_t* __restrict__ occ, const KeySlot* __restrict__ slots, uint32_t count,
+                                       const KeySlot* __restrict__ mslots, const uint32_t* __restrict__ mrank,
                                        uint32_t mask, uint32_t* __restrict__ l2g) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) l2g[0] = 0u;
   if (i >= count) return;
   const uint32_t s = occ[i];
-  l2g[s + 1] = mrank[merged_find(mkeys, mask, keys[s]) + 1];
+  l2g[s + 1] = mrank[merged_find(mslots, mask, slots[s].key) + 1];
 }
 
 // the identity table every rank ends up with: slot r-1 holds the key / first index of canonical class r
-__global__ void identity_table_kernel(const uint32_t* __restrict__ mocc, const uint64_t* __restrict__ mkeys,
-                                      const uint32_t* __restrict__ mmin, const uint32_t* __restrict__ mrank,
-                                      uint32_t count, uint64_t* __restrict__ keys, uint32_t* __restrict__ minidx,
+__global__ void identity_table_kernel(const uint32_t* __restrict__ mocc, const KeySlot* __restrict__ mslots,
+                                      const uint32_t* __restrict__ mrank, uint32_t count, KeySlot* __restrict__ slots,
                                       uint32_t* __restrict__ occ, uint32_t* __restrict__ rank, uint32_t* __restrict__ meta) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {
@@ -122,8 +121,8 @@ __global__ void identity_table_kernel(const uint32_t* __restrict__ mocc, const u
   if (i >= count) return;
   const uint32_t ms = mocc[i];
   const uint32_t r = mrank[ms + 1];          // 1 .. count
-  keys[r - 1] = mkeys[ms];
-  minidx[r - 1] = mmin[ms];
+  slots[r - 1].key = mslots[ms].key;
+  slots[r - 1].minidx = mslots[ms].minidx;
   occ[r - 1] = r - 1;
   rank[r] = r;
 }
@@ -195,7 +194,7 @@ int sdpsr_shard_merge(sdpsr_ctx* ctx, KeyTable& tloc, uint32_t* lab, int64_t* di
     const size_t rec = (size_t)maxc + 1;
     SDPSR_TRY(sdpsr_scratch_t(ctx, 31, rec * (size_t)G, &buf));
     pack_kernel<<<(std::max<uint32_t>(1u, std::min(tloc.count, maxc)) + 255) / 256, 256, 0, ctx->stream>>>(
-        tloc.occ, tloc.keys, tloc.minidx, tloc.count, maxc, buf + rec * ctx->rank);
+        tloc.occ, tloc.slots, tloc.count, maxc, buf + rec * ctx->rank);
     count_launch(ctx);
     SDPSR_TRY(sdpsr_comm_allgather(ctx, buf, rec * sizeof(PackedKey)));
     SDPSR_CUDA(cudaMemcpy2DAsync(h_hdr, sizeof(PackedKey), buf, rec * sizeof(PackedKey), sizeof(PackedKey), (size_t)G,
@@ -224,12 +223,12 @@ int sdpsr_shard_merge(sdpsr_ctx* ctx, KeyTable& tloc, uint32_t* lab, int64_t* di
   // ---- identical merge on every rank ---------------------------------------------------------------
   const size_t mcap = std::max<size_t>(64, next_pow2(2 * total));
   SDPSR_TRY(sdpsr_table_alloc(ctx, tm_, mcap));
-  SDPSR_CUDA(cudaMemsetAsync(tm_.keys, 0xff, (size_t)tm_.cap * 12, ctx->stream));
+  SDPSR_CUDA(cudaMemsetAsync(tm_.slots, 0xff, (size_t)tm_.cap * sizeof(KeySlot), ctx->stream));
   SDPSR_CUDA(cudaMemsetAsync(tm_.meta, 0, 4 * sizeof(uint32_t), ctx->stream));
   {
     const uint64_t nthreads = (uint64_t)maxc * G;
     merge_insert_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(
-        buf, d_cnt, maxc, G, tm_.keys, tm_.minidx, tm_.occ, tm_.meta, tm_.cap - 1, tm_.cap);
+        buf, d_cnt, maxc, G, tm_.slots, tm_.occ, tm_.meta, tm_.cap - 1, tm_.cap);
     count_launch(ctx);
   }
   uint32_t* hm = reinterpret_cast<uint32_t*>(ctx->h_pinned);
@@ -242,7 +241,7 @@ int sdpsr_shard_merge(sdpsr_ctx* ctx, KeyTable& tloc, uint32_t* lab, int64_t* di
   uint32_t* l2g = nullptr;
   SDPSR_TRY(sdpsr_scratch_t(ctx, 6, (size_t)tloc.cap + 1, &l2g));
   local_to_global_kernel<<<(std::max<uint32_t>(tloc.count, 1) + 255) / 256, 256, 0, ctx->stream>>>(
-      tloc.occ, tloc.keys, tloc.count, tm_.keys, tm_.rank, tm_.cap - 1, l2g);
+      tloc.occ, tloc.slots, tloc.count, tm_.slots, tm_.rank, tm_.cap - 1, l2g);
   count_launch(ctx);
   uint64_t b0, b1;
   sdpsr_shard_block(ctx, ctx->rank, &b0, &b1);
@@ -255,9 +254,9 @@ int sdpsr_shard_merge(sdpsr_ctx* ctx, KeyTable& tloc, uint32_t* lab, int64_t* di
   const size_t need = std::max<size_t>(tloc.cap, next_pow2(2 * (uint64_t)dimg));
   // (l2g was built from tloc by kernels earlier on this stream; a reallocation synchronises by itself)
   SDPSR_TRY(sdpsr_table_alloc(ctx, tloc, need));
-  SDPSR_CUDA(cudaMemsetAsync(tloc.keys, 0xff, (size_t)tloc.cap * 12, ctx->stream));
-  identity_table_kernel<<<(dimg + 255) / 256, 256, 0, ctx->stream>>>(tm_.occ, tm_.keys, tm_.minidx, tm_.rank, dimg, tloc.keys,
-                                                                      tloc.minidx, tloc.occ, tloc.rank, tloc.meta);
+  SDPSR_CUDA(cudaMemsetAsync(tloc.slots, 0xff, (size_t)tloc.cap * sizeof(KeySlot), ctx->stream));
+  identity_table_kernel<<<(dimg + 255) / 256, 256, 0, ctx->stream>>>(tm_.occ, tm_.slots, tm_.rank, dimg, tloc.slots,
+                                                                      tloc.occ, tloc.rank, tloc.meta);
   count_launch(ctx);
   SDPSR_CUDA(cudaGetLastError());
   tloc.count = dimg;
