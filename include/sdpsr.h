@@ -301,6 +301,13 @@ int sdpsr_comm_init_local(sdpsr_ctx* ctx, void* group, int rank);
  * 3: INT8 square on CTA pairs (256 x 256).  out (may be NULL) receives *count (tm, tn) pairs.                  */
 int sdpsr_debug_tile_deal(int kind, int64_t n, int nranks, int rank, int32_t* out, int64_t cap, int64_t* count);
 
+/* Test hook (host-only): the work list of the single-CTA INT8 square kernel for `rank` of `nranks` on `grid` CTAs
+ * (CTA b walks items b, b + grid, ...): whole tiles first, then the tiles of the partly filled last wave cut along K
+ * into equal runs, one per CTA (csrc/gemm_i8.cu, build_schedule).  out (may be NULL) receives 8 int32 per item: tm, tn,
+ * kb0, kb1, slot, part, nparts, sem; info (may be NULL) = {nmain, nslots, nsems, k-blocks per tile}.           */
+int sdpsr_debug_i8_schedule(int64_t n, int nranks, int rank, int grid, int32_t* out, int64_t cap, int64_t* count,
+                            int32_t* info);
+
 #ifdef __cplusplus
 }
 #endif

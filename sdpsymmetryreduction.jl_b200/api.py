@@ -93,7 +93,7 @@ def run_local_ranks(n: int, nranks: int, fn: Callable, *, devices=None, flags: i
     in-process communicator (``sdpsr_comm_init_local``).  ``devices[r]`` is the CUDA device of rank r
     (default: all on device 0 -- the sharded path with G ranks mapped onto one GPU, SURVEY.md section 4;
     with distinct devices it is the single-process multi-GPU mode).  Returns the list of results; the
-    first rank's exception is re-raised after every thread has finished."""
+    root-cause exception is re-raised after every thread has finished."""
     import threading
     devices = list(devices) if devices is not None else [0] * nranks
     group = B.Context.local_group(nranks)
@@ -116,9 +116,16 @@ def run_local_ranks(n: int, nranks: int, fn: Callable, *, devices=None, flags: i
         t.start()
     for t in threads:
         t.join()
-    for e in errors:
-        if e is not None:
-            raise e
+    failed = [(r, e) for r, e in enumerate(errors) if e is not None]
+    if failed:
+        # a rank that fails breaks the communicator and the others then report "a rank did not reach the barrier":
+        # re-raise the root cause (the first error that is not that follow-up), naming every failed rank
+        def follow_up(e):
+            return isinstance(e, B.SdpsrError) and "did not reach the barrier" in str(e)
+        r, e = next(((r, e) for r, e in failed if not follow_up(e)), failed[0])
+        if len(failed) > 1 and hasattr(e, "add_note"):
+            e.add_note("ranks that failed: " + "; ".join(f"rank {q}: {type(x).__name__}: {x}" for q, x in failed))
+        raise e
     return results
 
 

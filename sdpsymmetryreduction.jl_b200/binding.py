@@ -50,6 +50,19 @@ def tile_deal(kind: int, n: int, nranks: int, rank: int):
     return [tuple(int(x) for x in row) for row in out[:cnt.value]]
 
 
+def i8_schedule(n: int, nranks: int, rank: int, grid: int):
+    """The work list of the single-CTA INT8 square for `rank` of `nranks` on `grid` CTAs, straight from the library
+    (host-only test hook): (items, info) with items an int32 array of rows (tm, tn, kb0, kb1, slot, part, nparts, sem)
+    and info = dict(nmain, nslots, nsems, kblocks)."""
+    lib = load_library()
+    cnt = _i64(0)
+    info = np.zeros(4, dtype=np.int32)
+    assert lib.sdpsr_debug_i8_schedule(n, nranks, rank, grid, None, 0, C.byref(cnt), info.ctypes.data) == OK
+    out = np.zeros((max(cnt.value, 1), 8), dtype=np.int32)
+    assert lib.sdpsr_debug_i8_schedule(n, nranks, rank, grid, out.ctypes.data, cnt.value, C.byref(cnt), info.ctypes.data) == OK
+    return out[:cnt.value], dict(nmain=int(info[0]), nslots=int(info[1]), nsems=int(info[2]), kblocks=int(info[3]))
+
+
 class LibraryNotBuilt(RuntimeError):
     pass
 
@@ -94,6 +107,7 @@ _SIGNATURES = {
     "sdpsr_product_round_refine": ([_p, _p, _p, _i64, C.c_double, C.POINTER(_i64)], C.c_int),
     "sdpsr_eig": ([_p, _p, _i64, _p], C.c_int),
     "sdpsr_debug_tile_deal": ([C.c_int, _i64, C.c_int, C.c_int, _p, _i64, C.POINTER(_i64)], C.c_int),
+    "sdpsr_debug_i8_schedule": ([_i64, C.c_int, C.c_int, C.c_int, _p, _i64, C.POINTER(_i64), _p], C.c_int),
     "sdpsr_partition_constraints": ([_p, _p, _p, _i64, C.c_int], C.c_int),
     "sdpsr_block_norms": ([_p, _p, _i64, _p, _i64, _p], C.c_int),
     "sdpsr_irreducible": ([_p, _p, _i64, _p, _i64, _p, C.c_double, _p, C.POINTER(_i64)], C.c_int),

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cmath>
+#include <mutex>
 #include <cstring>
 
 #include "sdpsr_internal.cuh"
@@ -398,11 +399,8 @@ struct SolverApi {
   bool ok = false;
 };
 
-SolverApi& sapi() {
-  static SolverApi a;
-  static bool tried = false;
-  if (tried) return a;
-  tried = true;
+static SolverApi load_solver_api() {
+  SolverApi a;
   std::vector<std::string> names;
   if (const char* e = getenv("SDPSR_CUSOLVER_LIB")) names.push_back(e);
   names.push_back("@loaded");
@@ -449,6 +447,14 @@ SolverApi& sapi() {
     }
     dlclose(h);
   }
+  return a;
+}
+
+// (initialised once, by whichever thread comes first; the others block until the library is in -- in-process ranks
+//  reach their first dense decomposition together, and a `tried` flag set before the load finished handed the late
+//  threads an empty table)
+SolverApi& sapi() {
+  static SolverApi a = load_solver_api();
   return a;
 }
 
@@ -511,6 +517,16 @@ static int fill_into(sdpsr_ctx* ctx, const double* r, int64_t len, double* dst) 
   return SDPSR_OK;
 }
 
+
+// In-process ranks (one host thread each) reach their first dense decomposition at the same moment; handle creation
+// loads the library's kernels and is serialised here (cusolverDnCreate is documented thread-safe, this only removes
+// the concurrent first-use from the picture).
+static cusolverStatus_t solver_create(cusolverDnHandle_t* h) {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  return sapi().Create(h);
+}
+
 extern "C" int sdpsr_eig(sdpsr_ctx* ctx, const double* r1, int64_t len, double* vals) {
   CTX_ENTER();
   SDPSR_REQUIRE(vals != nullptr, SDPSR_E_INVALID, "vals is NULL");
@@ -525,7 +541,7 @@ extern "C" int sdpsr_eig(sdpsr_ctx* ctx, const double* r1, int64_t len, double* 
     Solver* s = new Solver();
     ctx->solver = s;
     SDPSR_REQUIRE(sapi().ok, SDPSR_E_CUSOLVER, "libcusolver.so.11 could not be loaded");
-    SDPSR_REQUIRE(sapi().Create(&s->h) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER, "cusolverDnCreate failed");
+    SDPSR_REQUIRE(solver_create(&s->h) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER, "cusolverDnCreate failed");
     SDPSR_REQUIRE(sapi().SetStream(s->h, ctx->stream) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
                   "cusolverDnSetStream failed");
     SDPSR_REQUIRE(sapi().CreateParams(&s->params) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
@@ -967,7 +983,7 @@ int sdpsr_small_syevd(sdpsr_ctx* ctx, double* dA, int64_t n, int64_t lda, double
     Solver* s = new Solver();
     ctx->solver = s;
     SDPSR_REQUIRE(sapi().ok, SDPSR_E_CUSOLVER, "libcusolver.so.11 could not be loaded");
-    SDPSR_REQUIRE(sapi().Create(&s->h) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER, "cusolverDnCreate failed");
+    SDPSR_REQUIRE(solver_create(&s->h) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER, "cusolverDnCreate failed");
     SDPSR_REQUIRE(sapi().SetStream(s->h, ctx->stream) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
                   "cusolverDnSetStream failed");
     SDPSR_REQUIRE(sapi().CreateParams(&s->params) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
@@ -1240,7 +1256,7 @@ extern "C" int sdpsr_eig_complex(sdpsr_ctx* ctx, const double* r1, int64_t len, 
     Solver* s = new Solver();
     ctx->solver = s;
     SDPSR_REQUIRE(sapi().ok, SDPSR_E_CUSOLVER, "libcusolver.so.11 could not be loaded");
-    SDPSR_REQUIRE(sapi().Create(&s->h) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER, "cusolverDnCreate failed");
+    SDPSR_REQUIRE(solver_create(&s->h) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER, "cusolverDnCreate failed");
     SDPSR_REQUIRE(sapi().SetStream(s->h, ctx->stream) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,
                   "cusolverDnSetStream failed");
     SDPSR_REQUIRE(sapi().CreateParams(&s->params) == CUSOLVER_STATUS_SUCCESS, SDPSR_E_CUSOLVER,

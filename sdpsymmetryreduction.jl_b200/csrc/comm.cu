@@ -41,9 +41,8 @@ struct NcclApi {
   bool ok = false;
 };
 
-NcclApi& api() {
-  static NcclApi a;
-  if (a.lib) return a;
+static NcclApi load_nccl_api() {
+  NcclApi a;
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
   for (const char* nme : names) {
     a.lib = dlopen(nme, RTLD_NOW | RTLD_GLOBAL);
@@ -61,6 +60,11 @@ NcclApi& api() {
   a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.lib, "ncclGroupEnd");
   a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.AllReduce && a.Broadcast &&
          a.GroupStart && a.GroupEnd;
+  return a;
+}
+
+NcclApi& api() {          // thread-safe one-time initialisation
+  static NcclApi a = load_nccl_api();
   return a;
 }
 
@@ -138,7 +142,7 @@ constexpr int NCCL_UINT8 = 1, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_MAX = 2;
 // Tile-column tn (columns [tn*tile_cols, ...)) of the column-major matrix C is owned by rank
 // tn % nranks; it is one contiguous slab.  One grouped launch broadcasts every slab from its owner.
 int sdpsr_comm_exchange_tilecols(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t ncols, int tile_cols,
-                                 int ntilecols) {
+                                 int ntilecols, bool snake) {
   if (ctx->nranks <= 1) return SDPSR_OK;
   Timed tm(ctx, SDPSR_K_MISC, (double)ldc * (double)ncols * 8.0);
   if (ctx->local_group) {
@@ -146,7 +150,7 @@ int sdpsr_comm_exchange_tilecols(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t
     g->posted[ctx->rank] = C;
     SDPSR_TRY(local_barrier(ctx));                 // every owner's slabs are complete and posted
     for (int tn = 0; tn < ntilecols; ++tn) {
-      const int owner = tn % ctx->nranks;
+      const int owner = snake ? sdpsr_tilecol_owner_snake(tn, ctx->nranks) : tn % ctx->nranks;
       if (owner == ctx->rank) continue;
       const int64_t c0 = (int64_t)tn * tile_cols;
       const int64_t w = std::min<int64_t>(tile_cols, ncols - c0);
@@ -160,7 +164,7 @@ int sdpsr_comm_exchange_tilecols(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t
     const int64_t c0 = (int64_t)tn * tile_cols;
     const int64_t w = std::min<int64_t>(tile_cols, ncols - c0);
     double* slab = C + ldc * c0;
-    NCCL_TRY(api().Broadcast(slab, slab, (size_t)(ldc * w), NCCL_FLOAT64, tn % ctx->nranks, (ncclComm_t)ctx->nccl,
+    NCCL_TRY(api().Broadcast(slab, slab, (size_t)(ldc * w), NCCL_FLOAT64, snake ? sdpsr_tilecol_owner_snake(tn, ctx->nranks) : tn % ctx->nranks, (ncclComm_t)ctx->nccl,
                              ctx->stream));
   }
   NCCL_TRY(api().GroupEnd());

@@ -339,10 +339,27 @@ __global__ void __launch_bounds__(256) colmax_labels_kernel(const uint32_t* __re
 // --------------------------------------------------------------------------------------------
 // the square
 // --------------------------------------------------------------------------------------------
+// One unit of work of a CTA: the k-blocks [kb0, kb1) of output tile (tm, tn), all accumulator pairs.  A tile that is
+// covered by ONE item (slot < 0) is folded straight into C.  The tiles of the last, partly filled wave are cut along K
+// into `nparts` items on different CTAs (the tail would otherwise keep most SMs idle for a whole tile time: 4160 tiles
+// on 148 SMs are 28.1 waves, 1040 tiles per rank on four GPUs 7.03): every part stores its raw int32 accumulators
+// into its own scratch slot and takes a ticket on the tile's semaphore; the part that draws the last ticket adds the
+// parts IN INTEGERS and folds in the usual order -- integer addition is exact and commutative, so the result has
+// the same bits as the unsplit schedule whatever the arrival order.
+struct I8Item {
+  int tm, tn;
+  int kb0, kb1;      // kb1 <= kb0: empty item (padding of the per-CTA lists)
+  int slot;          // scratch slot of this part, -1: unsplit tile
+  int part, nparts;
+  int sem;           // semaphore of the tile
+};
+constexpr size_t SPLIT_SLOT_INTS = (size_t)TM * TN;      // per accumulator; a slot holds S of them
+
 __global__ void __launch_bounds__(THREADS, 1)
 square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, double* __restrict__ C,
-                 int64_t ldc, int n, int S, int bits, int segblocks, const int2* __restrict__ tiles, int ntiles, int wexp,
-                 double* const* __restrict__ peers, int npeers, unsigned int* __restrict__ pace, int pace_kb) {
+                 int64_t ldc, int n, int S, int bits, int segblocks, const I8Item* __restrict__ items, int nitems, int nmain,
+                 int wexp, double* const* __restrict__ peers, int npeers, unsigned int* __restrict__ pace, int pace_kb,
+                 int* __restrict__ split_acc, unsigned int* __restrict__ split_sem) {
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const uint32_t bar_full = base + NPAIR * PAIR_BYTES;
@@ -350,13 +367,14 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t bar_tfull = bar_empty + NSLOT * 8;
   const uint32_t bar_tempty = bar_tfull + 8;
   const uint32_t tmem_slot = bar_tempty + 8;
+  const uint32_t ticket_slot = tmem_slot + 8;            // "this CTA drew the last ticket of the tile"
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int KB = (n + TK - 1) / TK;
   // K is cut into segments short enough for the int32 accumulators; every (accumulator pair, segment)
-  // is one MMA phase followed by one fold
-  const int nseg = (KB + segblocks - 1) / segblocks;
+  // is one MMA phase followed by one fold.  (Items in [0, nmain) are whole tiles, dealt in full waves except
+  // possibly the last; only they are paced.)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSLOT; ++s) {
@@ -388,18 +406,20 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t t = 0;
       const int npair = (S + 1) / 2, nsub = (KB + pace_kb - 1) / pace_kb;
       int wave = 0;
-      for (int w = blockIdx.x; w < ntiles; w += gridDim.x, ++wave) {
-        const int2 tile = tiles[w];
-        const int m0 = tile.x * TM, n0 = tile.y * TN;
+      for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++wave) {
+        const I8Item it = items[w];
+        if (it.kb1 <= it.kb0) continue;
+        const int m0 = it.tm * TM, n0 = it.tn * TN;
+        const bool paced = pace != nullptr && w < nmain;
         int pidx = 0;
         for (int c0 = S - 2; c0 >= -1; c0 -= 2, ++pidx) {
           const int nch = c0 + 2;
-          for (int kb = 0; kb < KB; ++kb) {      // (segments are contiguous: the producer just streams on)
-            if (kb % pace_kb == 0) {   // pacing: everyone who works in the previous epoch has issued its loads
+          for (int kb = it.kb0; kb < it.kb1; ++kb) {      // (segments are contiguous: the producer just streams on)
+            if (paced && kb % pace_kb == 0) {   // pacing: everyone who works in the previous epoch has issued its loads
               const int epoch = (wave * npair + pidx) * nsub + kb / pace_kb;
               if (epoch > 0) {
                 const int pw = (epoch - 1) / (npair * nsub);
-                pace_wait(pace, epoch - 1, (unsigned int)min((int)gridDim.x, ntiles - pw * (int)gridDim.x));
+                pace_wait(pace, epoch - 1, (unsigned int)min((int)gridDim.x, nmain - pw * (int)gridDim.x));
               }
             }
             for (int i = 0; i < nch; ++i) {
@@ -418,7 +438,7 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 ++t;
               }
             }
-            if ((kb + 1) % pace_kb == 0 || kb == KB - 1) pace_arrive(pace, (wave * npair + pidx) * nsub + kb / pace_kb);
+            if (paced && ((kb + 1) % pace_kb == 0 || kb == KB - 1)) pace_arrive(pace, (wave * npair + pidx) * nsub + kb / pace_kb);
           }
         }
       }
@@ -429,11 +449,14 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // The whole warp walks the loop (warp-uniform control flow keeps the descriptors in uniform
     // registers); one elected lane issues the tcgen05 instructions.
     uint32_t t = 0, drained = 0;
-    for (int w = blockIdx.x; w < ntiles; w += gridDim.x) {
+    for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
+      const I8Item it = items[w];
+      if (it.kb1 <= it.kb0) continue;
+      const int nseg = (it.kb1 - it.kb0 + segblocks - 1) / segblocks;
       for (int c0 = S - 2; c0 >= -1; c0 -= 2) {
        const int nprod = 2 * c0 + 3;
        for (int seg = 0; seg < nseg; ++seg) {
-        const int kb0 = seg * segblocks, kb1 = min(KB, kb0 + segblocks);
+        const int kb0 = it.kb0 + seg * segblocks, kb1 = min(it.kb1, kb0 + segblocks);
         mbar_wait(bar_tempty, (drained & 1u) ^ 1u);      // the epilogue has read the previous phase
         tc_fence_after();
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -469,10 +492,12 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== epilogue =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     uint32_t done = 0;
-    for (int w = blockIdx.x; w < ntiles; w += gridDim.x) {
-      const int2 tile = tiles[w];
-      const int row = tile.x * TM + q * 32 + lane;
-      const int n0 = tile.y * TN;
+    for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
+      const I8Item it = items[w];
+      if (it.kb1 <= it.kb0) continue;
+      const int nseg = (it.kb1 - it.kb0 + segblocks - 1) / segblocks;
+      const int row = it.tm * TM + q * 32 + lane;
+      const int n0 = it.tn * TN;
       for (int c0 = S - 2; c0 >= -1; c0 -= 2) {
        for (int seg = 0; seg < nseg; ++seg) {
         mbar_wait(bar_tfull, done & 1u);
@@ -482,6 +507,28 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool first = (c0 == S - 2) && seg == 0;
         const bool last = (c0 <= 0) && seg == nseg - 1;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        if (it.slot >= 0) {
+          // one part of a split tile (host guarantees a single segment): raw accumulators to this part's slot,
+          // layout [accumulator][column][row] so that the 32 lanes of a warp store 128 contiguous bytes
+          int* const acc_hi = split_acc + ((size_t)it.slot * S + (size_t)max(c0, 0)) * SPLIT_SLOT_INTS + (q * 32 + lane);
+          int* const acc_lo = split_acc + ((size_t)it.slot * S + (size_t)(c0 + 1)) * SPLIT_SLOT_INTS + (q * 32 + lane);
+#pragma unroll 1
+          for (int ch = 0; ch < TN / 32; ++ch) {
+            uint32_t a0[32], a1[32];
+            tmem_ld32(trow + (uint32_t)(ch * 32), a0);
+            tmem_ld32(trow + (uint32_t)(TN + ch * 32), a1);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              __stcg(acc_lo + (size_t)(ch * 32 + j) * TM, (int)a1[j]);
+              if (c0 >= 0) __stcg(acc_hi + (size_t)(ch * 32 + j) * TM, (int)a0[j]);
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(bar_tempty);
+          ++done;
+          continue;
+        }
 #pragma unroll 1
         for (int ch = 0; ch < TN / 32; ++ch) {
           uint32_t a0[32], a1[32];
@@ -521,6 +568,58 @@ square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_arrive(bar_tempty);
         ++done;
        }
+      }
+      if (it.slot >= 0) {
+        // ticket: the part whose ticket is the last one finishes the tile (the MMA warp is already on the next item)
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 128) {
+          const unsigned int ticket = atomicAdd(split_sem + it.sem, 1u);
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(ticket_slot), "r"(ticket == (unsigned int)(it.nparts - 1) ? 1u : 0u) : "memory");
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint32_t mine;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(mine) : "r"(ticket_slot) : "memory");
+        if (mine) {
+          __threadfence();
+          const int* const acc0 = split_acc + (size_t)(it.slot - it.part) * S * SPLIT_SLOT_INTS + (q * 32 + lane);
+#pragma unroll 1
+          for (int ch = 0; ch < TN / 32; ++ch) {
+            const int64_t off0 = (int64_t)row + ldc * (int64_t)(n0 + ch * 32);
+            const int ncol = row < n ? min(32, n - (n0 + ch * 32)) : 0;
+            double v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.0;
+            for (int c = S - 1; c >= 0; --c) {            // the order of the unsplit fold: smallest weight first
+              const double wc = pow2(wexp - bits * c);
+              int sum[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sum[j] = 0;
+              for (int p = 0; p < it.nparts; ++p) {
+                const int* const src = acc0 + ((size_t)p * S + (size_t)c) * SPLIT_SLOT_INTS + (size_t)(ch * 32) * TM;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum[j] += __ldcg(src + (size_t)j * TM);
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fma(wc, (double)sum[j], v[j]);
+            }
+            if (peers) {
+#pragma unroll 1
+              for (int r = 0; r < npeers; ++r) {
+                double* const pr = peers[r] + off0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncol) pr[ldc * j] = v[j];
+              }
+            } else {
+              double* const p0 = C + off0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncol) __stcg(p0 + ldc * j, v[j]);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");      // the ticket word is reused by the next split item
       }
     }
   }
@@ -815,7 +914,8 @@ void build_tiles(int n, int nranks, int rank, std::vector<int2>& out) {
   out.clear();
   for (int g0 = 0; g0 < tiles_m; g0 += GROUP) {
     const int g1 = std::min(tiles_m, g0 + GROUP);
-    for (int tn = rank; tn < tiles_n; tn += nranks) {    // tile-columns are dealt round-robin to the ranks
+    for (int tn = 0; tn < tiles_n; ++tn) {    // tile-columns are dealt to the ranks in snake order
+      if (sdpsr_tilecol_owner_snake(tn, nranks) != rank) continue;
       // the tile holds entries on or below the diagonal iff its last row >= its first column
       for (int tm = g0; tm < g1; ++tm)
         if ((tm + 1) * TM - 1 >= tn * TN) out.push_back(make_int2(tm, tn));
@@ -830,9 +930,88 @@ void build_tiles_2cta(int n, int nranks, int rank, std::vector<int2>& out) {
   out.clear();
   for (int g0 = 0; g0 < t; g0 += GROUP) {
     const int g1 = std::min(t, g0 + GROUP);
-    for (int tn = rank; tn < t; tn += nranks)
+    for (int tn = 0; tn < t; ++tn) {
+      if (sdpsr_tilecol_owner_snake(tn, nranks) != rank) continue;
       for (int tm = std::max(g0, tn); tm < g1; ++tm) out.push_back(make_int2(tm, tn));
+    }
   }
+}
+
+// The work list of square_i8_kernel: CTA b walks items[b], items[b + grid], ...  Whole tiles in full waves first
+// (`nmain` items, a multiple of `grid` unless nothing is split); then the tail region -- the tiles of the last, partly
+// filled wave, together with the wave before it when more than half a wave is left over -- cut into `grid` equal
+// runs of k-blocks, one run per CTA (a run may cover pieces of two or three tiles: one item each, padded to the same
+// number of items per CTA with empty ones).
+struct I8Schedule {
+  std::vector<I8Item> items;
+  int nmain = 0;
+  int nslots = 0;      // scratch slots (parts of split tiles)
+  int nsems = 0;
+};
+
+void build_schedule(const std::vector<int2>& tiles, int grid, int KB, bool allow_split, I8Schedule& out) {
+  const int ntiles = (int)tiles.size();
+  out = I8Schedule();
+  auto whole = [&](const int2& t) {
+    I8Item it;
+    it.tm = t.x; it.tn = t.y; it.kb0 = 0; it.kb1 = KB; it.slot = -1; it.part = 0; it.nparts = 1; it.sem = 0;
+    return it;
+  };
+  const int full = grid > 0 ? ntiles / grid : 0, r = grid > 0 ? ntiles % grid : 0;
+  if (!allow_split || grid < 2 || r == 0 || full == 0 || KB < 2) {
+    for (const int2& t : tiles) out.items.push_back(whole(t));
+    out.nmain = ntiles;
+    return;
+  }
+  // region: the leftover tiles alone when they fill at most half a wave, else together with the last full wave
+  const int region = (2 * r <= grid || full < 2) ? r : r + grid;
+  out.nmain = ntiles - region;
+  for (int i = 0; i < out.nmain; ++i) out.items.push_back(whole(tiles[(size_t)i]));
+  const int64_t total = (int64_t)region * KB;
+  const int64_t run = (total + grid - 1) / grid;
+  // pieces per CTA
+  std::vector<std::vector<I8Item>> per((size_t)grid);
+  std::vector<int> nparts((size_t)region, 0);
+  for (int b = 0; b < grid; ++b) {
+    const int64_t k0 = std::min<int64_t>(total, (int64_t)b * run), k1 = std::min<int64_t>(total, k0 + run);
+    for (int64_t k = k0; k < k1;) {
+      const int t = (int)(k / KB);
+      const int64_t kend = std::min<int64_t>(k1, (int64_t)(t + 1) * KB);
+      I8Item it;
+      it.tm = tiles[(size_t)(out.nmain + t)].x;
+      it.tn = tiles[(size_t)(out.nmain + t)].y;
+      it.kb0 = (int)(k - (int64_t)t * KB);
+      it.kb1 = (int)(kend - (int64_t)t * KB);
+      it.part = nparts[(size_t)t]++;
+      it.sem = t;
+      it.slot = 0;
+      it.nparts = 0;
+      per[(size_t)b].push_back(it);
+      k = kend;
+    }
+  }
+  std::vector<int> slot0((size_t)region, -1);
+  for (int t = 0; t < region; ++t)
+    if (nparts[(size_t)t] > 1) {
+      slot0[(size_t)t] = out.nslots;
+      out.nslots += nparts[(size_t)t];
+    }
+  out.nsems = region;
+  size_t depth = 0;
+  for (auto& v : per) depth = std::max(depth, v.size());
+  I8Item none;
+  none.tm = none.tn = 0; none.kb0 = none.kb1 = 0; none.slot = -1; none.part = 0; none.nparts = 1; none.sem = 0;
+  for (size_t j = 0; j < depth; ++j)
+    for (int b = 0; b < grid; ++b) {
+      if (j >= per[(size_t)b].size()) {
+        out.items.push_back(none);
+        continue;
+      }
+      I8Item it = per[(size_t)b][j];
+      it.nparts = nparts[(size_t)it.sem];
+      it.slot = it.nparts > 1 ? slot0[(size_t)it.sem] + it.part : -1;
+      out.items.push_back(it);
+    }
 }
 
 // width: bytes per label (4: u32 ids, 1 / 2: compact canonical labels)
@@ -867,6 +1046,35 @@ int sdpsr_tile_deal_i8(int64_t n, int nranks, int rank, int pair, std::vector<in
   if (pair) build_tiles_2cta((int)n, nranks, rank, out);
   else build_tiles((int)n, nranks, rank, out);
   return 0;
+}
+
+/* Test hook (host-only): the work list of the single-CTA INT8 square for `rank` of `nranks` with `grid` CTAs --
+ * whole tiles in full waves, then the tail region cut into equal runs of k-blocks (build_schedule).  out receives 8
+ * int32 per item: tm, tn, kb0, kb1, slot, part, nparts, sem; info = {nmain, nslots, nsems, KB}.                 */
+extern "C" int sdpsr_debug_i8_schedule(int64_t n, int nranks, int rank, int grid, int32_t* out, int64_t cap, int64_t* count,
+                                       int32_t* info) {
+  if (n < 1 || nranks < 1 || rank < 0 || rank >= nranks || grid < 1 || !count) return SDPSR_E_INVALID;
+  std::vector<int2> tiles;
+  build_tiles((int)n, nranks, rank, tiles);
+  I8Schedule sched;
+  const int KB = (int)((n + TK - 1) / TK);
+  build_schedule(tiles, std::max(1, std::min(grid, (int)tiles.size())), KB, true, sched);
+  *count = (int64_t)sched.items.size();
+  if (info) {
+    info[0] = sched.nmain;
+    info[1] = sched.nslots;
+    info[2] = sched.nsems;
+    info[3] = KB;
+  }
+  if (out) {
+    if (cap < *count) return SDPSR_E_INVALID;
+    for (size_t i = 0; i < sched.items.size(); ++i) {
+      const I8Item& it = sched.items[i];
+      const int32_t v[8] = {it.tm, it.tn, it.kb0, it.kb1, it.slot, it.part, it.nparts, it.sem};
+      for (int k = 0; k < 8; ++k) out[8 * i + k] = v[k];
+    }
+  }
+  return SDPSR_OK;
 }
 
 // X2 = X * X for bit-for-bit symmetric X (checked by the caller).  *done = 0 when the values are out of
@@ -1021,9 +1229,34 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits,
   else
     build_tiles((int)n, sharded ? ctx->nranks : 1, sharded ? ctx->rank : 0, tiles);
   int2* d_tiles = nullptr;
-  SDPSR_TRY(sdpsr_scratch_t(ctx, 27, std::max<size_t>(tiles.size(), 1024), &d_tiles));
-  SDPSR_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
-  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));          // `tiles` dies at scope end
+  I8Item* d_items = nullptr;
+  I8Schedule sched;
+  int grid1 = std::max(1, std::min(ctx->sm_count, (int)tiles.size()));
+  int* d_split = nullptr;
+  unsigned int* d_sem = nullptr;
+  if (pair) {
+    SDPSR_TRY(sdpsr_scratch_t(ctx, 27, std::max<size_t>(tiles.size(), 1024), &d_tiles));
+    SDPSR_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    // SDPSR_I8_GRID caps the number of CTAs (tests: small problems then have waves and a tail);
+    // SDPSR_I8_TAIL=0 keeps every tile whole (A/B switch of the split tail)
+    const char* ge = getenv("SDPSR_I8_GRID");
+    if (ge && atoi(ge) > 0) grid1 = std::max(1, std::min(grid1, atoi(ge)));
+    const char* te = getenv("SDPSR_I8_TAIL");
+    const int kb_all = (int)((n + TK - 1) / TK);
+    // (a split part must be a single K segment: the parts are added in int32)
+    const bool allow_split = !(te && atoi(te) == 0) && kb_all <= segblocks;
+    build_schedule(tiles, grid1, kb_all, allow_split, sched);
+    SDPSR_TRY(sdpsr_scratch_t(ctx, 27, std::max<size_t>(sched.items.size() * sizeof(I8Item) / sizeof(int2), 1024), &d_tiles));
+    d_items = reinterpret_cast<I8Item*>(d_tiles);
+    SDPSR_CUDA(cudaMemcpyAsync(d_items, sched.items.data(), sched.items.size() * sizeof(I8Item), cudaMemcpyHostToDevice, ctx->stream));
+    if (sched.nslots > 0) {
+      SDPSR_TRY(sdpsr_scratch_t(ctx, 42, (size_t)sched.nslots * (size_t)S * SPLIT_SLOT_INTS, &d_split));
+      SDPSR_TRY(sdpsr_scratch_t(ctx, 43, (size_t)std::max(sched.nsems, 64), &d_sem));
+      SDPSR_CUDA(cudaMemsetAsync(d_sem, 0, (size_t)sched.nsems * sizeof(unsigned int), ctx->stream));
+    }
+  }
+  SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));          // `tiles` / `sched` die at scope end
   CUtensorMap tmA, tmB;
   SDPSR_TRY(make_slice_map(ctx, &tmA, slices, n, ld, S, TM));
   SDPSR_TRY(make_slice_map(ctx, &tmB, slices, n, ld, S, TN));
@@ -1076,9 +1309,9 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits,
       square_i8_2cta_kernel<<<2 * nclusters, THREADS, SMEM2_BYTES, ctx->stream>>>(tmA, C, ld, (int)n, S, bits, segblocks, d_tiles,
                                                                                  ntiles, 2 * e - 12, peers, ctx->nranks, d_pace, pace_kb);
     } else {
-      const int grid = std::max(1, std::min(ctx->sm_count, ntiles));
-      square_i8_kernel<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, C, ld, (int)n, S, bits, segblocks, d_tiles, ntiles,
-                                                                   2 * e - 12, peers, ctx->nranks, d_pace, pace_kb);
+      square_i8_kernel<<<grid1, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, C, ld, (int)n, S, bits, segblocks, d_items,
+                                                                    (int)sched.items.size(), sched.nmain, 2 * e - 12, peers,
+                                                                    ctx->nranks, d_pace, pace_kb, d_split, d_sem);
     }
     count_launch(ctx);
   }
@@ -1087,7 +1320,7 @@ int sdpsr_square_i8(sdpsr_ctx* ctx, const double* X, double* C, int S, int bits,
     if (peers) {
       SDPSR_TRY(sdpsr_comm_barrier(ctx));      // every rank's tiles have landed in every copy of C
     } else {
-      SDPSR_TRY(sdpsr_comm_exchange_tilecols(ctx, C, ld, n, TN, (int)((n + TN - 1) / TN)));
+      SDPSR_TRY(sdpsr_comm_exchange_tilecols(ctx, C, ld, n, pair ? 256 : TN, (int)((n + (pair ? 256 : TN) - 1) / (pair ? 256 : TN)), /*snake=*/true));
     }
   }
   SDPSR_TRY(sdpsr_mirror_lower(ctx, C, ld, n, ctx->mirror_col0, ctx->mirror_col1));

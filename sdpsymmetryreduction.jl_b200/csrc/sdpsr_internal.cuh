@@ -320,7 +320,15 @@ void sdpsr_module_invalidate_qhat(sdpsr_ctx* ctx);
 
 // comm.cu
 void sdpsr_comm_free(sdpsr_ctx* ctx);
-int sdpsr_comm_exchange_tilecols(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t ncols, int tile_cols, int ntilecols);
+int sdpsr_comm_exchange_tilecols(sdpsr_ctx* ctx, double* C, int64_t ldc, int64_t ncols, int tile_cols, int ntilecols,
+                                 bool snake = false);
+// Owner of tile-column tn of a lower-triangle product.  Column tn holds (tiles_m - c*tn) tiles, so a plain round-robin
+// gives rank 0 the G heaviest columns of every round (576 vs 464 tiles at N = 16384 on 8 ranks); in snake order
+// (0..G-1, G-1..0, ...) the columns of two consecutive rounds pair up to the same weight on every rank.
+static inline int sdpsr_tilecol_owner_snake(int tn, int nranks) {
+  const int q = tn / nranks, p = tn % nranks;
+  return (q & 1) ? nranks - 1 - p : p;
+}
 int sdpsr_comm_bcast(sdpsr_ctx* ctx, void* buf, size_t bytes, int root);
 int sdpsr_comm_allgather(sdpsr_ctx* ctx, void* recv, size_t bytes_per_rank);
 int sdpsr_comm_allgatherv(sdpsr_ctx* ctx, void* base, const size_t* offset, const size_t* bytes);

@@ -41,16 +41,25 @@ I8_TILE_N = 256      # tile columns (UMMA N)
 I8_GROUP = 12        # tile rows walked together, so that the tiles in flight share operand panels
 
 
+def owner_of_tile_column_snake(tn: int, nranks: int) -> int:
+    """Snake deal of the INT8 square (csrc/sdpsr_internal.cuh::sdpsr_tilecol_owner_snake): 0..G-1, G-1..0, ...  Column
+    tn of the lower triangle holds fewer tiles the larger tn is; two consecutive rounds pair up to equal weight."""
+    q, p = divmod(tn, nranks)
+    return nranks - 1 - p if q & 1 else p
+
+
 def owned_tiles_i8(n: int, nranks: int, rank: int):
     """(tm, tn) tiles of the lower triangle this rank computes -- same order as
-    csrc/gemm_i8.cu::build_tiles: 256-column tile-columns dealt round-robin, and a tile is kept when
+    csrc/gemm_i8.cu::build_tiles: 256-column tile-columns dealt in snake order, and a tile is kept when
     it holds at least one entry on or below the diagonal."""
     tiles_m = (n + I8_TILE_M - 1) // I8_TILE_M
     tiles_n = (n + I8_TILE_N - 1) // I8_TILE_N
     out = []
     for g0 in range(0, tiles_m, I8_GROUP):
         g1 = min(tiles_m, g0 + I8_GROUP)
-        for tn in range(rank, tiles_n, nranks):
+        for tn in range(tiles_n):
+            if owner_of_tile_column_snake(tn, nranks) != rank:
+                continue
             for tm in range(g0, g1):
                 if (tm + 1) * I8_TILE_M - 1 >= tn * I8_TILE_N:
                     out.append((tm, tn))

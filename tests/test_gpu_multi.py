@@ -76,6 +76,15 @@ def test_sharded_path_kernel_variants(prob, flags):
         assert all(r[5]["gemm_i8"]["launches"] >= 1 for r in res), "the sharded INT8 square did not run"
 
 
+@pytest.mark.parametrize("grid", [3, 4])
+def test_sharded_int8_square_with_split_tail(grid, monkeypatch):
+    """The K-split tail of the INT8 square under sharding: the part that draws the last ticket stores the finished
+    tile into every rank's X2 (peer stores) -- same partition and blocks as the oracle (N = 1024: 8 x 4 tile grid)."""
+    monkeypatch.setenv("SDPSR_I8_GRID", str(grid))
+    res = _check_on_ranks(pr.hamming(5, 4), 2, B.F_FORCE_I8)
+    assert all(r[5]["gemm_i8"]["launches"] >= 1 for r in res)
+
+
 def test_sharded_dense_eigen_path():
     """blockDiagonalize through syevd: rank 0 factorises, Q is broadcast."""
     _check_on_ranks(pr.hamming(5, 4), 2, 0, eig="syevd")

@@ -536,6 +536,35 @@ def test_int8_square_with_k_segments(n, monkeypatch):
     assert np.max(np.abs(exact_square(X, 7, 8, kseg=128) - ref)) <= 1e-13 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("grid", [2, 3, 5, 7, 11])
+@pytest.mark.parametrize("n", [515, 700, 1100])
+def test_int8_square_split_tail(n, grid, monkeypatch):
+    """The tiles of the last, partly filled wave are cut along K over all CTAs (int32 parts in scratch slots, the
+    part that draws the last ticket adds them and folds): same bits as the unsplit schedule and the host model.
+    SDPSR_I8_GRID caps the number of CTAs so that small problems have waves and a tail; SDPSR_I8_TAIL=0 is the
+    unsplit schedule."""
+    from i8_model import exact_square
+    rng = np.random.default_rng(7 * n + grid)
+    X = _sym_matrix(n, rng, "wide")
+    items, info = B.i8_schedule(n, 1, 0, grid)
+    monkeypatch.setenv("SDPSR_I8_GRID", str(grid))
+    with B.Context(n) as ctx:
+        ctx.set_matrix(B.MAT_X, X)
+        for method, bits, S_ in ((3, 8, 7), (2, 7, 8), (3, 8, 4)):
+            want = exact_square(X, S_, bits)
+            monkeypatch.setenv("SDPSR_I8_TAIL", "1")
+            ctx.square(method, S_)
+            got = ctx.get_matrix(B.MAT_X2)
+            assert np.array_equal(got, want), (n, grid, bits, S_, info)
+            assert np.array_equal(got, got.T)
+            monkeypatch.setenv("SDPSR_I8_TAIL", "0")
+            ctx.square(method, S_)
+            assert np.array_equal(ctx.get_matrix(B.MAT_X2), want)
+    # the parametrisation must really exercise the split path somewhere
+    if (n, grid) in ((700, 5), (1100, 7), (515, 5)):
+        assert info["nslots"] > 0, info
+
+
 @pytest.mark.parametrize("n", [1, 130, 257, 515, 700])
 def test_int8_square_cta_pair_kernel(n, monkeypatch):
     """The cta_group::2 variant (256 x 256 tiles on CTA pairs, default for N > 16384) computes the same

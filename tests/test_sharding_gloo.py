@@ -30,7 +30,7 @@ def test_python_model_equals_the_library_deal(n, nranks):
     seen = set()
     for r in range(nranks):
         for tm, tn in B.tile_deal(3, n, nranks, r):
-            assert (tm, tn) not in seen and tn % nranks == r and tm >= tn
+            assert (tm, tn) not in seen and sh.owner_of_tile_column_snake(tn, nranks) == r and tm >= tn
             seen.add((tm, tn))
     assert len(seen) == t2 * (t2 + 1) // 2
 
@@ -57,11 +57,11 @@ def test_tile_deal_partitions_the_tiles(n, nranks, lower):
 @pytest.mark.parametrize("nranks", [1, 2, 4, 8])
 def test_int8_tile_deal_covers_the_lower_triangle(n, nranks):
     """csrc/gemm_i8.cu::build_tiles: every entry on or below the diagonal lies in exactly one owned tile,
-    the owner of a tile is the owner of its 256-column tile-column, and the deal is balanced."""
+    the owner of a tile is the (snake-order) owner of its 256-column tile-column, and the deal is balanced."""
     seen = {}
     for r in range(nranks):
         for tm, tn in sh.owned_tiles_i8(n, nranks, r):
-            assert (tm, tn) not in seen and tn % nranks == r
+            assert (tm, tn) not in seen and sh.owner_of_tile_column_snake(tn, nranks) == r
             seen[(tm, tn)] = r
     for i, j in [(0, 0), (n - 1, 0), (n - 1, n - 1), (n // 2, n // 3), (min(n - 1, 255), min(n - 1, 255)),
                  (min(n - 1, 256), min(n - 1, 255)), (min(n - 1, 127), min(n - 1, 100))]:
@@ -75,6 +75,54 @@ def test_int8_tile_deal_covers_the_lower_triangle(n, nranks):
     counts = [sum(1 for v in seen.values() if v == r) for r in range(nranks)]
     if tiles_n >= 8 * nranks:
         assert max(counts) <= 1.15 * sum(counts) / nranks + 1
+    if tiles_n % (2 * nranks) == 0:       # whole snake rounds: every rank holds exactly the same number of tiles
+        assert max(counts) == min(counts)
+
+
+@pytest.mark.parametrize("n,nranks,grid", [(16384, 1, 148), (16384, 2, 148), (16384, 4, 148), (16384, 8, 148), (15504, 1, 148),
+                                            (15504, 3, 132), (4096, 1, 148), (2048, 1, 5), (2048, 2, 7), (1000, 1, 3),
+                                            (384, 1, 2), (200, 1, 3), (130, 1, 148)])
+def test_int8_work_list_covers_every_k_block_once(n, nranks, grid):
+    """csrc/gemm_i8.cu::build_schedule (exported as sdpsr_debug_i8_schedule): whole tiles in full waves, then the tail
+    region cut along K.  Every k-block of every owned tile is covered exactly once, the parts of a split tile are
+    numbered 0..nparts-1 with consecutive scratch slots, unsplit tiles carry no slot, no two tiles share a slot or a
+    semaphore, and no CTA carries more than one k-block above the ideal share."""
+    for rank in range(nranks):
+        items, info = B.i8_schedule(n, nranks, rank, grid)
+        tiles = B.tile_deal(2, n, nranks, rank)
+        KB, g = info["kblocks"], min(grid, max(1, len(tiles)))
+        assert KB == -(-n // 128)
+        cover, load = {}, np.zeros(g)
+        for i, row in enumerate(items):
+            tm, tn, k0, k1, slot, part, nparts, sem = (int(x) for x in row)
+            if k1 <= k0:
+                assert i >= info["nmain"]                     # padding only in the tail
+                continue
+            if i < info["nmain"]:
+                assert (k0, k1, slot, nparts) == (0, KB, -1, 1)
+            cover.setdefault((tm, tn), []).append((k0, k1, slot, part, nparts, sem))
+            load[i % g] += k1 - k0
+        assert sorted(cover) == sorted(tiles)
+        slots, sems = set(), {}
+        for t, parts in cover.items():
+            parts.sort()
+            assert parts[0][0] == 0 and parts[-1][1] == KB
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            assert all(p[4] == len(parts) for p in parts)
+            if len(parts) == 1:
+                assert parts[0][2] == -1
+                continue
+            assert sorted(p[3] for p in parts) == list(range(len(parts)))
+            base = {p[2] - p[3] for p in parts}
+            assert len(base) == 1 and min(base) >= 0
+            for p in parts:
+                assert p[2] not in slots and p[2] < info["nslots"]
+                slots.add(p[2])
+            assert len({p[5] for p in parts}) == 1 and parts[0][5] < info["nsems"]
+            assert sems.setdefault(parts[0][5], t) == t
+        assert len(slots) == info["nslots"]
+        if len(tiles) >= g and KB >= 2:
+            assert load.max() <= len(tiles) * KB / g + 1.0001
 
 
 @pytest.mark.parametrize("slices", [2, 3, 4, 5, 6, 7, 8])
