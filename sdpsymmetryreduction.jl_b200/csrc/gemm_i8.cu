@@ -354,6 +354,7 @@ struct I8Item {
   int sem;           // semaphore of the tile
 };
 constexpr size_t SPLIT_SLOT_INTS = (size_t)TM * TN;      // per accumulator; a slot holds S of them
+constexpr int SPLIT_MAX_PARTS = 4;                         // (a run may straddle tiles: up to one more part)
 
 __global__ void __launch_bounds__(THREADS, 1)
 square_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, double* __restrict__ C,
@@ -968,7 +969,10 @@ void build_schedule(const std::vector<int2>& tiles, int grid, int KB, bool allow
   out.nmain = ntiles - region;
   for (int i = 0; i < out.nmain; ++i) out.items.push_back(whole(tiles[(size_t)i]));
   const int64_t total = (int64_t)region * KB;
-  const int64_t run = (total + grid - 1) / grid;
+  // a run is at least a quarter of a tile: the part that finishes a tile re-reads every part's accumulators
+  // (7 x 128 KB each) with the 128 epilogue threads, ~0.05 ms per part -- with 32 parts per tile (4 leftover
+  // tiles on 148 CTAs) that serial tail cost more than the idle wave it replaced (measured on 4 GPUs)
+  const int64_t run = std::max<int64_t>((total + grid - 1) / grid, (KB + SPLIT_MAX_PARTS - 1) / SPLIT_MAX_PARTS);
   // pieces per CTA
   std::vector<std::vector<I8Item>> per((size_t)grid);
   std::vector<int> nparts((size_t)region, 0);
