@@ -98,7 +98,9 @@ def test_numerical_issues_jl():
     Pm = np.load(os.path.join(GOLDEN, "numerical_issues_P.npy"))
     prt = SR.Partition(Pm)                                                # :70
     c = Coeffs(7)
-    N, eps = 200, 1e-7                                                    # 10_000 in the reference (:91)
+    # The reference repeats ONE draw 10_000 times (:72-91); here every trial is a NEW coefficient draw, which is the
+    # stronger statement.  1000 draws by default, SDPSR_ROBUSTNESS_TRIALS=10000 for the reference's count.
+    N, eps = int(os.environ.get("SDPSR_ROBUSTNESS_TRIALS", "1000")), 1e-7
     res = (N, None)
     for it in range(1, N + 1):                                            # try_fail_eigen_decomposition :72-89
         try:

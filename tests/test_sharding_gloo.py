@@ -83,8 +83,8 @@ def test_int8_tile_deal_covers_the_lower_triangle(n, nranks):
                                             (15504, 3, 132), (4096, 1, 148), (2048, 1, 5), (2048, 2, 7), (1000, 1, 3),
                                             (384, 1, 2), (200, 1, 3), (130, 1, 148)])
 def test_int8_work_list_covers_every_k_block_once(n, nranks, grid):
-    """csrc/gemm_i8.cu::build_schedule (exported as sdpsr_debug_i8_schedule): whole tiles in full waves, then the tail
-    region cut along K.  Every k-block of every owned tile is covered exactly once, the parts of a split tile are
+    """csrc/gemm_i8.cu::build_schedule (exported as sdpsr_debug_i8_schedule): whole tiles in full waves, then the tiles
+    of a last wave that is at most half full cut along K.  Every k-block of every owned tile is covered exactly once, the parts of a split tile are
     numbered 0..nparts-1 with consecutive scratch slots, unsplit tiles carry no slot, no two tiles share a slot or a
     semaphore, and no CTA carries more than one k-block above the ideal share."""
     for rank in range(nranks):
@@ -121,8 +121,12 @@ def test_int8_work_list_covers_every_k_block_once(n, nranks, grid):
             assert len({p[5] for p in parts}) == 1 and parts[0][5] < info["nsems"]
             assert sems.setdefault(parts[0][5], t) == t
         assert len(slots) == info["nslots"]
-        if len(tiles) >= g and KB >= 2:          # balanced up to the minimum run of a quarter tile
-            assert load.max() <= max(len(tiles) * KB / g + 1.0001, info["nmain"] / g * KB + -(-KB // 4))
+        r = len(tiles) % g
+        if len(tiles) >= g and KB >= 2 and 0 < 2 * r <= g:      # split: equal runs of at least a quarter tile
+            assert info["nslots"] > 0 and info["nmain"] == len(tiles) - r
+            assert load.max() <= info["nmain"] / g * KB + max(-(-r * KB // g), -(-KB // 4))      # one run on top
+        else:
+            assert info["nslots"] == 0 and info["nmain"] == len(tiles)
         assert max(len(v) for v in cover.values()) <= 5
 
 
