@@ -207,6 +207,8 @@ def job_e2e(S, prob, C_pinned, labels_pinned, seed, ctx=None, eig="auto", fetch=
     P = S.admissible_subspace(C_pinned, A_pin if A_pin is not None else prob.A, prob.b, rand=rand,
                               labels_out=labels_pinned, ctx=ctx, label_dtype=labels_pinned.dtype, fetch_labels=fetch)
     bd = S.blockDiagonalize(P, False, rand=rand, eig=eig)
+    if fetch:
+        _ = P.matrix          # the label matrix has arrived in the caller's buffer (its export overlapped blockDiagonalize)
     if ctx is None:
         P.release()
     return P, bd

@@ -127,6 +127,7 @@ int sdpsr_constraint_patterns(sdpsr_ctx* ctx, int64_t* npatterns);
  * (src/partitions.jl:124); the projection onto the row space is unchanged by that.              */
 int sdpsr_constraint_rank(sdpsr_ctx* ctx, int64_t* rank);
 
+
 /* ------------------------------------------------------------- Partition state
  * The context holds one Partition S (src/partitions.jl:6-9): labels 0..dim.         */
 /* S = empty partition (all labels 0, dim 0).                                         */
@@ -139,6 +140,12 @@ int sdpsr_partition_set_labels(sdpsr_ctx* ctx, const void* labels, int elt_bytes
  * fit elt_bytes (InexactError in the reference; the reference may throw earlier, for an intermediate
  * p1 + p2*(dim+1) of refine! that the engine never forms, src/partitions.jl:62-66).   */
 int sdpsr_partition_get_labels(sdpsr_ctx* ctx, void* labels, int elt_bytes);
+/* sdpsr_partition_get_labels without the wait (the reference hands P.matrix to the caller, src/partitions.jl:84,188):
+ * the canonical labels are produced into a staging buffer of their own and travel to `labels` on the context's copy
+ * stream while later calls (blockDiagonalize) compute; `labels` should be pinned host memory and must stay valid until
+ * sdpsr_partition_labels_wait returns (SDPSR_E_LABEL_OVERFLOW there if a label did not fit elt_bytes).            */
+int sdpsr_partition_get_labels_async(sdpsr_ctx* ctx, void* labels, int elt_bytes);
+int sdpsr_partition_labels_wait(sdpsr_ctx* ctx);
 /* dim(P) (src/partitions.jl:13) */
 int sdpsr_partition_dim(sdpsr_ctx* ctx, int64_t* dim);
 /* number of entries with label 0 */
@@ -159,6 +166,13 @@ int sdpsr_refine_values(sdpsr_ctx* ctx, const double* M, double atol, int do_rou
                         int64_t* dim);
 /* S = refine!(S, Partition(L)) for an integer label matrix L (src/partitions.jl:62-66). */
 int sdpsr_refine_labels(sdpsr_ctx* ctx, const void* labels, int elt_bytes, int64_t* dim);
+
+/* Optional: start the upload of a HOST objective C (vec(C) of admissible_subspace, src/partitions.jl:109-118) on the
+ * context's copy stream so that it overlaps sdpsr_set_constraints_*: stage, set constraints, sdpsr_init_partition with
+ * the same pointer.  Any other call in between drops the staging (init_partition then copies as usual).  No-op for
+ * device-resident C and for sharded contexts.  Returns without waiting; C must stay valid until init_partition.   */
+int sdpsr_stage_objective(sdpsr_ctx* ctx, const double* C);
+
 
 /* ------------------------------------------------- admissible_subspace pieces */
 /* The initial partition of src/partitions.jl:129-146, computed on the device:

@@ -185,6 +185,19 @@ experiment knob: the integer products stay exact, but the random coefficients ar
 """
 square_digits!(c::Ctx, k::Integer) = check(c, ccall((:sdpsr_set_square_slices, LIB), Cint, (Ptr{Cvoid}, Cint), c.h, k))
 
+"""
+    labels_async!(out, P::CuPartition);  wait_labels(P)
+
+Start the export of `P.matrix` into `out` (`Matrix{UInt8|UInt16|UInt32|UInt64}`, N x N; page-locked memory for a real
+overlap) on the context's copy stream and return at once, so that `blockDiagonalize(P)` can run meanwhile;
+`wait_labels(P)` returns once `out` is complete (throws for a label that does not fit, like the reference's
+`InexactError`).
+"""
+labels_async!(out::Matrix{T}, p::CuPartition) where {T<:Union{UInt8,UInt16,UInt32,UInt64}} =
+    GC.@preserve out check(p.ctx, ccall((:sdpsr_partition_get_labels_async, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Cint), p.ctx.h, out, sizeof(T)))
+wait_labels(p::CuPartition) = check(p.ctx, ccall((:sdpsr_partition_labels_wait, LIB), Cint, (Ptr{Cvoid},), p.ctx.h))
+
 "Drop-in with the reference's signature: returns a host Partition{UInt16} (src/partitions.jl:77-85)."
 admissible_subspace_cuda(C, A, b; kw...) = SR.Partition{UInt16}(SR.admissible_subspace(CuPartition, C, A, b; kw...))
 

@@ -145,6 +145,8 @@ class Partition:
     def __init__(self, *args, device: int = 0, _ctx: Optional[B.Context] = None):
         self._ctx = _ctx
         self.device = device
+        self._matrix = None
+        self._arrival = None          # callable that waits for an export still in flight (get_labels_async)
         if len(args) == 2:
             self.nparts = int(args[0])
             self.matrix = None if args[1] is None else np.asarray(args[1])   # None: device-resident only
@@ -160,6 +162,20 @@ class Partition:
                 self.matrix = ctx.get_labels(np.uint32)
         else:
             raise TypeError("Partition(M) or Partition(nparts, matrix)")
+
+    @property
+    def matrix(self):
+        """P.matrix (src/partitions.jl:6-9).  When admissible_subspace started the export on the copy stream, the first
+        access waits for it (and raises OverflowError if a label did not fit the requested type)."""
+        if self._arrival is not None:
+            wait, self._arrival = self._arrival, None
+            wait()
+        return self._matrix
+
+    @matrix.setter
+    def matrix(self, value):
+        self._arrival = None
+        self._matrix = value
 
     @property
     def shape(self):
@@ -189,6 +205,8 @@ class Partition:
 
     def release(self):
         """Give the device state kept alive for follow-up calls back to the context pool."""
+        if self._arrival is not None:
+            _ = self.matrix                       # an export still in flight reads a buffer of this context
         if self._ctx is not None:
             _release_context(self._ctx)
             self._ctx = None
@@ -248,6 +266,11 @@ def admissible_subspace(C, A, b, *, verbose: bool = False, atol: float = RTOL_DE
         ctx = _acquire_context(n, device, flags)
     t0 = time.perf_counter()
     if init_elements is None:
+        if isinstance(Cv, np.ndarray):
+            # one float64 buffer for both calls: the upload of a host C starts now, on the copy stream, and overlaps the
+            # constraint set-up (a no-op for sharded contexts, whose ranks upload a column block each)
+            Cv = np.ascontiguousarray(Cv, dtype=np.float64).reshape(-1)
+            ctx.stage_objective(Cv)
         ctx.set_constraints(A)
         cur = ctx.init_partition(Cv, b, atol, snap_decimals)         # :124-146
     else:
@@ -281,16 +304,31 @@ def admissible_subspace(C, A, b, *, verbose: bool = False, atol: float = RTOL_DE
     if trace is not None:
         trace["iterations"] = it
         trace["t_total"] = time.perf_counter() - t0
+    def overflow(e):
+        if e.code == B.E_LABEL_OVERFLOW:
+            return OverflowError("InexactError: label does not fit " + str(np.dtype(label_dtype)))
+        return e
+
+    arrival = None
     try:
         if not fetch_labels:          # caller keeps the partition on the device
             labels = None
+        elif labels_out is not None and keep_context:
+            # a caller-owned (pinned) buffer: the export runs on the copy stream while the caller goes on to
+            # blockDiagonalize; P.matrix waits for it on first access
+            labels = ctx.get_labels_async(label_dtype, labels_out)
+
+            def arrival(ctx=ctx):
+                try:
+                    ctx.labels_wait()
+                except B.SdpsrError as e:
+                    raise overflow(e) from e
         else:
             labels = ctx.get_labels(label_dtype, out=labels_out)
     except B.SdpsrError as e:
-        if e.code == B.E_LABEL_OVERFLOW:
-            raise OverflowError("InexactError: label does not fit " + str(np.dtype(label_dtype))) from e
-        raise
+        raise overflow(e) from e
     P = Partition(ctx.dim(), labels, device=device, _ctx=ctx if keep_context else None)
+    P._arrival = arrival
     if own and not keep_context:
         _release_context(ctx)
     return P

@@ -108,6 +108,9 @@ _SIGNATURES = {
     "sdpsr_eig": ([_p, _p, _i64, _p], C.c_int),
     "sdpsr_debug_tile_deal": ([C.c_int, _i64, C.c_int, C.c_int, _p, _i64, C.POINTER(_i64)], C.c_int),
     "sdpsr_debug_i8_schedule": ([_i64, C.c_int, C.c_int, C.c_int, _p, _i64, C.POINTER(_i64), _p], C.c_int),
+    "sdpsr_stage_objective": ([_p, _p], C.c_int),
+    "sdpsr_partition_get_labels_async": ([_p, _p, C.c_int], C.c_int),
+    "sdpsr_partition_labels_wait": ([_p], C.c_int),
     "sdpsr_partition_constraints": ([_p, _p, _p, _i64, C.c_int], C.c_int),
     "sdpsr_block_norms": ([_p, _p, _i64, _p, _i64, _p], C.c_int),
     "sdpsr_irreducible": ([_p, _p, _i64, _p, _i64, _p, C.c_double, _p, C.POINTER(_i64)], C.c_int),
@@ -307,6 +310,21 @@ class Context:
             return out
         self._check(self.lib.sdpsr_partition_get_labels(self._h, _ptr(out), dtype.itemsize))
         return out
+
+    def get_labels_async(self, dtype, out):
+        """Start the label export into `out` (pinned host memory for a real overlap) on the copy stream; `labels_wait`
+        returns once it has arrived."""
+        dtype = np.dtype(dtype)
+        self._check(self.lib.sdpsr_partition_get_labels_async(self._h, _ptr(out), dtype.itemsize))
+        return out
+
+    def labels_wait(self):
+        self._check(self.lib.sdpsr_partition_labels_wait(self._h))
+
+    def stage_objective(self, Cvec):
+        """Start the upload of a host objective on the copy stream (overlaps set_constraints); pass the SAME buffer to
+        init_partition next."""
+        self._check(self.lib.sdpsr_stage_objective(self._h, _ptr(Cvec)))
 
     def dim(self) -> int:
         d = _i64(0)

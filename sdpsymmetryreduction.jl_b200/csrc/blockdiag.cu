@@ -499,7 +499,8 @@ void sdpsr_blockdiag_rebind(sdpsr_ctx* ctx) {
 
 #define CTX_ENTER()                 \
   if (!ctx) return SDPSR_E_INVALID; \
-  if (cudaSetDevice(ctx->device) != cudaSuccess) return ctx->fail(SDPSR_E_CUDA, "cudaSetDevice failed")
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return ctx->fail(SDPSR_E_CUDA, "cudaSetDevice failed"); \
+  ++ctx->api_seq
 
 static int finish(sdpsr_ctx* ctx) {
   SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));

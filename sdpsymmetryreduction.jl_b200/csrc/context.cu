@@ -198,6 +198,13 @@ extern "C" int sdpsr_destroy(sdpsr_ctx* ctx) {
   if (!ctx) return SDPSR_OK;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaEventDestroy(ctx->copy_gate);
+    cudaEventDestroy(ctx->staged_ev);
+    cudaEventDestroy(ctx->labels_ev);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
   drain_events(ctx);
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   sdpsr_comm_free(ctx);
@@ -229,7 +236,8 @@ extern "C" int sdpsr_destroy(sdpsr_ctx* ctx) {
 
 #define CTX_ENTER()                                   \
   if (!ctx) return SDPSR_E_INVALID;                   \
-  if (cudaSetDevice(ctx->device) != cudaSuccess) return ctx->fail(SDPSR_E_CUDA, "cudaSetDevice failed")
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return ctx->fail(SDPSR_E_CUDA, "cudaSetDevice failed"); \
+  ++ctx->api_seq
 
 static int finish(sdpsr_ctx* ctx) {
   SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -341,6 +349,106 @@ extern "C" int sdpsr_partition_get_labels(sdpsr_ctx* ctx, void* labels, int elt_
   SDPSR_CUDA(cudaGetLastError());
   SDPSR_CUDA(cudaMemcpyAsync(labels, raw, (size_t)nn * elt_bytes, cudaMemcpyDefault, ctx->stream));
   return finish(ctx);
+}
+
+// ---------------------------------------------------------------------------
+// Transfers on the copy stream (overlap with the kernels of ctx->stream)
+// ---------------------------------------------------------------------------
+int sdpsr_copy_stream(sdpsr_ctx* ctx) {
+  if (ctx->copy_stream) return SDPSR_OK;
+  SDPSR_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  SDPSR_CUDA(cudaEventCreateWithFlags(&ctx->copy_gate, cudaEventDisableTiming));
+  SDPSR_CUDA(cudaEventCreateWithFlags(&ctx->staged_ev, cudaEventDisableTiming));
+  SDPSR_CUDA(cudaEventCreateWithFlags(&ctx->labels_ev, cudaEventDisableTiming));
+  return SDPSR_OK;
+}
+
+/* Start the upload of a HOST objective matrix C into the context (the staging copy sdpsr_init_partition would do
+ * first) so that it overlaps the constraint set-up: stage, sdpsr_set_constraints_*, sdpsr_init_partition(same C).
+ * Any other call in between drops the staging (init_partition then copies as usual).  A no-op for device-resident C
+ * and for sharded contexts (their upload is split across the ranks).  Returns without waiting. */
+extern "C" int sdpsr_stage_objective(sdpsr_ctx* ctx, const double* C) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(C != nullptr, SDPSR_E_INVALID, "C is NULL");
+  if (ctx->staged_src) {                              // an earlier staging that was never consumed
+    SDPSR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->staged_ev, 0));
+    ctx->staged_src = nullptr;
+  }
+  if (ctx->nranks > 1) return SDPSR_OK;
+  cudaPointerAttributes pa;
+  const bool on_device = cudaPointerGetAttributes(&pa, C) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
+  cudaGetLastError();
+  if (on_device) return SDPSR_OK;
+  SDPSR_TRY(sdpsr_copy_stream(ctx));
+  // whatever ctx->stream still does with X comes first
+  SDPSR_CUDA(cudaEventRecord(ctx->copy_gate, ctx->stream));
+  SDPSR_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_gate, 0));
+  if (ctx->ld != ctx->n) SDPSR_CUDA(cudaMemsetAsync(ctx->X, 0, ctx->elems * 8, ctx->copy_stream));
+  SDPSR_CUDA(cudaMemcpy2DAsync(ctx->X, (size_t)ctx->ld * 8, C, (size_t)ctx->n * 8, (size_t)ctx->n * 8, (size_t)ctx->n,
+                               cudaMemcpyDefault, ctx->copy_stream));
+  SDPSR_CUDA(cudaEventRecord(ctx->staged_ev, ctx->copy_stream));
+  ctx->staged_src = C;
+  ctx->staged_seq = ctx->api_seq;
+  ctx->x_valid = false;
+  ctx->x_is_fill = false;
+  return SDPSR_OK;
+}
+
+/* sdpsr_partition_get_labels without the wait: the canonical labels are produced on ctx->stream into a staging
+ * buffer of their own and travel to `labels` (pinned host memory for a real overlap) on the copy stream while later
+ * calls compute; sdpsr_partition_labels_wait returns once they have arrived (and reports SDPSR_E_LABEL_OVERFLOW if a
+ * label did not fit).  `labels` must stay valid until then. */
+extern "C" int sdpsr_partition_get_labels_async(sdpsr_ctx* ctx, void* labels, int elt_bytes) {
+  CTX_ENTER();
+  SDPSR_REQUIRE(labels != nullptr, SDPSR_E_INVALID, "labels is NULL");
+  SDPSR_REQUIRE(elt_bytes == 1 || elt_bytes == 2 || elt_bytes == 4 || elt_bytes == 8, SDPSR_E_INVALID,
+                "elt_bytes must be 1, 2, 4 or 8");
+  const uint64_t maxval = elt_bytes == 1 ? 0xffull : elt_bytes == 2 ? 0xffffull : ~0ull;
+  SDPSR_REQUIRE(elt_bytes == 4 || (uint64_t)ctx->dim <= maxval, SDPSR_E_LABEL_OVERFLOW,
+                "dim(P) does not fit the requested label type (InexactError in the reference)");
+  SDPSR_TRY(sdpsr_copy_stream(ctx));
+  if (ctx->labels_pending) {
+    SDPSR_CUDA(cudaEventSynchronize(ctx->labels_ev));
+    ctx->labels_pending = false;
+  }
+  const int64_t nn = ctx->n * ctx->n;
+  unsigned char* stage = nullptr;
+  SDPSR_TRY(sdpsr_scratch_t(ctx, 44, (size_t)nn * (size_t)elt_bytes, &stage));
+  uint32_t* bad = ctx->d_scalars;
+  uint32_t* h_bad = reinterpret_cast<uint32_t*>(ctx->h_pinned) + 384;
+  SDPSR_CUDA(cudaMemsetAsync(bad, 0, sizeof(uint32_t), ctx->stream));
+  if (elt_bytes == 4) {
+    SDPSR_TRY(sdpsr_canonical_labels(ctx, reinterpret_cast<uint32_t*>(stage)));
+  } else {
+    SDPSR_TRY(sdpsr_ensure_tmp_labels(ctx));
+    SDPSR_TRY(sdpsr_canonical_labels(ctx, ctx->labels_tmp));
+    const int grid = (int)std::min<int64_t>((nn + 255) / 256, (int64_t)ctx->sm_count * 8);
+    switch (elt_bytes) {
+      case 1: labels_out_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(ctx->labels_tmp, (uint8_t*)stage, nn, maxval, bad); break;
+      case 2: labels_out_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(ctx->labels_tmp, (uint16_t*)stage, nn, maxval, bad); break;
+      default: labels_out_kernel<uint64_t><<<grid, 256, 0, ctx->stream>>>(ctx->labels_tmp, (uint64_t*)stage, nn, maxval, bad); break;
+    }
+    count_launch(ctx);
+    SDPSR_CUDA(cudaGetLastError());
+  }
+  // (the flag leaves on ctx->stream: d_scalars is reused by the calls that follow)
+  SDPSR_CUDA(cudaMemcpyAsync(h_bad, bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  SDPSR_CUDA(cudaEventRecord(ctx->copy_gate, ctx->stream));
+  SDPSR_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_gate, 0));
+  SDPSR_CUDA(cudaMemcpyAsync(labels, stage, (size_t)nn * elt_bytes, cudaMemcpyDefault, ctx->copy_stream));
+  SDPSR_CUDA(cudaEventRecord(ctx->labels_ev, ctx->copy_stream));
+  ctx->labels_pending = true;
+  return SDPSR_OK;
+}
+
+extern "C" int sdpsr_partition_labels_wait(sdpsr_ctx* ctx) {
+  CTX_ENTER();
+  if (!ctx->labels_pending) return SDPSR_OK;
+  SDPSR_CUDA(cudaEventSynchronize(ctx->labels_ev));
+  ctx->labels_pending = false;
+  const uint32_t* h_bad = reinterpret_cast<const uint32_t*>(ctx->h_pinned) + 384;
+  SDPSR_REQUIRE(*h_bad == 0u, SDPSR_E_LABEL_OVERFLOW, "a label does not fit the requested integer width");
+  return SDPSR_OK;
 }
 
 extern "C" int sdpsr_partition_dim(sdpsr_ctx* ctx, int64_t* dim) {

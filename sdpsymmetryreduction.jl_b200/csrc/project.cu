@@ -789,7 +789,8 @@ int sdpsr_constraints_finalize(sdpsr_ctx* ctx) {
 
 #define CTX_ENTER()                 \
   if (!ctx) return SDPSR_E_INVALID; \
-  if (cudaSetDevice(ctx->device) != cudaSuccess) return ctx->fail(SDPSR_E_CUDA, "cudaSetDevice failed")
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return ctx->fail(SDPSR_E_CUDA, "cudaSetDevice failed"); \
+  ++ctx->api_seq
 
 static int finish(sdpsr_ctx* ctx) {
   SDPSR_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -835,6 +836,7 @@ static int set_constraints_csr_impl(sdpsr_ctx* ctx, int64_t m, const int64_t* ro
 extern "C" int sdpsr_set_constraints_csr(sdpsr_ctx* ctx, int64_t m, const int64_t* rowptr, const int64_t* colidx,
                                          const double* vals, int index_base) {
   CTX_ENTER();
+  if (ctx->staged_src) ctx->staged_seq = ctx->api_seq;      // a staged objective survives the constraint set-up
   SDPSR_TRY(set_constraints_csr_impl<int64_t>(ctx, m, rowptr, colidx, vals, index_base));
   return finish(ctx);
 }
@@ -842,12 +844,14 @@ extern "C" int sdpsr_set_constraints_csr(sdpsr_ctx* ctx, int64_t m, const int64_
 extern "C" int sdpsr_set_constraints_csr_i32(sdpsr_ctx* ctx, int64_t m, const int64_t* rowptr, const int32_t* colidx,
                                              const double* vals, int index_base) {
   CTX_ENTER();
+  if (ctx->staged_src) ctx->staged_seq = ctx->api_seq;      // a staged objective survives the constraint set-up
   SDPSR_TRY(set_constraints_csr_impl<int32_t>(ctx, m, rowptr, colidx, vals, index_base));
   return finish(ctx);
 }
 
 extern "C" int sdpsr_set_constraints_dense(sdpsr_ctx* ctx, int64_t m, const double* A) {
   CTX_ENTER();
+  if (ctx->staged_src) ctx->staged_seq = ctx->api_seq;      // a staged objective survives the constraint set-up
   SDPSR_REQUIRE(m >= 1 && A, SDPSR_E_INVALID, "bad dense constraint arguments");
   sdpsr_constraints_free(ctx);
   ConstraintSet& c = ctx->cons;
@@ -877,6 +881,7 @@ extern "C" int sdpsr_set_constraints_dense(sdpsr_ctx* ctx, int64_t m, const doub
 extern "C" int sdpsr_set_constraints_csc(sdpsr_ctx* ctx, int64_t m, const int64_t* colptr, const int64_t* rowval,
                                          const double* nzval, int index_base) {
   CTX_ENTER();
+  if (ctx->staged_src) ctx->staged_seq = ctx->api_seq;      // a staged objective survives the constraint set-up
   SDPSR_REQUIRE(m >= 1 && colptr && (index_base == 0 || index_base == 1), SDPSR_E_INVALID, "bad CSC arguments");
   sdpsr_constraints_free(ctx);
   ConstraintSet& c = ctx->cons;
@@ -1017,12 +1022,21 @@ extern "C" int sdpsr_init_partition(sdpsr_ctx* ctx, const double* C, const doubl
     cudaGetLastError();
     int split = (!on_device && ctx->nranks > 1) ? 1 : 0;
     if (ctx->nranks > 1) SDPSR_TRY(sdpsr_comm_agree_min(ctx, &split));     // a branch with a collective
+    // a staged upload of this very matrix (sdpsr_stage_objective) with nothing but constraint set-up since
+    bool staged = false;
+    if (ctx->staged_src) {
+      SDPSR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->staged_ev, 0));     // (also when it is dropped: X is ours again)
+      staged = ctx->staged_src == C && ctx->staged_seq + 1 == ctx->api_seq && !on_device && !split;
+      ctx->staged_src = nullptr;
+    }
     if (on_device && ctx->ld == ctx->n && ((uintptr_t)C % 16 == 0)) {
       Csrc = C;
     } else {
-      if (ctx->ld != ctx->n) SDPSR_CUDA(cudaMemsetAsync(ctx->X, 0, ctx->elems * 8, ctx->stream));
+      if (ctx->ld != ctx->n && !staged) SDPSR_CUDA(cudaMemsetAsync(ctx->X, 0, ctx->elems * 8, ctx->stream));
       Timed tm(ctx, SDPSR_K_MISC, (double)ctx->elems * 16.0);              // staging copy (or the H2D upload)
-      if (split) {
+      if (staged) {
+        // sdpsr_stage_objective already moved this matrix into X on the copy stream
+      } else if (split) {
         const int64_t b0 = ctx->n * ctx->rank / ctx->nranks, b1 = ctx->n * (ctx->rank + 1) / ctx->nranks;
         if (b1 > b0)
           SDPSR_CUDA(cudaMemcpy2DAsync(ctx->X + b0 * ctx->ld, (size_t)ctx->ld * 8, C + b0 * ctx->n, (size_t)ctx->n * 8,

@@ -176,6 +176,16 @@ struct sdpsr_ctx {
 
   uint32_t* d_scalars = nullptr;   // small device scratch (64 words)
   void* h_pinned = nullptr;        // small pinned host scratch (4 KB)
+  // copy stream (sdpsr_stage_objective, sdpsr_partition_get_labels_async): host <-> device transfers that overlap
+  // the kernels of ctx->stream
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_gate = nullptr;       // recorded on ctx->stream: the copy may start
+  cudaEvent_t staged_ev = nullptr;       // recorded on the copy stream: C has arrived in X
+  cudaEvent_t labels_ev = nullptr;       // recorded on the copy stream: the labels have arrived on the host
+  const double* staged_src = nullptr;    // host matrix whose upload into X is in flight / done
+  uint64_t staged_seq = 0;               // api_seq at which the staging is still valid
+  uint64_t api_seq = 0;                  // C-ABI calls entered so far
+  bool labels_pending = false;
 
   ConstraintSet cons;
 

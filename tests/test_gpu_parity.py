@@ -259,6 +259,72 @@ def test_dense_and_sparse_constraints_agree():
         assert ctx.init_partition(prob.C, prob.b, ATOL) == 2
 
 
+def test_staged_objective_upload():
+    """sdpsr_stage_objective starts the upload of a host C on the copy stream (it overlaps the constraint set-up);
+    init_partition consumes it only for the same buffer with nothing but set_constraints in between, and copies as
+    usual otherwise -- the partition is the same in every case."""
+    prob = pr.qap_esc16j(os.path.join(GOLDEN, "esc16j.npz"))
+    Cv = np.ascontiguousarray(np.asarray(prob.C, dtype=np.float64).reshape(-1))
+    junk = np.random.default_rng(1).random(Cv.size)
+    with B.Context(prob.n) as ctx:
+        ctx.set_constraints(prob.A)
+        want_d = ctx.init_partition(Cv, prob.b, ATOL)
+        want = ctx.get_labels()
+    assert want_d == 150
+
+    def run(steps):
+        with B.Context(prob.n) as ctx:
+            for st in steps:
+                st(ctx)
+            d = ctx.init_partition(Cv, prob.b, ATOL)
+            return d, ctx.get_labels()
+
+    cases = {
+        "staged": [lambda c: c.stage_objective(Cv), lambda c: c.set_constraints(prob.A)],
+        "staged after the constraints": [lambda c: c.set_constraints(prob.A), lambda c: c.stage_objective(Cv)],
+        "another buffer staged": [lambda c: c.stage_objective(junk), lambda c: c.set_constraints(prob.A)],
+        "dropped by a call in between": [lambda c: c.stage_objective(junk), lambda c: c.set_constraints(prob.A),
+                                         lambda c: c.dim()],
+        "staged twice": [lambda c: c.stage_objective(junk), lambda c: c.stage_objective(Cv),
+                         lambda c: c.set_constraints(prob.A)],
+    }
+    for name, steps in cases.items():
+        d, lab = run(steps)
+        assert d == want_d and np.array_equal(lab, want), name
+
+
+def test_async_label_export():
+    """With a caller-owned label buffer admissible_subspace starts the export on the copy stream and returns;
+    blockDiagonalize runs without the host copy, P.matrix waits for it on first access."""
+    prob = pr.lovasz_er(5)
+    Po = O.admissible_subspace(*prob, Coeffs(7))
+    so, bo = O.blockDiagonalize(Po, Coeffs(8))
+    out = np.zeros((prob.n, prob.n), dtype=np.uint16, order="F")
+    P = S.admissible_subspace(*prob, rand=Coeffs(7), labels_out=out, label_dtype=np.uint16)
+    assert P._arrival is not None
+    bd = S.blockDiagonalize(P, False, rand=Coeffs(8))
+    assert P._arrival is not None                      # nothing on that path needed the host copy
+    M = P.matrix
+    assert P._arrival is None and np.shares_memory(M, out)
+    assert np.array_equal(M, Po.matrix) and list(bd.blkSizes) == list(so)
+    P.release()
+    # a second export while one is pending, and release() with one pending, are both safe
+    out2 = np.zeros((prob.n, prob.n), dtype=np.uint32, order="F")
+    P2 = S.admissible_subspace(*prob, rand=Coeffs(7), labels_out=out2, label_dtype=np.uint32)
+    P2._ctx.get_labels_async(np.uint16, out)
+    P2.release()
+    assert np.array_equal(out2, Po.matrix) and np.array_equal(out, Po.matrix)
+    # a label type that cannot hold dim(P) is refused before anything is started
+    rng = np.random.default_rng(3)
+    Mbig = rng.integers(1, 400, size=(40, 40))
+    with B.Context(40) as ctx:
+        assert ctx.set_labels(Mbig.astype(np.int64)) > 255
+        with pytest.raises(B.SdpsrError) as ei:
+            ctx.get_labels_async(np.uint8, np.zeros((40, 40), dtype=np.uint8, order="F"))
+        assert ei.value.code == B.E_LABEL_OVERFLOW
+        ctx.labels_wait()                                # nothing pending: a no-op
+
+
 def test_uint16_default_label_type():
     prob = pr.lovasz_er(3)
     P = S.admissible_subspace(*prob, rand=Coeffs(2), label_dtype=np.uint16, keep_context=False)
