@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import logging
 import math
+import os
 import time
 from collections import namedtuple
 from typing import Callable, List, Optional
@@ -127,6 +128,10 @@ def run_local_ranks(n: int, nranks: int, fn: Callable, *, devices=None, flags: i
             e.add_note("ranks that failed: " + "; ".join(f"rank {q}: {type(x).__name__}: {x}" for q, x in failed))
         raise e
     return results
+
+
+# SDPSR_COPY_STREAM=0: host transfers on the compute stream, as before the copy stream existed (A/B switch)
+_COPY_STREAM = os.environ.get("SDPSR_COPY_STREAM", "1") != "0"
 
 
 def _default_rand():
@@ -266,7 +271,7 @@ def admissible_subspace(C, A, b, *, verbose: bool = False, atol: float = RTOL_DE
         ctx = _acquire_context(n, device, flags)
     t0 = time.perf_counter()
     if init_elements is None:
-        if isinstance(Cv, np.ndarray):
+        if isinstance(Cv, np.ndarray) and _COPY_STREAM:
             # one float64 buffer for both calls: the upload of a host C starts now, on the copy stream, and overlaps the
             # constraint set-up (a no-op for sharded contexts, whose ranks upload a column block each)
             Cv = np.ascontiguousarray(Cv, dtype=np.float64).reshape(-1)
@@ -313,7 +318,7 @@ def admissible_subspace(C, A, b, *, verbose: bool = False, atol: float = RTOL_DE
     try:
         if not fetch_labels:          # caller keeps the partition on the device
             labels = None
-        elif labels_out is not None and keep_context:
+        elif labels_out is not None and keep_context and _COPY_STREAM:
             # a caller-owned (pinned) buffer: the export runs on the copy stream while the caller goes on to
             # blockDiagonalize; P.matrix waits for it on first access
             labels = ctx.get_labels_async(label_dtype, labels_out)

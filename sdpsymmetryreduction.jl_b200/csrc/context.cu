@@ -354,6 +354,51 @@ extern "C" int sdpsr_partition_get_labels(sdpsr_ctx* ctx, void* labels, int elt_
 // ---------------------------------------------------------------------------
 // Transfers on the copy stream (overlap with the kernels of ctx->stream)
 // ---------------------------------------------------------------------------
+// The large host transfers are done by a KERNEL (zero-copy loads / stores over PCIe, a few CTAs) rather than by the
+// copy engines: a DMA engine serves the streams in submission order, so a 2 GB cudaMemcpyAsync on the copy stream
+// made every small cudaMemcpyAsync of the compute stream (index arrays, counters, flags: every call has some) wait
+// for it -- measured: no overlap at all.  Needs page-locked (mapped) host memory; anything else takes cudaMemcpyAsync.
+__global__ void __launch_bounds__(256) pcie_copy_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n16; i += 4 * stride) {          // four independent 16-byte requests per thread in flight
+    const uint4 a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
+    dst[i] = a;
+    dst[i + stride] = b;
+    dst[i + 2 * stride] = c;
+    dst[i + 3 * stride] = d;
+  }
+  for (; i < n16; i += stride) dst[i] = src[i];
+}
+
+// true when `host` is page-locked memory the device can address directly (cudaHostAlloc / cudaHostRegister)
+static bool device_can_address(const void* host, void** dev) {
+  cudaPointerAttributes pa;
+  if (cudaPointerGetAttributes(&pa, host) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (pa.type != cudaMemoryTypeHost || pa.devicePointer == nullptr) return false;
+  *dev = pa.devicePointer;
+  return true;
+}
+
+// bytes % 16 == 0 and both pointers 16-byte aligned, else cudaMemcpyAsync
+static int big_copy(sdpsr_ctx* ctx, void* dst, const void* src, size_t bytes, bool to_host) {
+  void* mapped = nullptr;
+  const void* host = to_host ? dst : src;
+  if (bytes % 16 == 0 && ((uintptr_t)dst % 16 == 0) && ((uintptr_t)src % 16 == 0) && device_can_address(host, &mapped)) {
+    uint4* d = reinterpret_cast<uint4*>(to_host ? mapped : dst);
+    const uint4* s = reinterpret_cast<const uint4*>(to_host ? src : mapped);
+    pcie_copy_kernel<<<32, 256, 0, ctx->copy_stream>>>(d, s, bytes / 16);
+    count_launch(ctx);
+    SDPSR_CUDA(cudaGetLastError());
+    return SDPSR_OK;
+  }
+  SDPSR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->copy_stream));
+  return SDPSR_OK;
+}
+
 int sdpsr_copy_stream(sdpsr_ctx* ctx) {
   if (ctx->copy_stream) return SDPSR_OK;
   SDPSR_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -383,9 +428,13 @@ extern "C" int sdpsr_stage_objective(sdpsr_ctx* ctx, const double* C) {
   // whatever ctx->stream still does with X comes first
   SDPSR_CUDA(cudaEventRecord(ctx->copy_gate, ctx->stream));
   SDPSR_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_gate, 0));
-  if (ctx->ld != ctx->n) SDPSR_CUDA(cudaMemsetAsync(ctx->X, 0, ctx->elems * 8, ctx->copy_stream));
-  SDPSR_CUDA(cudaMemcpy2DAsync(ctx->X, (size_t)ctx->ld * 8, C, (size_t)ctx->n * 8, (size_t)ctx->n * 8, (size_t)ctx->n,
-                               cudaMemcpyDefault, ctx->copy_stream));
+  if (ctx->ld != ctx->n) {
+    SDPSR_CUDA(cudaMemsetAsync(ctx->X, 0, ctx->elems * 8, ctx->copy_stream));
+    SDPSR_CUDA(cudaMemcpy2DAsync(ctx->X, (size_t)ctx->ld * 8, C, (size_t)ctx->n * 8, (size_t)ctx->n * 8, (size_t)ctx->n,
+                                 cudaMemcpyDefault, ctx->copy_stream));
+  } else {
+    SDPSR_TRY(big_copy(ctx, ctx->X, C, (size_t)ctx->n * (size_t)ctx->n * 8, /*to_host=*/false));
+  }
   SDPSR_CUDA(cudaEventRecord(ctx->staged_ev, ctx->copy_stream));
   ctx->staged_src = C;
   ctx->staged_seq = ctx->api_seq;
@@ -435,7 +484,7 @@ extern "C" int sdpsr_partition_get_labels_async(sdpsr_ctx* ctx, void* labels, in
   SDPSR_CUDA(cudaMemcpyAsync(h_bad, bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   SDPSR_CUDA(cudaEventRecord(ctx->copy_gate, ctx->stream));
   SDPSR_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_gate, 0));
-  SDPSR_CUDA(cudaMemcpyAsync(labels, stage, (size_t)nn * elt_bytes, cudaMemcpyDefault, ctx->copy_stream));
+  SDPSR_TRY(big_copy(ctx, labels, stage, (size_t)nn * elt_bytes, /*to_host=*/true));
   SDPSR_CUDA(cudaEventRecord(ctx->labels_ev, ctx->copy_stream));
   ctx->labels_pending = true;
   return SDPSR_OK;
