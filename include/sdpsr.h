@@ -170,7 +170,8 @@ int sdpsr_refine_labels(sdpsr_ctx* ctx, const void* labels, int elt_bytes, int64
 /* Optional: start the upload of a HOST objective C (vec(C) of admissible_subspace, src/partitions.jl:109-118) on the
  * context's copy stream so that it overlaps sdpsr_set_constraints_*: stage, set constraints, sdpsr_init_partition with
  * the same pointer.  Any other call in between drops the staging (init_partition then copies as usual).  No-op for
- * device-resident C and for sharded contexts.  Returns without waiting; C must stay valid until init_partition.   */
+ * device-resident C; a sharded context stages its own column block.  Returns without waiting; C must stay valid
+ * until init_partition.                                                                                          */
 int sdpsr_stage_objective(sdpsr_ctx* ctx, const double* C);
 
 

@@ -273,7 +273,7 @@ def admissible_subspace(C, A, b, *, verbose: bool = False, atol: float = RTOL_DE
     if init_elements is None:
         if isinstance(Cv, np.ndarray) and _COPY_STREAM:
             # one float64 buffer for both calls: the upload of a host C starts now, on the copy stream, and overlaps the
-            # constraint set-up (a no-op for sharded contexts, whose ranks upload a column block each)
+            # constraint set-up (a sharded context stages its own column block)
             Cv = np.ascontiguousarray(Cv, dtype=np.float64).reshape(-1)
             ctx.stage_objective(Cv)
         ctx.set_constraints(A)

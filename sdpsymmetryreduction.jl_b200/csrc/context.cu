@@ -410,8 +410,8 @@ int sdpsr_copy_stream(sdpsr_ctx* ctx) {
 
 /* Start the upload of a HOST objective matrix C into the context (the staging copy sdpsr_init_partition would do
  * first) so that it overlaps the constraint set-up: stage, sdpsr_set_constraints_*, sdpsr_init_partition(same C).
- * Any other call in between drops the staging (init_partition then copies as usual).  A no-op for device-resident C
- * and for sharded contexts (their upload is split across the ranks).  Returns without waiting. */
+ * Any other call in between drops the staging (init_partition then copies as usual).  A no-op for device-resident C.
+ * A sharded context stages its own column block only.  Returns without waiting. */
 extern "C" int sdpsr_stage_objective(sdpsr_ctx* ctx, const double* C) {
   CTX_ENTER();
   SDPSR_REQUIRE(C != nullptr, SDPSR_E_INVALID, "C is NULL");
@@ -419,16 +419,21 @@ extern "C" int sdpsr_stage_objective(sdpsr_ctx* ctx, const double* C) {
     SDPSR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->staged_ev, 0));
     ctx->staged_src = nullptr;
   }
-  if (ctx->nranks > 1) return SDPSR_OK;
   cudaPointerAttributes pa;
   const bool on_device = cudaPointerGetAttributes(&pa, C) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
   cudaGetLastError();
   if (on_device) return SDPSR_OK;
+  if (ctx->nranks > 1 && ctx->ld != ctx->n) return SDPSR_OK;
   SDPSR_TRY(sdpsr_copy_stream(ctx));
   // whatever ctx->stream still does with X comes first
   SDPSR_CUDA(cudaEventRecord(ctx->copy_gate, ctx->stream));
   SDPSR_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_gate, 0));
-  if (ctx->ld != ctx->n) {
+  if (ctx->nranks > 1) {
+    // sharded: this rank's column block only (init_partition all-gathers the blocks over NVLink)
+    const int64_t b0 = ctx->n * ctx->rank / ctx->nranks, b1 = ctx->n * (ctx->rank + 1) / ctx->nranks;
+    if (b1 > b0)
+      SDPSR_TRY(big_copy(ctx, ctx->X + b0 * ctx->ld, C + b0 * ctx->n, (size_t)(b1 - b0) * (size_t)ctx->n * 8, /*to_host=*/false));
+  } else if (ctx->ld != ctx->n) {
     SDPSR_CUDA(cudaMemsetAsync(ctx->X, 0, ctx->elems * 8, ctx->copy_stream));
     SDPSR_CUDA(cudaMemcpy2DAsync(ctx->X, (size_t)ctx->ld * 8, C, (size_t)ctx->n * 8, (size_t)ctx->n * 8, (size_t)ctx->n,
                                  cudaMemcpyDefault, ctx->copy_stream));

@@ -1026,7 +1026,8 @@ extern "C" int sdpsr_init_partition(sdpsr_ctx* ctx, const double* C, const doubl
     bool staged = false;
     if (ctx->staged_src) {
       SDPSR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->staged_ev, 0));     // (also when it is dropped: X is ours again)
-      staged = ctx->staged_src == C && ctx->staged_seq + 1 == ctx->api_seq && !on_device && !split;
+      staged = ctx->staged_src == C && ctx->staged_seq + 1 == ctx->api_seq && !on_device &&
+               (ctx->nranks > 1) == (split != 0);
       ctx->staged_src = nullptr;
     }
     if (on_device && ctx->ld == ctx->n && ((uintptr_t)C % 16 == 0)) {
@@ -1034,11 +1035,11 @@ extern "C" int sdpsr_init_partition(sdpsr_ctx* ctx, const double* C, const doubl
     } else {
       if (ctx->ld != ctx->n && !staged) SDPSR_CUDA(cudaMemsetAsync(ctx->X, 0, ctx->elems * 8, ctx->stream));
       Timed tm(ctx, SDPSR_K_MISC, (double)ctx->elems * 16.0);              // staging copy (or the H2D upload)
-      if (staged) {
+      if (staged && !split) {
         // sdpsr_stage_objective already moved this matrix into X on the copy stream
       } else if (split) {
         const int64_t b0 = ctx->n * ctx->rank / ctx->nranks, b1 = ctx->n * (ctx->rank + 1) / ctx->nranks;
-        if (b1 > b0)
+        if (b1 > b0 && !staged)          // (staged: this rank's block is already in place)
           SDPSR_CUDA(cudaMemcpy2DAsync(ctx->X + b0 * ctx->ld, (size_t)ctx->ld * 8, C + b0 * ctx->n, (size_t)ctx->n * 8,
                                        (size_t)ctx->n * 8, (size_t)(b1 - b0), cudaMemcpyDefault, ctx->stream));
         size_t off[sdpsr_ctx::MAX_RANKS], len[sdpsr_ctx::MAX_RANKS];
