@@ -38,6 +38,10 @@
 // A second kernel runs the same schedule on CTA pairs (cta_group::2, 256 x 256 tiles); it is the default
 // for N > 16384 (see square_i8_2cta_kernel below and DESIGN.md 5b).  tests/i8_model.py is the host model
 // both kernels are held to, bit for bit.
+// Scheduling (round 2): the TMA producers of a launch are PACED through epoch counters in global
+// memory so that the CTAs of a wave stay inside one L2 working set (pace_arrive / pace_wait); the tiles of a last
+// wave that is at most half full are cut along K over all CTAs, int32 parts being added exactly by whichever part
+// finishes last (I8Item, build_schedule); across ranks the tile-columns are dealt in snake order.
 #include <cuda.h>
 
 #include <algorithm>
