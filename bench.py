@@ -685,7 +685,11 @@ def main():
                    "max_block_err": parity_err},
         "step_ms": {"min": min(per_step_ms), "max": max(per_step_ms)},
         "e2e": {"value": sec_e2e, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "labels": "UInt16 (the reference's default label type, src/partitions.jl:84)"},
+                "labels": "UInt16 (the reference's default label type, src/partitions.jl:84)",
+                "transfers": "inside the timed region, from / to page-locked host buffers: C uploaded on the context's "
+                             "copy stream while the constraints are set up, the label matrix exported while "
+                             "blockDiagonalize runs and waited for before the step ends (SDPSR_COPY_STREAM=0: both on "
+                             "the compute stream)"},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": None,

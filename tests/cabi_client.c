@@ -216,6 +216,17 @@ int main(int argc, char** argv) {
   CHECK(sdpsr_partition_dim(ctx, &d));
   uint32_t* labels = (uint32_t*)malloc((size_t)(n * n) * 4);
   CHECK(sdpsr_partition_get_labels(ctx, labels, 4));
+  /* the same export without the wait (copy stream; pageable memory here, so it degrades to a plain copy) and
+   * as the reference's default UInt16 */
+  uint16_t* labels16 = (uint16_t*)malloc((size_t)(n * n) * 2);
+  CHECK(sdpsr_partition_get_labels_async(ctx, labels16, 2));
+  CHECK(sdpsr_partition_labels_wait(ctx));
+  for (int64_t i = 0; i < n * n; ++i)
+    if ((uint32_t)labels16[i] != labels[i]) {
+      fprintf(stderr, "asynchronous label export differs at %lld\n", (long long)i);
+      return 1;
+    }
+  free(labels16);
 
   /* ---- blockDiagonalize(P): module path first, dense path with the SAME draws when it does not apply -- */
   double* r1 = next_coeffs(d);

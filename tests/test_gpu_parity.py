@@ -325,6 +325,26 @@ def test_async_label_export():
         ctx.labels_wait()                                # nothing pending: a no-op
 
 
+def test_copy_stream_with_page_locked_buffers():
+    """Page-locked host buffers take the kernel-driven transfers (pcie_copy_kernel: zero-copy loads of C, zero-copy
+    stores of the labels); pageable ones take cudaMemcpyAsync.  Same partition either way."""
+    torch = pytest.importorskip("torch")
+    prob = pr.hamming(5, 3, sparse=True)                       # N = 243 (ld = 256 != N: staged through the 2-D copy)
+    prob2 = pr.hamming(4, 4, sparse=True)                      # N = 256 (ld == N: the kernel path)
+    for q in (prob, prob2):
+        Po = O.admissible_subspace(*q, Coeffs(5))
+        Cpin = torch.from_numpy(np.ascontiguousarray(np.asarray(q.C, dtype=np.float64).reshape(-1))).pin_memory()
+        Lpin = torch.zeros(q.n * q.n, dtype=torch.int16).pin_memory()
+        out = Lpin.numpy().view(np.uint16).reshape(q.n, q.n, order="F")
+        P = S.admissible_subspace(Cpin.numpy(), q.A, q.b, rand=Coeffs(5), labels_out=out, label_dtype=np.uint16)
+        assert P._arrival is not None
+        bd = S.blockDiagonalize(P, False, rand=Coeffs(6))
+        assert np.array_equal(P.matrix, Po.matrix) and np.shares_memory(P.matrix, out)
+        so, _ = O.blockDiagonalize(Po, Coeffs(6))
+        assert list(bd.blkSizes) == list(so)
+        P.release()
+
+
 def test_uint16_default_label_type():
     prob = pr.lovasz_er(3)
     P = S.admissible_subspace(*prob, rand=Coeffs(2), label_dtype=np.uint16, keep_context=False)
